@@ -1,0 +1,148 @@
+"""Generate golden traces from the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+
+The reference has no tests or golden vectors of its own, so these traces —
+recorded by importing /root/reference behind oracle/refshim and driving
+CookingEnvironment.accumulated_step / get_feature_vector directly — are the
+pins for oracle/cz_oracle.py and for the CUDA path.  /root/reference does not exist on the
+GPU box; the .npz files travel instead.
+
+Each file holds `n` traces of one configuration:
+    config   JSON: level, meta_file, num_agents, max_steps, recipes, end_all, reward_scheme
+    layouts  JSON list: describe_layout() of every trace's initial world
+    actions  i8 [n,T,A]      teleport i8 [n,T,A,2] (-1 = none; applied before the step)
+    length   i32[n]          number of valid steps (trace stops at terminated/truncated)
+    agents i16[n,T+1,A,6]  objs i16[n,T+1,D,9]  statics i16[n,T+1,S,4]  marks i32[n,T+1,R]
+    reward f64[n,T,A]  term u8[n,T,A]  trunc u8[n,T,A]  rel u8[n,T,A]  obs f64[n,T+1,A,L]
+index 0 along the T+1 axis is the state right after reset().
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.ref_harness import RefEnv  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+# Scripted single-agent solve of TomatoLettuceSalad on the coop_test layout of seed 3
+# (SURVEY.md Appendix E16).  Moves are (dx,dy)->action: 1 left, 2 right, 3 down, 4 up.
+
+
+def record(cfg, seeds, T, policy, teleports=None):
+    traces = []
+    for seed in seeds:
+        env = RefEnv(seed, cfg["level"], cfg["meta_file"], cfg["num_agents"], cfg["max_steps"],
+                     cfg["recipes"], end_condition_all_dishes=cfg["end_all"],
+                     reward_scheme=cfg.get("reward_scheme"))
+        A = cfg["num_agents"]
+        rng = np.random.default_rng(1000 + seed)
+        tr = {"layout": env.layout(), "actions": np.zeros((T, A), np.int8),
+              "teleport": -np.ones((T, A, 2), np.int8)}
+        st = env.export_state()
+        keys = ("agents", "objs", "statics", "marks")
+        hist = {k: [st[k]] for k in keys}
+        obs = [env.observe_all()]
+        rew, term, trunc, rel = [], [], [], []
+        length = T
+        prev = np.zeros(A, np.int64)
+        for t in range(T):
+            if teleports is not None and t in teleports:
+                for i, (x, y) in teleports[t].items():
+                    env.teleport(i, x, y)
+                    tr["teleport"][t, i] = (x, y)
+            act = policy(rng, t, A, prev)
+            prev = act
+            tr["actions"][t] = act
+            r, te, tu, re_ = env.step(act)
+            rew.append(r); term.append(te); trunc.append(tu); rel.append(re_)
+            st = env.export_state()
+            for k in keys:
+                hist[k].append(st[k])
+            obs.append(env.observe_all())
+            if te.any() or tu.any():
+                length = t + 1
+                break
+        tr["length"] = length
+        for k in keys:
+            tr[k] = np.stack(hist[k])
+        tr["obs"] = np.stack(obs)
+        tr["reward"] = np.stack(rew); tr["term"] = np.stack(term)
+        tr["trunc"] = np.stack(trunc); tr["rel"] = np.stack(rel)
+        traces.append(tr)
+    return traces
+
+
+def save(name, cfg, traces, T):
+    n = len(traces)
+
+    def pad(key, axis_len):
+        first = traces[0][key]
+        out = np.zeros((n, axis_len) + first.shape[1:], first.dtype)
+        for i, tr in enumerate(traces):
+            out[i, :tr[key].shape[0]] = tr[key]
+        return out
+
+    arrays = {
+        "config": np.array(json.dumps(cfg)),
+        "layouts": np.array(json.dumps([tr["layout"] for tr in traces])),
+        "actions": np.stack([tr["actions"] for tr in traces]),
+        "teleport": np.stack([tr["teleport"] for tr in traces]),
+        "length": np.array([tr["length"] for tr in traces], np.int32),
+    }
+    for k in ("agents", "objs", "statics", "marks", "obs"):
+        arrays[k] = pad(k, T + 1)
+    for k in ("reward", "term", "trunc", "rel"):
+        arrays[k] = pad(k, T)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {n} traces, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def uniform(rng, t, A, prev):
+    return rng.integers(0, 5, size=A)
+
+
+def sticky(rng, t, A, prev):
+    """repeat the previous action w.p. 0.5: more bumping into appliances, deeper states"""
+    new = rng.integers(0, 5, size=A)
+    keep = rng.random(A) < 0.5
+    return np.where(keep & (t > 0), prev, new)
+
+
+def scripted(seq):
+    def pol(rng, t, A, prev):
+        return np.array(seq[t] if t < len(seq) else [0] * A)
+    return pol
+
+
+def main():
+    base = {"level": "coop_test", "meta_file": "example", "max_steps": 400, "reward_scheme": None}
+    # BASELINE config 1: single agent, TomatoLettuceSalad
+    cfg1 = dict(base, num_agents=1, recipes=["TomatoLettuceSalad"], end_all=False)
+    save("cfg1_uniform", cfg1, record(cfg1, range(4), 400, uniform), 400)
+    # BASELINE config 2: two agents, two recipes, all dishes
+    cfg2 = dict(base, num_agents=2, recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True)
+    save("cfg2_uniform", cfg2, record(cfg2, range(12), 400, uniform), 400)
+    save("cfg2_sticky", cfg2, record(cfg2, range(100, 112), 400, sticky), 400)
+    # short max_steps: truncation path
+    cfg3 = dict(cfg2, max_steps=25)
+    save("cfg2_trunc25", cfg3, record(cfg3, range(200, 204), 25, sticky), 25)
+    # non-default reward scheme with float terms and node rewards
+    cfg4 = dict(cfg2, reward_scheme={"recipe_reward": 12.5, "max_time_penalty": -3.3,
+                                     "recipe_penalty": -7.25, "recipe_node_reward": 1.1})
+    save("cfg2_rewardscheme", cfg4, record(cfg4, range(300, 304), 400, sticky), 400)
+    # every recipe of the book once (BASELINE config 4 draws per-env recipe pairs from it)
+    book = ["TomatoSalad", "TomatoLettuceSalad", "CarrotBanana", "MashedCarrotBanana",
+            "CucumberOnion", "AppleWatermelon", "TomatoLettuceOnionSalad", "no_recipe"]
+    for k in range(0, 8, 2):
+        cfg = dict(base, num_agents=2, recipes=book[k:k + 2], end_all=False, max_steps=200)
+        save(f"book_{k}", cfg, record(cfg, range(400 + k, 402 + k), 200, sticky), 200)
+
+
+if __name__ == "__main__":
+    main()

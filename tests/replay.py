@@ -1,0 +1,42 @@
+"""Shared lockstep-replay helpers: golden trace / live env  vs  an env under test."""
+import glob
+import json
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STATE_KEYS = ("agents", "objs", "statics", "marks")
+
+
+def golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(path):
+    z = np.load(path)
+    g = {k: z[k] for k in z.files}
+    g["config"] = json.loads(str(g["config"]))
+    g["layouts"] = json.loads(str(g["layouts"]))
+    return g
+
+
+def bits(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64)).view(np.uint64)
+
+
+def assert_state_equal(want, got, ctx):
+    for k in STATE_KEYS:
+        w, g = np.asarray(want[k]), np.asarray(got[k])
+        if not np.array_equal(w, g):
+            bad = np.argwhere(w != g)
+            raise AssertionError(f"{ctx}: state[{k}] differs at {bad[:8].tolist()}\nwant={w[tuple(bad[0][:-1])] if w.ndim > 1 else w}\n"
+                                 f"got ={g[tuple(bad[0][:-1])] if g.ndim > 1 else g}")
+
+
+def assert_obs_equal(want, got, ctx):
+    wb, gb = bits(want), bits(got)
+    if not np.array_equal(wb, gb):
+        bad = np.argwhere(wb != gb)
+        i = tuple(bad[0])
+        raise AssertionError(f"{ctx}: obs differs at {bad[:8].tolist()} want {np.asarray(want)[i]!r} got {np.asarray(got)[i]!r}")
