@@ -1,0 +1,211 @@
+"""BatchedCookingEnv — the batched entry point over N CookingZoo environments on one B200.
+
+Keeps the reference constructor's arguments (cooking_zoo/environment/cooking_env.py:62-64:
+level, meta_file, num_agents, max_steps, recipes, obs_spaces, end_condition_all_dishes,
+action_scheme, reward_scheme, agent_respawn_rate, grace_period, agent_despawn_rate) and its
+step/reset semantics, with every per-environment quantity becoming a leading batch axis.
+This file is thin host code: tensors are torch-owned device memory, the work happens in
+libcz_b200.so (include/cz_b200.h) on torch's current CUDA stream.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native
+from .tables import compile_tables, NUM_MISC, ROW_SBITS, ROW_TINFO, ROW_MARKS, ROW_VARIANT
+
+
+class BatchedCookingEnv:
+    def __init__(self, num_envs, level, meta_file, num_agents, max_steps, recipes, agent_visualization=None,
+                 obs_spaces=None, end_condition_all_dishes=False, action_scheme="scheme3", render=False,
+                 reward_scheme=None, agent_respawn_rate=0.0, grace_period=20, agent_despawn_rate=0.0, *,
+                 device="cuda:0", recipe_pool=None, layout_pool_size=256, layout_seed=0, layouts=None,
+                 auto_reset=False, seed=0, env_offset=0):
+        obs_spaces = obs_spaces or ["feature_vector"] * num_agents
+        if any(o != "feature_vector" for o in obs_spaces):
+            raise NotImplementedError("the batched entry point builds feature_vector observations only "
+                                      "(symbolic/full are host object graphs in the reference)")
+        if action_scheme != "scheme3":
+            raise NotImplementedError("only action_scheme='scheme3' is compiled (scheme1 is next; scheme2 "
+                                      "raises AttributeError in the reference itself)")
+        if render:
+            raise NotImplementedError("rendering is out of scope")
+        if agent_respawn_rate != 0.0 or agent_despawn_rate != 0.0:
+            raise NotImplementedError("agent despawn/respawn needs host-supplied uniforms (not built yet)")
+        self.lib = _native.load_library()       # raises when the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise _native.NativeError("BatchedCookingEnv needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device(device)
+        self.num_envs, self.num_agents = int(num_envs), int(num_agents)
+        self.possible_agents = ["player_" + str(r) for r in range(num_agents)]   # cooking_env.py:76
+        self.tables = compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_scheme,
+                                     end_condition_all_dishes, grace_period, agent_respawn_rate,
+                                     agent_despawn_rate, recipe_pool, layout_pool_size, layout_seed, layouts)
+        t = self.tables
+        self.obs_len, self.max_steps = t.obs_len, t.max_steps
+        self.auto_reset, self.seed, self.env_offset = bool(auto_reset), int(seed), int(env_offset)
+        desc, self._keep = _native.make_desc(t)
+        handle = C.c_void_p()
+        _native.check(self.lib.cz_tables_create(C.byref(desc), self.device.index or 0, C.byref(handle)))
+        self._handle = handle
+        N, A, L = self.num_envs, self.num_agents, self.obs_len
+        dev = self.device
+        self.state = torch.zeros((t.rows, N), dtype=torch.int32, device=dev)
+        self.obs = torch.zeros((N, A, L), dtype=torch.float64, device=dev)
+        self.reward = torch.zeros((N, A), dtype=torch.float64, device=dev)
+        self.terminated = torch.zeros((N, A), dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros((N, A), dtype=torch.uint8, device=dev)
+        self.error_flags = torch.zeros((N,), dtype=torch.int32, device=dev)
+        self._actions = torch.zeros((N, A), dtype=torch.uint8, device=dev)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self.lib.cz_tables_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ API
+    def reset(self, layout_ids=None, recipe_ids=None, mask=None):
+        """reset(layout_ids[N]) -> obs[N, A, L] float64 (cooking_env.py:178-210).
+
+        layout_ids index the compiled layout pool (default: cz_layout_draw(seed, env, 0) % P);
+        recipe_ids [N, R] index tables.recipe_names; mask selects the environments to reset."""
+        N = self.num_envs
+        if layout_ids is None:
+            layout_ids = self.default_layout_ids(episode=0)
+        lid = torch.as_tensor(layout_ids, dtype=torch.int32).to(self.device).contiguous()
+        if lid.shape != (N,):
+            raise ValueError("layout_ids must have shape [num_envs]")
+        if int(lid.min()) < 0 or int(lid.max()) >= self.tables.num_layouts:
+            raise ValueError("layout id out of range")
+        rid = mk = None
+        if recipe_ids is not None:
+            rid = torch.as_tensor(recipe_ids, dtype=torch.uint8).to(self.device).contiguous()
+            if rid.shape != (N, self.tables.num_recipes) or int(rid.max()) >= len(self.tables.recipe_names):
+                raise ValueError("recipe_ids must be [num_envs, R] indices into tables.recipe_names")
+        if mask is not None:
+            mk = torch.as_tensor(mask).to(torch.uint8).to(self.device).contiguous()
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.cz_reset(self._handle, self.state.data_ptr(), lid.data_ptr(),
+                                            rid.data_ptr() if rid is not None else None,
+                                            mk.data_ptr() if mk is not None else None,
+                                            self.obs.data_ptr(), N, self._stream()))
+        return self.obs
+
+    def step(self, actions):
+        """step(actions[N, A]) -> (obs f64[N,A,L], reward f64[N,A], terminated u8[N,A], truncated u8[N,A], info)
+        (cooking_env.py:243-288).  Outputs are views of buffers that the next step overwrites."""
+        a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
+        if a.shape != (self.num_envs, self.num_agents):
+            raise ValueError("actions must have shape [num_envs, num_agents]")
+        if a.dtype != torch.uint8 or a.device != self.device or not a.is_contiguous():
+            self._actions.copy_(a)
+            a = self._actions
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.cz_step(self._handle, self.state.data_ptr(), a.data_ptr(), self.obs.data_ptr(),
+                                           self.reward.data_ptr(), self.terminated.data_ptr(),
+                                           self.truncated.data_ptr(), self.error_flags.data_ptr(), self.num_envs,
+                                           _native.STEP_AUTO_RESET if self.auto_reset else 0,
+                                           self.seed, self.env_offset, self._stream()))
+        return self.obs, self.reward, self.terminated, self.truncated, self.info()
+
+    def observe(self):
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.cz_observe(self._handle, self.state.data_ptr(), self.obs.data_ptr(),
+                                              self.num_envs, self._stream()))
+        return self.obs
+
+    def info(self):
+        """Lazy views of the info tensors: t[N], recipe_done[N, R], active[N, A]."""
+        t = self.tables
+        misc = self.state[t.num_dyn_slots + t.num_agents:]
+        agents = self.state[t.num_dyn_slots:t.num_dyn_slots + t.num_agents]
+        return {"t": misc[ROW_TINFO] & 0xFFFFF,
+                "recipe_done": torch.stack([(misc[ROW_MARKS] >> (8 * r)) & 1 for r in range(t.num_recipes)], 1),
+                "active": ((agents >> 15) & 1).T,
+                "error_flags": self.error_flags}
+
+    def default_layout_ids(self, episode=0):
+        P = self.tables.num_layouts
+        return np.array([self.lib.cz_layout_draw(self.seed, self.env_offset + e, episode) % P
+                         for e in range(self.num_envs)], np.int32)
+
+    # ------------------------------------------------------------------ state import/export
+    def export_state(self, env=None):
+        """Canonical arrays per environment (same convention as oracle/ref_dump.dump_state)."""
+        t = self.tables
+        st = self.state.cpu().numpy().astype(np.uint32)
+        D, A, W = t.num_dyn_slots, t.num_agents, t.width
+        envs = range(self.num_envs) if env is None else [env]
+        out = []
+        for e in envs:
+            o = st[:D, e]
+            objs = np.zeros((D, 9), np.int16)
+            pres = (o >> 6) & 1
+            ck = (o >> 10) & 3
+            cid = (o >> 12) & 31
+            x, y = o & 7, (o >> 3) & 7
+            objs[:, 0] = pres
+            objs[:, 1], objs[:, 2] = x, y
+            objs[:, 3] = (o >> 7) & 1
+            objs[:, 4] = ((o >> 8) & 1) * 2
+            objs[:, 5] = (o >> 9) & 1
+            objs[:, 6] = ck
+            objs[:, 7] = np.where(ck == 1, y * W + x, cid)
+            objs[:, 8] = (o >> 17) & 63
+            objs[pres == 0] = 0
+            a = st[D:D + A, e]
+            agents = np.zeros((A, 6), np.int16)
+            agents[:, 0], agents[:, 1], agents[:, 2] = a & 7, (a >> 3) & 7, (a >> 6) & 7
+            agents[:, 3] = np.where((a >> 9) & 1, (a >> 10) & 31, -1)
+            agents[:, 4], agents[:, 5] = (a >> 15) & 1, a >> 16
+            misc = st[D + A:, e]
+            sb, var = int(misc[ROW_SBITS]), int(misc[ROW_VARIANT])
+            statics = np.zeros((t.num_static_slots, 4), np.int16)
+            for s in range(t.num_static_slots):
+                cell = int(t.static_cells[var, s])
+                if cell == 0xFF:
+                    continue
+                g = int(t.grid[var, cell])
+                kind, sp = g & 15, g >> 4
+                bits = 0
+                if kind == 3 and sb >> sp & 1:
+                    bits |= 1
+                if kind == 4:
+                    bits |= (sb >> (4 + sp) & 1) | (sb >> (8 + sp) & 1) << 1
+                if kind == 6:
+                    bits |= (sb >> (12 + sp) & 1) << 2 | 8
+                if kind == 7:
+                    bits |= (sb >> (16 + sp) & 1) << 3
+                statics[s] = (1, cell & 7, cell >> 3, bits)
+            marks = np.array([(int(misc[ROW_MARKS]) >> (8 * r)) & 255 for r in range(t.num_recipes)], np.int32)
+            out.append({"agents": agents, "objs": objs, "statics": statics, "marks": marks,
+                        "t": np.int32(int(misc[ROW_TINFO]) & 0xFFFFF)})
+        return out if env is None else out[0]
+
+    def teleport(self, env, agent, x, y):
+        """Agent.move_to (world_objects.py:794-797) on one environment — test helper."""
+        t = self.tables
+        D = t.num_dyn_slots
+        col = self.state[:, env].cpu().numpy().astype(np.uint32)
+        rec = int(col[D + agent])
+        xy = x | y << 3
+        col[D + agent] = (rec & ~63) | xy
+        if rec >> 9 & 1:
+            h = (rec >> 10) & 31
+            col[h] = (int(col[h]) & ~63) | xy
+            for s in range(D):
+                r = int(col[s])
+                if r >> 6 & 1 and (r >> 10) & 3 == 2 and (r >> 12) & 31 == h:
+                    col[s] = (r & ~63) | xy
+        self.state[:, env] = torch.from_numpy(col.astype(np.int32)).to(self.device)

@@ -1,0 +1,483 @@
+// cz_device.cuh — device-side data model and per-environment dynamics (sm_100a).
+//
+// One LANE owns one environment during the dynamics phase (scalar, table-driven code over a
+// shared-memory column of packed object records); the WARP then cooperates on the
+// observation rows of its 32 environments.  Citations: /root/reference/cooking_zoo/...
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/cz_b200.h"
+
+// ---- device copy of the compiled tables (passed to kernels by value) ------------------
+struct CzDev {
+  int W, H, A, R, D, S, T, n_obs_slots, L, V, P, B, max_steps, end_all, grace, n_switches, n_blocks, rows;
+  double r_node, r_recipe, r_penalty, r_time, respawn, despawn;
+  const double* xlut;
+  const double* ylut;
+  const uint8_t* grid;
+  const uint8_t* static_cells;
+  const uint8_t* scan_order;
+  const uint8_t* special_cells;
+  const uint64_t* static_masks;
+  const uint8_t* slot_type;
+  const uint8_t* type_flags;
+  const uint8_t* type_base;
+  const uint8_t* type_count;
+  const uint32_t* obs_slots;
+  const uint32_t* recipe_nodes;
+  const uint8_t* recipe_len;
+  const uint32_t* pool;
+  const uint8_t* default_recipes;
+};
+
+// static kinds (grid low nibble) — cooking_zoo_b200/entities.py ST_*
+enum { ST_NONE = 0, ST_FLOOR, ST_COUNTER, ST_CUTBOARD, ST_BLENDER, ST_DELIVER, ST_SWITCH, ST_BLOCK };
+// dynamic type flags
+enum { TF_PLATE = 1, TF_CHOP = 2, TF_BLEND = 4, TF_SPAWN = 8 };
+// feature layouts
+enum { FV_NONE = 0, FV_ONE, FV_CHOP, FV_CHOPBLEND, FV_AGENT, FV_SWITCH, FV_BLOCK };
+
+// ---- packed records (cz_b200.h) ----------------------------------------------------------
+#define O_XY(r) ((r) & 63u)
+#define O_PRESENT 64u
+#define O_CHOP 128u
+#define O_MASH 256u
+#define O_FREE 512u
+#define O_CK(r) (((r) >> 10) & 3u)
+#define O_CID(r) (((r) >> 12) & 31u)
+#define O_POS(r) (((r) >> 17) & 63u)
+#define O_WITH_XY(r, xy) (((r) & ~63u) | (xy))
+#define O_WITH_CONT(r, k, id, pos) (((r) & 0x3FFu) | ((uint32_t)(k) << 10) | ((uint32_t)(id) << 12) | ((uint32_t)(pos) << 17))
+#define CK_HELD 0u
+#define CK_STATIC 1u
+#define CK_PLATE 2u
+
+#define A_XY(r) ((r) & 63u)
+#define A_ORI(r) (((r) >> 6) & 7u)
+#define A_HAS(r) (((r) >> 9) & 1u)
+#define A_HOLD(r) (((r) >> 10) & 31u)
+#define A_ACTIVE(r) (((r) >> 15) & 1u)
+#define A_GRACE(r) ((r) >> 16)
+
+#define SB_CUT_READY(k) (1u << (k))
+#define SB_BL_READY(k) (1u << (4 + (k)))
+#define SB_BL_TOGGLE(k) (1u << (8 + (k)))
+#define SB_SW_ACTIVE(k) (1u << (12 + (k)))
+#define SB_BLK_WALK(k) (1u << (16 + (k)))
+
+#define TI_T(x) ((x) & 0xFFFFFu)
+#define TI_DONE (1u << 20)
+#define TI_NLIVE(x) (((x) >> 21) & 7u)
+
+#define OSTRIDE 33  // shared-memory column stride (words): lane-per-env and lane-per-slot are both conflict-free
+
+// Per-lane view of one environment.  Object records live in a shared-memory column.
+struct EnvRegs {
+  uint32_t* o;   // &sobj[lane]; dynamic slot s at o[s * OSTRIDE]
+  uint32_t* ag;  // &sag[lane];  agent i at ag[i * OSTRIDE]
+  uint32_t sbits, tinfo, marks, variant, rids, episode, err;
+};
+
+__device__ __forceinline__ uint64_t cz_mix(uint64_t seed, uint64_t env, uint64_t episode) {
+  // splitmix64 finaliser over a counter built from (seed, env, episode)
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (env + 1) + 0xD1B54A32D192ED03ull * (episode + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ bool cz_walkable(const CzDev& T, const EnvRegs& e, uint32_t cell) {
+  // StaticObject.walkable (world_objects.py:20,148,199): Floor and Switch always, Block by state
+  uint32_t g = __ldg(T.grid + e.variant * 64 + cell);
+  uint32_t kind = g & 15u;
+  if (kind == ST_FLOOR || kind == ST_SWITCH) return true;
+  if (kind == ST_BLOCK) return (e.sbits & SB_BLK_WALK(g >> 4)) != 0;
+  return false;
+}
+
+__device__ __forceinline__ bool cz_agent_on(const CzDev& T, const EnvRegs& e, uint32_t cell) {
+  // `any(agent.location == interaction_location for agent in self.agents)` (cooking_world.py:116,158)
+  bool on = false;
+  for (int j = 0; j < T.A; ++j)
+    if (A_XY(e.ag[j * OSTRIDE]) == cell) on = true;
+  return on;
+}
+
+// Move a dynamic object (and, for a Plate, its content) — Object.move_to / Plate.move_to
+// (abstract_classes.py:21-22, world_objects.py:393-396).
+__device__ __forceinline__ void cz_move_obj(const CzDev& T, EnvRegs& e, uint32_t s, uint32_t xy) {
+  e.o[s * OSTRIDE] = O_WITH_XY(e.o[s * OSTRIDE], xy);
+  if (__ldg(T.type_flags + __ldg(T.slot_type + s)) & TF_PLATE) {
+    for (int k = 0; k < T.D; ++k) {
+      uint32_t r = e.o[k * OSTRIDE];
+      if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == s) e.o[k * OSTRIDE] = O_WITH_XY(r, xy);
+    }
+  }
+}
+
+// list.remove(obj) on the content of the static object at `cell`: later items shift down.
+__device__ __forceinline__ void cz_remove_from_static(const CzDev& T, EnvRegs& e, uint32_t cell, uint32_t pos) {
+  for (int k = 0; k < T.D; ++k) {
+    uint32_t r = e.o[k * OSTRIDE];
+    if ((r & O_PRESENT) && O_CK(r) == CK_STATIC && O_XY(r) == cell && O_POS(r) > pos) e.o[k * OSTRIDE] = r - (1u << 17);
+  }
+}
+
+// add_content's `for c in content: c.free = False; content[-1].free = True` for a plate
+// (world_objects.py:398-406): clear the flag of everything already on plate `p`, count it.
+__device__ __forceinline__ uint32_t cz_plate_count_clear_free(const CzDev& T, EnvRegs& e, uint32_t p, bool clear) {
+  uint32_t n = 0;
+  for (int k = 0; k < T.D; ++k) {
+    uint32_t r = e.o[k * OSTRIDE];
+    if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == p) {
+      ++n;
+      if (clear) e.o[k * OSTRIDE] = r & ~O_FREE;
+    }
+  }
+  return n;
+}
+
+// resolve_interaction -> resolve_execute_action | resolve_primary_interaction -> attempt_merge
+// (action_scheme3.py:37-43, cooking_world.py:114-136, 156-170, 243-261).
+__device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, uint32_t cell) {
+  const uint32_t agent_rec = e.ag[i * OSTRIDE];
+  const uint32_t g = __ldg(T.grid + e.variant * 64 + cell);
+  const uint32_t kind = g & 15u, sp = g >> 4;
+  // one pass in scan order over the dynamic objects at the faced cell (cooking_world.py:232-241)
+  int n_dyn = 0, last = -1, first_free = -1, n_plates = 0, plate = -1, n_content = 0;
+  bool any_not_done = false;
+  const uint8_t* scan = T.scan_order + e.variant * T.D;
+  for (int k = 0; k < T.D; ++k) {
+    int s = __ldg(scan + k);
+    uint32_t r = e.o[s * OSTRIDE];
+    if (!(r & O_PRESENT) || O_XY(r) != cell) continue;
+    ++n_dyn;
+    last = s;
+    if (first_free < 0 && (r & O_FREE)) first_free = s;
+    if (__ldg(T.type_flags + __ldg(T.slot_type + s)) & TF_PLATE) {
+      ++n_plates;
+      plate = s;
+    } else if (!(r & (O_CHOP | O_MASH))) {
+      any_not_done = true;  // Food.done() (world_objects.py:441,549,...)
+    }
+    if (O_CK(r) == CK_STATIC) ++n_content;
+  }
+  const bool blocked = cz_agent_on(T, e, cell);
+
+  if ((kind == ST_CUTBOARD || kind == ST_BLENDER) && any_not_done) {
+    // ---- resolve_execute_action (cooking_world.py:156-170)
+    if (blocked) return;
+    if (kind == ST_CUTBOARD) {  // Cutboard.action (world_objects.py:250-269)
+      if (!(e.sbits & SB_CUT_READY(sp))) return;
+      for (int p = 0; p < n_content; ++p) {
+        int s = -1;
+        for (int k = 0; k < T.D; ++k) {
+          uint32_t r = e.o[k * OSTRIDE];
+          if ((r & O_PRESENT) && O_CK(r) == CK_STATIC && O_XY(r) == cell && O_POS(r) == (uint32_t)p) s = k;
+        }
+        if (s < 0) break;
+        uint32_t r = e.o[s * OSTRIDE];
+        uint32_t tid = __ldg(T.slot_type + s);
+        uint32_t tf = __ldg(T.type_flags + tid);
+        if (!(tf & TF_CHOP)) return;
+        if (r & O_CHOP) continue;  // ChopFood.chop / Bread.chop: already chopped -> not executed
+        e.o[s * OSTRIDE] = r | O_CHOP;
+        e.sbits &= ~SB_CUT_READY(sp);
+        if (tf & TF_SPAWN) {  // Bread.chop spawns a chopped twin (world_objects.py:738-745)
+          int base = __ldg(T.type_base + tid), cnt = __ldg(T.type_count + tid);
+          int slot = -1;
+          for (int k = base; k < base + cnt; ++k)
+            if (slot < 0 && !(e.o[k * OSTRIDE] & O_PRESENT)) slot = k;
+          if (slot < 0) {
+            e.err |= CZ_ERR_OBS_OVERFLOW;  // the reference's obs vector would grow (cooking_env.py:371)
+          } else {
+            e.o[slot * OSTRIDE] = O_WITH_CONT(cell | O_PRESENT | O_CHOP | O_FREE, CK_STATIC, 0, n_content);
+          }
+        }
+        return;
+      }
+      e.err |= CZ_ERR_CUTBOARD_NONE;
+    } else {  // Blender.action (world_objects.py:356-360)
+      if (e.sbits & SB_BL_READY(sp)) e.sbits ^= SB_BL_TOGGLE(sp);
+    }
+    return;
+  }
+
+  // ---- resolve_primary_interaction (cooking_world.py:114-136)
+  if (blocked) return;
+  const uint32_t axy = A_XY(agent_rec);
+  if (!A_HAS(agent_rec)) {
+    if (n_dyn == 0) return;
+    bool rel = true;  // StaticObject.releases() with side effects
+    if (kind == ST_DELIVER) rel = false;  // world_objects.py:117-118
+    else if (kind == ST_CUTBOARD) {  // :275-278
+      if (n_content == 1) e.sbits &= ~SB_CUT_READY(sp);
+    } else if (kind == ST_BLENDER) {  // :340-346
+      if (e.sbits & SB_BL_TOGGLE(sp)) rel = false;
+      else if (n_content - 1 == 0) e.sbits &= ~SB_BL_READY(sp);
+    }
+    if (!rel) return;
+    int gs = first_free >= 0 ? first_free : last;
+    uint32_t r = e.o[gs * OSTRIDE];
+    if (O_CK(r) != CK_STATIC) return;  // `object_to_grab in static_object.content`
+    cz_remove_from_static(T, e, cell, O_POS(r));
+    e.o[gs * OSTRIDE] = O_WITH_CONT(r, CK_HELD, i, 0);
+    cz_move_obj(T, e, gs, axy);  // Agent.grab (world_objects.py:786-788)
+    e.ag[i * OSTRIDE] = (agent_rec & ~(0x3Fu << 9)) | (1u << 9) | ((uint32_t)gs << 10);
+    return;
+  }
+
+  // ---- attempt_merge (cooking_world.py:243-261)
+  const uint32_t h = A_HOLD(agent_rec);
+  const uint32_t hr = e.o[h * OSTRIDE];
+  const uint32_t htf = __ldg(T.type_flags + __ldg(T.slot_type + h));
+  const uint32_t dropped = agent_rec & ~(0x3Fu << 9);
+  if (n_plates == 1) {
+    // Plate.accepts: Food and done and room (world_objects.py:408-409)
+    if ((htf & (TF_CHOP | TF_BLEND)) && (hr & (O_CHOP | O_MASH))) {
+      uint32_t n = cz_plate_count_clear_free(T, e, plate, false);
+      if (n < 64) {
+        cz_plate_count_clear_free(T, e, plate, true);
+        e.o[h * OSTRIDE] = O_WITH_XY(O_WITH_CONT(hr, CK_PLATE, plate, n) | O_FREE, cell);
+        e.ag[i * OSTRIDE] = dropped;  // put_down (world_objects.py:790-792)
+      }
+    }
+  } else if ((htf & TF_PLATE) && n_dyn > 0) {
+    uint32_t pr = e.o[last * OSTRIDE];
+    uint32_t ptf = __ldg(T.type_flags + __ldg(T.slot_type + last));
+    if ((ptf & (TF_CHOP | TF_BLEND)) && (pr & (O_CHOP | O_MASH))) {
+      uint32_t n = cz_plate_count_clear_free(T, e, h, false);
+      if (n < 64) {
+        cz_plate_count_clear_free(T, e, h, true);
+        if (O_CK(pr) == CK_STATIC) cz_remove_from_static(T, e, cell, O_POS(pr));
+        else e.err |= CZ_ERR_REMOVE;
+        e.o[last * OSTRIDE] = O_WITH_XY(O_WITH_CONT(pr, CK_PLATE, h, n) | O_FREE, axy);
+      }
+    }
+  } else {
+    bool ok = false;  // StaticObject.accepts
+    if (kind == ST_COUNTER || kind == ST_DELIVER) ok = n_content < 1;  // :64-66, :107-108
+    else if (kind == ST_CUTBOARD) ok = (htf & TF_CHOP) && n_content < 1 && !(hr & O_CHOP);  // :271-273
+    else if (kind == ST_BLENDER)
+      ok = (htf & TF_BLEND) && !(e.sbits & SB_BL_TOGGLE(sp)) && n_content + 1 <= 1 && !(hr & O_MASH);  // :337-338
+    if (ok) {
+      if (kind == ST_CUTBOARD) e.sbits |= SB_CUT_READY(sp);
+      if (kind == ST_BLENDER) e.sbits |= SB_BL_READY(sp);
+      e.o[h * OSTRIDE] = O_WITH_CONT(hr, CK_STATIC, 0, n_content) | O_FREE;
+      cz_move_obj(T, e, h, cell);
+      e.ag[i * OSTRIDE] = dropped;
+    }
+  }
+}
+
+// progress_world's free-flag refresh for one static container (cooking_world.py:82-88):
+// only containers that lost an item or gained a spawned Bread this step can be stale.
+__device__ __forceinline__ void cz_refresh_static_free(const CzDev& T, EnvRegs& e, uint32_t cell) {
+  int top = -1;
+  for (int k = 0; k < T.D; ++k) {
+    uint32_t r = e.o[k * OSTRIDE];
+    if ((r & O_PRESENT) && O_CK(r) == CK_STATIC && O_XY(r) == cell && (int)O_POS(r) > top) top = O_POS(r);
+  }
+  for (int k = 0; k < T.D; ++k) {
+    uint32_t r = e.o[k * OSTRIDE];
+    if ((r & O_PRESENT) && O_CK(r) == CK_STATIC && O_XY(r) == cell)
+      e.o[k * OSTRIDE] = ((int)O_POS(r) == top) ? (r | O_FREE) : (r & ~O_FREE);
+  }
+}
+
+// Recipe.update_recipe_state as cell bitmasks (recipe.py:77-104): node mask = cells holding an
+// object of the node's type that meets its condition, ANDed with every child's mask.
+__device__ __forceinline__ uint32_t cz_recipe_marks(const CzDev& T, const EnvRegs& e, uint32_t rid) {
+  uint64_t m[CZ_MAX_NODES];
+  const int n = __ldg(T.recipe_len + rid);
+  uint32_t marks = 0;
+#pragma unroll
+  for (int k = CZ_MAX_NODES - 1; k >= 0; --k) {
+    m[k] = 0;
+    if (k < n) {
+      uint32_t node = __ldg(T.recipe_nodes + rid * CZ_MAX_NODES + k);
+      uint64_t mask = 0;
+      uint32_t ty = node & 255u;
+      if (node & 256u) {
+        mask = __ldg(T.static_masks + e.variant * 8 + (ty & 7u));
+      } else if (ty != 255u) {
+        uint32_t cond = (node >> 9) & 3u;
+        uint32_t need = cond == 1 ? O_CHOP : (cond == 2 ? O_MASH : 0u);
+        int base = __ldg(T.type_base + ty), cnt = __ldg(T.type_count + ty);
+        for (int s = base; s < base + cnt; ++s) {
+          uint32_t r = e.o[s * OSTRIDE];
+          if ((r & O_PRESENT) && (r & need) == need) mask |= 1ull << O_XY(r);
+        }
+      }
+      uint32_t kids = node >> 16;
+#pragma unroll
+      for (int j = k + 1; j < CZ_MAX_NODES; ++j)
+        if (kids & (1u << j)) mask &= m[j];
+      m[k] = mask;
+      if (mask) marks |= 1u << k;
+    }
+  }
+  return marks;
+}
+
+// CookingEnvironment.accumulated_step (cooking_env.py:243-269) for one environment.
+// Writes reward f64[A], terminated u8[A], truncated u8[A] of this environment.
+__device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const uint32_t act_packed,
+                                            double* __restrict__ reward, uint8_t* __restrict__ term_out,
+                                            uint8_t* __restrict__ trunc_out) {
+  const int A = T.A;
+  const uint32_t t = TI_T(e.tinfo) + 1;  // :244
+  uint32_t active = 0;
+  for (int i = 0; i < A; ++i)
+    if (A_ACTIVE(e.ag[i * OSTRIDE])) active |= 1u << i;
+  uint32_t changed = 0;
+
+  // ---- action_scheme3.perform_agent_actions (action_scheme3.py:4-16)
+  // per agent, 8 bits each: apack = action after checks, fpack = faced cell, epack = end cell | 0x40 walkable
+  uint32_t apack = 0, fpack = 0, epack = 0x80808080u;
+  for (int i = 0; i < A; ++i) {
+    if (!(active >> i & 1u)) continue;
+    uint32_t ai = (act_packed >> (8 * i)) & 255u;
+    if (ai > 4u) ai = 0;  // outside Discrete(5): behaves as a no-op
+    uint32_t rec = e.ag[i * OSTRIDE];
+    int x = rec & 7u, y = (rec >> 3) & 7u;
+    uint32_t faced = A_XY(rec);
+    if (ai) {
+      rec = (rec & ~(7u << 6)) | (ai << 6);  // change_orientation even if cancelled later (:8-10)
+      e.ag[i * OSTRIDE] = rec;
+      int tx = x + (ai == 2) - (ai == 1), ty = y + (ai == 3) - (ai == 4);  // cooking_world.py:172-184
+      if (tx < 0 || ty < 0 || tx > T.W - 1 || ty > T.H - 1) ai = 0;  // check_inbounds :192-204
+      else faced = (uint32_t)(tx | ty << 3);
+    }
+    // check_collisions, first loop (:206-216)
+    uint32_t tgt = ai ? faced : A_XY(rec);
+    bool w = cz_walkable(T, e, tgt);
+    uint32_t endc = (w ? tgt : A_XY(rec)) | (w ? 0x40u : 0u);
+    apack |= ai << (8 * i);
+    fpack |= faced << (8 * i);
+    epack = (epack & ~(0xFFu << (8 * i))) | (endc << (8 * i));
+  }
+  // check_collisions, second loop (:217-221): one pass over pre-move end cells
+  uint32_t cancel = 0;
+  for (int i = 0; i < A; ++i) {
+    uint32_t ei = (epack >> (8 * i)) & 255u;
+    if (!(ei & 0x40u) || (ei & 0x80u)) continue;  // not walkable, or inactive
+    for (int j = 0; j < A; ++j) {
+      uint32_t ej = (epack >> (8 * j)) & 255u;
+      if (j != i && !(ej & 0x80u) && (ej & 63u) == (ei & 63u)) cancel |= 1u << i;
+    }
+  }
+  // sequential resolution in agent order (action_scheme3.py:15-34)
+  uint32_t pressed = 0, dirty = 0xFFFFFFFFu;
+  for (int i = 0; i < A; ++i) {
+    if (!(active >> i & 1u)) continue;
+    uint32_t rec = e.ag[i * OSTRIDE];
+    uint32_t ai = (cancel >> i & 1u) ? 0u : ((apack >> (8 * i)) & 255u);
+    uint32_t tgt = ai ? ((fpack >> (8 * i)) & 63u) : A_XY(rec);
+    if (cz_walkable(T, e, tgt)) {  // resolve_walking_action (:26-34)
+      rec = (rec & ~63u) | tgt;
+      e.ag[i * OSTRIDE] = rec;
+      if (A_HAS(rec)) cz_move_obj(T, e, A_HOLD(rec), tgt);  // Agent.move_to (world_objects.py:793-796)
+      uint32_t g = __ldg(T.grid + e.variant * 64 + tgt);
+      if ((g & 15u) == ST_SWITCH) {  // Switch.add_content (:159-163)
+        e.sbits ^= SB_SW_ACTIVE(g >> 4);
+        pressed |= 1u << (g >> 4);
+      }
+    } else if (ai) {
+      cz_interact(T, e, i, tgt);
+      dirty = (dirty & ~(0xFFu << (8 * i))) | (tgt << (8 * i));
+    }
+  }
+
+  // ---- progress_world (cooking_world.py:77-88)
+  if (e.sbits & (0xFu << 8)) {  // some blender is switched on: Blender.process (world_objects.py:321-335)
+    for (int k = 0; k < CZ_MAX_SPECIAL; ++k) {
+      if (!(e.sbits & SB_BL_TOGGLE(k))) continue;
+      uint32_t cell = __ldg(T.special_cells + (e.variant * 4 + 1) * CZ_MAX_SPECIAL + k);
+      if (cell == 0xFFu) continue;
+      int n = 0;
+      bool all_mashed = true;
+      for (int s = 0; s < T.D; ++s) {
+        uint32_t r = e.o[s * OSTRIDE];
+        if (!(r & O_PRESENT) || O_CK(r) != CK_STATIC || O_XY(r) != cell) continue;
+        ++n;
+        if (!(r & (O_CHOP | O_MASH))) {  // BlenderFood.blend: one call takes FRESH to MASHED (abstract_classes.py:266-273)
+          r |= O_MASH;
+          e.o[s * OSTRIDE] = r;
+        }
+        if (!(r & O_MASH)) all_mashed = false;
+      }
+      if (n > 0 && all_mashed) e.sbits &= ~(SB_BL_TOGGLE(k) | SB_BL_READY(k));
+    }
+  }
+  if (dirty != 0xFFFFFFFFu) {
+    for (int i = 0; i < A; ++i) {
+      uint32_t c = (dirty >> (8 * i)) & 255u;
+      if (c != 0xFFu) cz_refresh_static_free(T, e, c);
+    }
+  }
+  // ---- resolve_linked_interactions (cooking_world.py:90-92; Switch :165-169, Block :215-216)
+  if (pressed) {
+    uint32_t blocks = 0, n_sw = 0;
+    for (int k = 0; k < CZ_MAX_SPECIAL; ++k) {
+      if (__ldg(T.special_cells + (e.variant * 4 + 3) * CZ_MAX_SPECIAL + k) != 0xFFu) blocks |= SB_BLK_WALK(k);
+      if (__ldg(T.special_cells + (e.variant * 4 + 2) * CZ_MAX_SPECIAL + k) != 0xFFu) ++n_sw;
+    }
+    if (n_sw > 1) e.err |= CZ_ERR_SWITCH_LINK;
+    for (int k = 0; k < CZ_MAX_SPECIAL; ++k)
+      if (pressed >> k & 1u) e.sbits ^= blocks;
+  }
+  // ---- handle_agent_spawn (cooking_world.py:267-277): grace countdown; the draws that follow
+  // change nothing at the default rates 0.0 (despawn/respawn with host uniforms: see DESIGN.md)
+  for (int i = 0; i < A; ++i)
+    if (A_GRACE(e.ag[i * OSTRIDE]) > 0) e.ag[i * OSTRIDE] -= 1u << 16;
+
+  uint32_t relevant = active | changed;  // compute_relevant_agents :292
+
+  // ---- compute_rewards / compute_truncated (cooking_env.py:290-350)
+  const bool time_up = t >= (uint32_t)T.max_steps;
+  uint32_t trunc_mask = 0;
+  if (time_up) {
+    if (TI_NLIVE(e.tinfo) < (uint32_t)A) e.err |= CZ_ERR_TRUNC_DESPAWN;
+    trunc_mask = relevant;
+    changed = relevant;
+    active = 0;
+  }
+  trunc_mask |= changed & ~active & relevant;
+  relevant = active | changed;
+  // agent i is the k-th relevant agent and receives entry k of the recipe lists (:250-262)
+  uint32_t new_marks = 0;
+  bool all_done = true, any_done = false;
+  for (int r = 0; r < T.R; ++r) {
+    uint32_t rid = (e.rids >> (8 * r)) & 255u;
+    uint32_t before = (e.marks >> (8 * r)) & 255u;
+    uint32_t after = cz_recipe_marks(T, e, rid);
+    new_marks |= after << (8 * r);
+    bool was = before & 1u, now = after & 1u;
+    int delta = __popc(after) - __popc(before);  // sum(goals_before) - sum(goals_after)
+    double v = 0.0;
+    v = __dadd_rn(v, __dmul_rn((double)delta, T.r_node));
+    v = __dadd_rn(v, (now && !was) ? T.r_recipe : 0.0);
+    v = __dadd_rn(v, (!now && was) ? T.r_penalty : 0.0);
+    v = __dadd_rn(v, T.r_time);
+    all_done = all_done && now;
+    any_done = any_done || now;
+    // which agent is the r-th relevant one?
+    uint32_t m = relevant;
+    for (int q = 0; q < r; ++q) m &= m - 1;
+    if (m) reward[__ffs(m) - 1] = v;
+  }
+  e.marks = new_marks;
+  const bool done = T.end_all ? all_done : any_done;
+  int k = 0;
+  for (int i = 0; i < A; ++i) {
+    bool rel = relevant >> i & 1u;
+    if (!rel || k >= T.R) reward[i] = 0.0;
+    if (rel) ++k;
+    term_out[i] = (rel && done) ? 1 : 0;
+    trunc_out[i] = (trunc_mask >> i & 1u) ? 1 : 0;
+    e.ag[i * OSTRIDE] = (e.ag[i * OSTRIDE] & ~(1u << 15)) | ((active >> i & 1u) << 15);
+  }
+  uint32_t n_live = __popc(relevant);
+  e.tinfo = (t & 0xFFFFFu) | ((done || time_up) ? TI_DONE : 0u) | (n_live << 21);
+}

@@ -1,0 +1,221 @@
+"""Table compiler: level + meta + recipes + reward scheme -> the constant tables of cz_b200.h.
+
+Replaces, once per configuration, what the reference re-derives every step from live Python
+objects: `StringToClass`/`issubclass` scans (cooking_world.py:232-241), the class methods
+accepts/releases/done/feature_vector_representation (world_objects.py), the recipe node graph
+(recipe_drawer.py:40-118, recipe.py:29-33) and the constructor arithmetic of
+CookingEnvironment (cooking_env.py:62-161).  Output: numpy arrays laid out exactly as
+include/cz_b200.h documents, plus the layout pool of packed initial states.
+"""
+import random
+
+import numpy as np
+
+from . import entities as E
+from .layout import sample_layout
+from .levels import load_level_object, load_meta
+from .recipes import active_book
+
+MAX_CELLS, MAX_DYN, MAX_AGENTS, MAX_RECIPES, MAX_NODES, MAX_TYPES = 64, 32, 4, 4, 8, 16
+MAX_STATIC_SLOTS, MAX_SPECIAL = 96, 4
+ROW_SBITS, ROW_TINFO, ROW_MARKS, ROW_VARIANT, ROW_RECIPES, ROW_EPISODE, NUM_MISC = 0, 1, 2, 3, 4, 5, 6
+SPECIAL_KINDS = {E.ST_CUTBOARD: 0, E.ST_BLENDER: 1, E.ST_SWITCH: 2, E.ST_BLOCK: 3}
+DEFAULT_REWARD = {"recipe_reward": 20, "max_time_penalty": -5, "recipe_penalty": -40,
+                  "recipe_node_reward": 0}          # cooking_env.py:79-80
+
+
+# ---- packed records (bit layout documented in include/cz_b200.h) -------------------------
+def pack_obj(x, y, present=1, chopped=0, mashed=0, free=1, ckind=1, cid=0, pos=0):
+    return (x | y << 3 | present << 6 | chopped << 7 | mashed << 8 | free << 9 | ckind << 10
+            | cid << 12 | pos << 17)
+
+
+def pack_agent(x, y, orientation=1, holding=-1, active=1, grace=0):
+    h = 0 if holding < 0 else (1 << 9 | holding << 10)
+    return x | y << 3 | orientation << 6 | h | active << 15 | grace << 16
+
+
+class CompiledTables:
+    """All arrays of cz_table_desc as numpy, plus python-side metadata."""
+
+
+def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_scheme=None,
+                   end_condition_all_dishes=False, grace_period=20, agent_respawn_rate=0.0,
+                   agent_despawn_rate=0.0, recipe_pool=None, layout_pool_size=256, layout_seed=0,
+                   layouts=None):
+    """`recipes`: the per-agent recipe names of the reference constructor (default per-env
+    assignment).  `recipe_pool`: every recipe name environments may be assigned (defaults to
+    `recipes`).  `layouts`: explicit list of layout dicts (overrides sampling)."""
+    t = CompiledTables()
+    level_object = load_level_object(level)
+    meta = load_meta(meta_file)
+    meta_count = dict(meta)
+    if "Agent" not in meta_count or num_agents > meta_count["Agent"]:
+        raise AssertionError("Too many agents for this level")        # cooking_env.py:93-94
+    if not 1 <= num_agents <= MAX_AGENTS:
+        raise ValueError(f"num_agents must be in 1..{MAX_AGENTS}")
+    recipes = list(recipes)
+    if len(recipes) < num_agents:
+        # the reference raises IndexError in compute_infos (cooking_env.py:329) on the first step
+        raise ValueError("the reference requires at least one recipe per agent")
+    if len(recipes) > MAX_RECIPES:
+        raise ValueError(f"at most {MAX_RECIPES} recipes per environment")
+
+    # ---- canonical slots, in meta order ----------------------------------------------
+    dyn_types, type_base, type_count = [], [], []
+    static_base = {}
+    obs_slots = []
+    D = S = off = 0
+    for name, num in meta:
+        et = E.entity(name)
+        n_fv = E.FV_LEN[et.fv]
+        if et.kind == "dynamic":
+            dyn_types.append(name)
+            type_base.append(D)
+            type_count.append(num)
+            for k in range(num):
+                obs_slots.append((off + k * n_fv, et.fv, 1, D + k))
+            D += num
+        elif et.kind == "static":
+            static_base[name] = (S, num)
+            for k in range(num):
+                if n_fv:
+                    obs_slots.append((off + k * n_fv, et.fv, 0, S + k))
+            S += num
+        else:
+            for k in range(num):
+                obs_slots.append((off + k * n_fv, et.fv, 2, k))
+        off += n_fv * num
+    L = off                                                              # cooking_env.py:114-117
+    if D > MAX_DYN or len(dyn_types) > MAX_TYPES or S > MAX_STATIC_SLOTS or L >= 4096:
+        raise ValueError("meta file exceeds the kernel's compile-time capacity (see cz_b200.h)")
+    type_id = {n: i for i, n in enumerate(dyn_types)}
+    rows = D + num_agents + NUM_MISC
+
+    # ---- layout pool -----------------------------------------------------------------
+    if layouts is None:
+        rng = random.Random(layout_seed)
+        layouts = [sample_layout(level_object, meta, num_agents, rng) for _ in range(layout_pool_size)]
+    W, H = layouts[0]["width"], layouts[0]["height"]
+    if W > 8 or H > 8 or W * H > MAX_CELLS:
+        raise ValueError("levels larger than 8x8 are not supported by the kernels")
+
+    variants, variant_of = [], {}
+    pool = np.zeros((len(layouts), rows), np.uint32)
+    for li, lay in enumerate(layouts):
+        if (lay["width"], lay["height"]) != (W, H) or len(lay["agents"]) != num_agents:
+            raise ValueError("all pooled layouts must share size and agent count")
+        grid = np.zeros(MAX_CELLS, np.uint8)
+        static_cells = np.full(max(S, 1), 0xFF, np.uint8)
+        special = np.full((4, MAX_SPECIAL), 0xFF, np.uint8)
+        masks = np.zeros(8, np.uint64)
+        dyn_order = []
+        counts = {}
+        for name, locs in lay["objects"]:
+            et = E.entity(name)
+            if et.kind == "static":
+                for k, (x, y) in enumerate(locs):
+                    cell = y * 8 + x          # device cell index: 8-stride (== low 6 bits of a record)
+                    sp = 0
+                    if et.static_code in SPECIAL_KINDS:
+                        if k >= MAX_SPECIAL:
+                            raise ValueError(f"more than {MAX_SPECIAL} {name} objects")
+                        sp = k
+                        special[SPECIAL_KINDS[et.static_code], k] = cell
+                    grid[cell] = et.static_code | sp << 4
+                    masks[et.static_code] |= np.uint64(1) << np.uint64(cell)
+                    if name in static_base:
+                        base, num = static_base[name]
+                        if k >= num:
+                            raise ValueError(f"level places more {name} objects than the meta file allows")
+                        static_cells[base + k] = cell
+                    elif E.FV_LEN[et.fv]:
+                        raise KeyError(name)
+            elif et.kind == "dynamic":
+                if name not in type_id:
+                    raise KeyError(name)
+                dyn_order.append(name)
+                counts[name] = len(locs)
+                tid = type_id[name]
+                if len(locs) > type_count[tid]:
+                    raise ValueError(f"level places more {name} objects than the meta file allows")
+                for k, (x, y) in enumerate(locs):
+                    pool[li, type_base[tid] + k] = pack_obj(x, y)
+        # scan order: present types in world_objects insertion order, then the rest
+        order = dyn_order + [n for n in dyn_types if n not in dyn_order]
+        scan = np.array([type_base[type_id[n]] + k for n in order for k in range(type_count[type_id[n]])],
+                        np.uint8)
+        key = (grid.tobytes(), static_cells.tobytes(), scan.tobytes())
+        if key not in variant_of:
+            variant_of[key] = len(variants)
+            variants.append((grid, static_cells, scan, special, masks))
+        for i, (x, y) in enumerate(lay["agents"]):
+            pool[li, D + i] = pack_agent(x, y, 1, -1, 1, grace_period)
+        pool[li, D + num_agents + ROW_TINFO] = num_agents << 21
+        pool[li, D + num_agents + ROW_VARIANT] = variant_of[key]
+    V = len(variants)
+
+    # ---- recipes ---------------------------------------------------------------------
+    book = active_book()
+    pool_names = list(recipe_pool) if recipe_pool is not None else []
+    for n in recipes:
+        if n not in pool_names:
+            pool_names.append(n)
+    recipe_nodes = np.zeros((len(pool_names), MAX_NODES), np.uint32)
+    recipe_len = np.zeros(len(pool_names), np.uint8)
+    for b, name in enumerate(pool_names):
+        nodes = book[name].node_list()
+        if len(nodes) > MAX_NODES:
+            raise ValueError(f"recipe {name} has more than {MAX_NODES} nodes")
+        recipe_len[b] = len(nodes)
+        pos = {id(n): k for k, n in enumerate(nodes)}
+        for k, n in enumerate(nodes):
+            et = E.entity(n.name)
+            kids = 0
+            for c in n.contains:
+                kids |= 1 << pos[id(c)]
+            if et.kind == "static":
+                word = et.static_code | 1 << 8
+            elif et.kind == "dynamic":
+                # a food type that is not in the meta file can never exist in the world
+                word = type_id.get(n.name, 0xFF)
+            else:
+                raise ValueError("recipe nodes over agents cannot be compiled")
+            recipe_nodes[b, k] = word | n.condition_code() << 9 | kids << 16
+
+    rs = dict(reward_scheme or DEFAULT_REWARD)
+    t.level_object, t.meta, t.layouts = level_object, meta, layouts
+    t.width, t.height, t.num_agents, t.num_recipes = W, H, num_agents, len(recipes)
+    t.num_dyn_slots, t.num_static_slots, t.num_types = D, S, len(dyn_types)
+    t.obs_len, t.rows, t.num_variants, t.num_layouts = L, rows, V, len(layouts)
+    t.max_steps, t.end_all, t.grace_period = int(max_steps), int(bool(end_condition_all_dishes)), int(grace_period)
+    t.reward_scheme = rs
+    t.reward_node = float(rs["recipe_node_reward"])
+    t.reward_recipe = float(rs["recipe_reward"])
+    t.reward_penalty = float(rs["recipe_penalty"])
+    t.reward_time = float(rs["max_time_penalty"] / max_steps)          # cooking_env.py:307
+    t.respawn_rate, t.despawn_rate = float(agent_respawn_rate), float(agent_despawn_rate)
+    t.xlut = np.array([k / W for k in range(-(W - 1), W)], np.float64)  # cooking_env.py:364-368
+    t.ylut = np.array([k / H for k in range(-(H - 1), H)], np.float64)
+    t.grid = np.stack([v[0] for v in variants])
+    t.static_cells = np.stack([v[1] for v in variants])
+    t.scan_order = np.stack([v[2] for v in variants])
+    t.special_cells = np.stack([v[3] for v in variants])
+    t.static_masks = np.stack([v[4] for v in variants])
+    t.num_switches = int((t.special_cells[0, 2] != 0xFF).sum())
+    t.num_blocks = int((t.special_cells[0, 3] != 0xFF).sum())
+    slot_type = np.zeros(max(D, 1), np.uint8)
+    for tid, (b, c) in enumerate(zip(type_base, type_count)):
+        slot_type[b:b + c] = tid
+    t.slot_type = slot_type
+    t.dyn_types = dyn_types
+    t.type_flags = np.array([E.entity(n).flags for n in dyn_types], np.uint8)
+    t.type_base = np.array(type_base, np.uint8)
+    t.type_count = np.array(type_count, np.uint8)
+    t.obs_slots = np.array([o | fv << 12 | kind << 15 | idx << 17 for o, fv, kind, idx in obs_slots], np.uint32)
+    t.recipe_names = pool_names
+    t.recipe_nodes, t.recipe_len = recipe_nodes, recipe_len
+    t.default_recipes = np.array([pool_names.index(n) for n in recipes], np.uint8)
+    t.pool = pool
+    t.static_base = static_base
+    return t

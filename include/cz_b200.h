@@ -1,0 +1,176 @@
+/* cz_b200.h — C ABI of libcz_b200.so, the B200 (sm_100a) batched CookingZoo step path.
+ *
+ * The reference (DavidRother/cooking_zoo) is pure Python and has no FFI: its boundary for
+ * this path is the in-process Python env API.  Each entry point below names the reference
+ * interface it replaces (paths relative to /root/reference/cooking_zoo/).  The host side
+ * that binds these (ctypes) is cooking_zoo_b200/_native.py; the stub a reference maintainer
+ * would add is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only (no torch / C++ types); every function returns
+ * 0 on success or a negative CZ_E* code and cz_last_error() then describes it; no exception
+ * crosses the boundary; all env buffers are caller-owned DEVICE memory (cz_*_host variants
+ * take HOST memory); launches are asynchronous on the given stream (a cudaStream_t passed
+ * as void*, NULL = legacy default stream) with no hidden synchronisation; the library owns
+ * only cz_tables.  One host thread per device; not thread-safe on the same state.
+ */
+#ifndef CZ_B200_H
+#define CZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CZ_ABI_VERSION 1
+
+/* compile-time capacity of the kernels */
+#define CZ_MAX_CELLS 64       /* width<=8, height<=8; device cell index = y*8 + x */
+#define CZ_MAX_DYN 32         /* dynamic-object slots (sum of meta counts of dynamic types) */
+#define CZ_MAX_AGENTS 4
+#define CZ_MAX_RECIPES 4      /* recipes evaluated per environment */
+#define CZ_MAX_NODES 8        /* nodes per recipe (Recipe.node_list) */
+#define CZ_MAX_TYPES 16       /* dynamic types */
+#define CZ_MAX_STATIC_SLOTS 96
+#define CZ_MAX_SPECIAL 4      /* cutboards / blenders / switches / blocks per level (each) */
+
+/* error codes */
+#define CZ_OK 0
+#define CZ_EINVAL (-1)
+#define CZ_ECUDA (-2)
+#define CZ_ELIMIT (-3)
+
+/* per-environment error_flags bits: "the reference would have raised / diverged here" */
+#define CZ_ERR_CUTBOARD_NONE 1u   /* Cutboard.action() returns None (world_objects.py:250-269)      */
+#define CZ_ERR_REMOVE 2u          /* list.remove of an object not in content (cooking_world.py:254) */
+#define CZ_ERR_SWITCH_LINK 4u     /* Switch linked to a Switch: no switch_state (world_objects.py:165-169) */
+#define CZ_ERR_SPAWN_LOC 8u       /* generate_location timed out (parsing.py:154-167)               */
+#define CZ_ERR_TRUNC_DESPAWN 16u  /* IndexError at cooking_env.py:348 (truncation with despawned agent) */
+#define CZ_ERR_OBS_OVERFLOW 32u   /* more objects of a type than meta slots (cooking_env.py:371)    */
+
+/* ---- packed per-environment state --------------------------------------------------
+ * `state` is a u32 matrix [cz_state_rows()][n_envs] (structure of arrays: row-major, the
+ * environment index is the fastest axis).  Rows:
+ *   [0, D)          dynamic-object slot records   (D = num_dyn_slots, canonical meta order)
+ *   [D, D+A)        agent records                 (A = num_agents)
+ *   D+A+0  SBITS    mutable bits of static objects
+ *   D+A+1  TINFO    bits 0-19 t | 20 done | 21-23 n_live | 24-31 reserved
+ *   D+A+2  MARKS    recipe r: bits [8r, 8r+8) = node_list[k].marked
+ *   D+A+3  VARIANT  static variant id of the current layout
+ *   D+A+4  RECIPES  recipe r: bits [8r, 8r+8) = index into the compiled recipe list
+ *   D+A+5  EPISODE  episodes started by this environment (auto-reset counter)
+ *
+ * object record : 0-2 x | 3-5 y | 6 present | 7 chopped | 8 mashed | 9 free |
+ *                 10-11 container kind (0 held by agent, 1 static content, 2 plate content) |
+ *                 12-16 container id (agent index / 0 / plate slot) | 17-22 position in content
+ * agent record  : 0-2 x | 3-5 y | 6-8 orientation | 9 holding? | 10-14 held slot |
+ *                 15 active | 16-31 grace period left
+ * SBITS         : 0-3 cutboard k READY | 4-7 blender k READY | 8-11 blender k toggle |
+ *                 12-15 switch k active | 16-19 block k walkable
+ */
+#define CZ_ROW_SBITS 0
+#define CZ_ROW_TINFO 1
+#define CZ_ROW_MARKS 2
+#define CZ_ROW_VARIANT 3
+#define CZ_ROW_RECIPES 4
+#define CZ_ROW_EPISODE 5
+#define CZ_NUM_MISC_ROWS 6
+
+/* cz_step flags */
+#define CZ_STEP_AUTO_RESET 1u  /* an environment whose `done` bit is set is re-initialised from
+                                  the layout pool instead of stepped (reward 0, flags 0) */
+
+/* Host-side description of everything compiled once per (level, meta, recipes, scheme):
+ * replaces load_level.load_level / parsing.parse_* (engine/load_level.py:55-71,
+ * engine/parsing.py:5-151), the class tables of world_objects.py, recipe_drawer.py:40-118
+ * and the constructor of CookingEnvironment (environment/cooking_env.py:62-161).
+ * All pointers are HOST memory, copied by cz_tables_create. */
+typedef struct cz_table_desc {
+  int32_t abi_version;
+  int32_t width, height;
+  int32_t num_agents;         /* A: agents per environment                                  */
+  int32_t num_recipes;        /* R: recipes evaluated per environment (>= A in the reference) */
+  int32_t num_dyn_slots;      /* D */
+  int32_t num_static_slots;   /* S: observed static slots (meta order)                      */
+  int32_t num_types;          /* dynamic types                                              */
+  int32_t num_obs_slots;      /* entries of obs_slots                                       */
+  int32_t obs_len;            /* L: doubles per agent observation                           */
+  int32_t num_variants;       /* V: distinct static configurations in the layout pool       */
+  int32_t num_layouts;        /* P: layout pool size                                        */
+  int32_t num_book;           /* B: compiled recipes                                        */
+  int32_t max_steps;
+  int32_t end_all;            /* end_condition_all_dishes                                   */
+  int32_t grace_period;
+  int32_t num_switches, num_blocks;
+  double reward_node, reward_recipe, reward_penalty; /* reward_scheme terms                  */
+  double reward_time;         /* max_time_penalty / max_steps, divided by the host           */
+  double respawn_rate, despawn_rate;
+  const double* xlut;         /* [2*width-1]  k/width  for k=-(width-1)..width-1            */
+  const double* ylut;         /* [2*height-1]                                               */
+  const uint8_t* grid;        /* [V][64] low nibble static kind, high nibble special index  */
+  const uint8_t* static_cells;/* [V][S] cell of observed static slot, 0xFF = empty          */
+  const uint8_t* scan_order;  /* [V][D] dynamic slots in get_objects_at scan order          */
+  const uint8_t* special_cells;/* [V][4 kinds][CZ_MAX_SPECIAL] cell, 0xFF = none            */
+  const uint64_t* static_masks;/* [V][8] cells occupied by each static kind                 */
+  const uint8_t* slot_type;   /* [D] dynamic type id of a slot                              */
+  const uint8_t* type_flags;  /* [T] 1 plate | 2 chop | 4 blend | 8 spawn-on-chop           */
+  const uint8_t* type_base;   /* [T] first slot of the type                                 */
+  const uint8_t* type_count;  /* [T] slots of the type                                      */
+  const uint32_t* obs_slots;  /* [num_obs_slots] 0-11 offset | 12-14 FV layout | 15-16 kind (0 static,1 dynamic,2 agent) | 17-24 index */
+  const uint32_t* recipe_nodes;/* [B][8] 0-7 type | 8 static? | 9-10 cond | 16-23 children  */
+  const uint8_t* recipe_len;  /* [B] nodes in the recipe                                    */
+  const uint32_t* pool;       /* [P][rows] initial state of every pooled layout             */
+  const uint8_t* default_recipes; /* [R] recipe index per slot when no per-env ids are given */
+} cz_table_desc;
+
+typedef struct cz_tables cz_tables;
+
+/* Compile-once tables -> device.  Replaces CookingWorld.__init__ + load_level + the class
+ * and recipe tables (cooking_world/cooking_world.py:23-44, 263-265). */
+int cz_tables_create(const cz_table_desc* desc, int device, cz_tables** out);
+int cz_tables_destroy(cz_tables* t);
+
+/* Rows of the u32 state matrix for these tables (= D + A + CZ_NUM_MISC_ROWS). */
+int cz_state_rows(const cz_tables* t);
+
+/* CookingEnvironment.reset (environment/cooking_env.py:178-210) for every environment whose
+ * mask byte is non-zero (mask NULL = all): copy pooled layout layout_ids[e] into the state,
+ * evaluate the recipes (cooking_book/recipe.py:77-87), write the first observations
+ * (cooking_env.py:352-373).  recipe_ids: [n][R] u8 or NULL (default assignment). */
+int cz_reset(const cz_tables* t, uint32_t* state, const int32_t* layout_ids, const uint8_t* recipe_ids,
+             const uint8_t* mask, double* obs, int n_envs, void* stream);
+
+/* CookingEnvironment.accumulated_step + observe (environment/cooking_env.py:243-288):
+ * world_step (cooking_world/cooking_world.py:104-112, action_scheme3.py:4-43), compute_rewards /
+ * compute_truncated (:290-350), get_feature_vector (:352-373) for n_envs environments.
+ * actions u8 [n][A]; obs f64 [n][A][L]; reward f64 [n][A]; terminated/truncated u8 [n][A];
+ * error_flags u32 [n] (OR-accumulated, may be NULL).  With CZ_STEP_AUTO_RESET the layout of
+ * episode k of global environment g = env_offset + e is pool[cz_layout_draw(seed, g, k) % P]. */
+int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actions, double* obs, double* reward,
+            uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs,
+            uint32_t flags, uint64_t seed, int64_t env_offset, void* stream);
+
+/* get_feature_vector only (cooking_env.py:352-373): rebuild obs from the current state. */
+int cz_observe(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, void* stream);
+
+/* The reference-facing call with HOST buffers: copies actions host->device, steps, copies
+ * obs/reward/flags device->host, and synchronises the stream before returning.  Scratch
+ * device buffers are owned by the tables object (sized on first use). */
+int cz_step_host(cz_tables* t, uint32_t* state_dev, const uint8_t* actions_host, double* obs_host,
+                 double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                 int n_envs, uint32_t flags, uint64_t seed, int64_t env_offset, void* stream);
+
+/* The counter-based draw used by auto-reset (splitmix64 finaliser over seed, env, episode). */
+uint64_t cz_layout_draw(uint64_t seed, uint64_t global_env, uint64_t episode);
+
+/* Number of kernels launched by this library since load (the bench's gpu_launches claim). */
+uint64_t cz_launch_count(void);
+
+const char* cz_last_error(void);
+int cz_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CZ_B200_H */

@@ -1,0 +1,142 @@
+"""GPU: the CUDA path (through the C ABI) against the golden traces and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.cz_oracle import OracleEnv
+from tests.replay import golden_files, load_golden, assert_state_equal, assert_obs_equal, bits, STATE_KEYS
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(n, cfg, **kw):
+    from cooking_zoo_b200 import BatchedCookingEnv
+    return BatchedCookingEnv(n, cfg["level"], cfg["meta_file"], cfg["num_agents"], cfg["max_steps"],
+                             cfg["recipes"], end_condition_all_dishes=cfg["end_all"],
+                             reward_scheme=cfg["reward_scheme"], **kw)
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_cuda_replays_golden(path):
+    """Lockstep replay of traces recorded from the unmodified reference: bit-exact state,
+    rewards (f64), flags and feature-vector observations (f64)."""
+    g = load_golden(path)
+    cfg = g["config"]
+    n, A = len(g["layouts"]), cfg["num_agents"]
+    env = _make(n, cfg, layouts=g["layouts"])
+    obs = env.reset(layout_ids=np.arange(n)).cpu().numpy()
+    states = env.export_state()
+    for k in range(n):
+        assert_state_equal({key: g[key][k, 0] for key in STATE_KEYS}, states[k], f"{path} trace {k} reset")
+        assert_obs_equal(g["obs"][k, 0], obs[k], f"{path} trace {k} reset")
+    T = g["actions"].shape[1]
+    for t in range(T):
+        live = [k for k in range(n) if t < g["length"][k]]
+        if not live:
+            break
+        for k in live:
+            for i in range(A):
+                if g["teleport"][k, t, i, 0] >= 0:
+                    env.teleport(k, i, *map(int, g["teleport"][k, t, i]))
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(g["actions"][:, t].astype(np.uint8)))
+        obs, rew, term, trunc = obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+        states = env.export_state()
+        for k in live:
+            ctx = f"{path} trace {k} step {t}"
+            assert np.array_equal(bits(g["reward"][k, t]), bits(rew[k])), ctx
+            assert np.array_equal(g["term"][k, t], term[k]), ctx
+            assert np.array_equal(g["trunc"][k, t], trunc[k]), ctx
+            assert_state_equal({key: g[key][k, t + 1] for key in STATE_KEYS}, states[k], ctx)
+            assert_obs_equal(g["obs"][k, t + 1], obs[k], ctx)
+    assert int(env.error_flags.abs().sum()) == 0
+
+
+def _oracle_lockstep(n_envs, check, steps, A, recipes, seed, max_steps=400, end_all=True):
+    cfg = dict(level="coop_test", meta_file="example", num_agents=A, max_steps=max_steps, recipes=recipes,
+               end_all=end_all, reward_scheme=None)
+    env = _make(n_envs, cfg, layout_pool_size=64, layout_seed=seed)
+    lids = np.random.default_rng(seed).integers(0, 64, size=n_envs).astype(np.int32)
+    obs = env.reset(layout_ids=lids).cpu().numpy()
+    picks = np.linspace(0, n_envs - 1, check).astype(int)
+    oracles = {int(k): OracleEnv(env.tables.layouts[lids[k]], recipes, max_steps, end_condition_all_dishes=end_all)
+               for k in picks}
+    for k, orc in oracles.items():
+        assert_obs_equal(np.stack([orc.observe(i) for i in range(A)]), obs[k], f"env {k} reset")
+    rng = np.random.default_rng(seed + 1)
+    prev = np.zeros((n_envs, A), np.uint8)
+    alive = set(oracles)
+    for t in range(steps):
+        act = np.where(rng.random((n_envs, A)) < 0.4, prev, rng.integers(0, 5, size=(n_envs, A))).astype(np.uint8)
+        prev = act
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(act))
+        obs, rew, term, trunc = obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+        st = env.state.cpu()
+        for k in sorted(alive):
+            orc = oracles[k]
+            ctx = f"env {k} step {t}"
+            r, te, tu, _ = orc.step(act[k])
+            assert np.array_equal(bits(r), bits(rew[k])), ctx
+            assert [int(v) for v in te] == list(term[k]) and [int(v) for v in tu] == list(trunc[k]), ctx
+            assert_obs_equal(np.stack([orc.observe(i) for i in range(A)]), obs[k], ctx)
+            if t % 16 == 0 or any(te) or any(tu):
+                assert_state_equal(orc.export_state(), env.export_state(env=k), ctx)
+            if any(te) or any(tu):
+                alive.discard(k)
+    return env
+
+
+def test_cuda_vs_oracle_4096_envs():
+    """BASELINE config 3 shape (4096 two-agent coop_test envs): 96 sampled envs in lockstep with the oracle."""
+    _oracle_lockstep(4096, 96, 120, 2, ["TomatoLettuceSalad", "CarrotBanana"], seed=5)
+
+
+def test_cuda_vs_oracle_ragged_batch():
+    """batch sizes that do not fill a warp / a block, single agent"""
+    for n in (1, 31, 33, 129):
+        _oracle_lockstep(n, min(n, 8), 40, 1, ["TomatoLettuceSalad"], seed=n, end_all=False)
+
+
+def test_observe_is_idempotent_and_matches_step_obs():
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=400,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    env = _make(20000, cfg)
+    env.reset()
+    rng = np.random.default_rng(0)
+    for t in range(30):
+        obs, *_ = env.step(torch.from_numpy(rng.integers(0, 5, size=(20000, 2)).astype(np.uint8)))
+    a = obs.clone()
+    b = env.observe().clone()
+    assert torch.equal(a.view(torch.int64), b.view(torch.int64))
+
+
+def test_auto_reset_and_shard_independence():
+    """truncation -> next step re-initialises from the pool draw cz_layout_draw(seed, env, episode);
+    results do not depend on how the env range is split across devices/processes."""
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=7,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    n = 300
+    whole = _make(n, cfg, auto_reset=True, seed=11, layout_pool_size=32)
+    lo = _make(100, cfg, auto_reset=True, seed=11, layout_pool_size=32)
+    hi = _make(200, cfg, auto_reset=True, seed=11, layout_pool_size=32, env_offset=100)
+    for e in (whole, lo, hi):
+        e.reset()
+    rng = np.random.default_rng(3)
+    P = whole.tables.num_layouts
+    for t in range(20):
+        act = rng.integers(0, 5, size=(n, 2)).astype(np.uint8)
+        o, r, te, tr, info = whole.step(torch.from_numpy(act))
+        o1, r1, te1, tr1, _ = lo.step(torch.from_numpy(act[:100]))
+        o2, r2, te2, tr2, _ = hi.step(torch.from_numpy(act[100:]))
+        assert torch.equal(o.view(torch.int64), torch.cat([o1, o2]).view(torch.int64))
+        assert torch.equal(r.view(torch.int64), torch.cat([r1, r2]).view(torch.int64))
+        assert torch.equal(tr, torch.cat([tr1, tr2])) and torch.equal(te, torch.cat([te1, te2]))
+        tt = info["t"].cpu().numpy()
+        if t % 8 == 6:      # step 7, 15: every env truncates
+            assert tr.all() and (tt == 7).all()
+        if t % 8 == 7:      # the step after: reset obs, zero reward, t == 0
+            assert not tr.any() and (tt == 0).all() and float(r.abs().sum()) == 0.0
+            episode = t // 8 + 1
+            for k in (0, 57, 299):
+                lid = whole.lib.cz_layout_draw(11, k, episode) % P
+                orc = OracleEnv(whole.tables.layouts[lid], cfg["recipes"], 7, end_condition_all_dishes=True)
+                assert_obs_equal(np.stack([orc.observe(i) for i in range(2)]), o[k].cpu().numpy(), f"autoreset env {k}")
