@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the batched CookingZoo step + feature_vector observation path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU baseline arm (oracle port)
+
+One "step" = one cz_step launch advancing every environment of this rank once (each agent acts,
+rewards / termination / truncation computed, every agent's float64 feature vector written).
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): 1 Mi
+two-agent coop_test environments sharded over 8 GPUs = 131072 environments per GPU (weak
+scaling: per-GPU work is fixed), per-environment recipe pairs drawn from the 8-recipe book,
+uniform random actions resident in HBM, max_steps 400 with auto-reset from the layout pool.
+The per-step working set (observations 583 MB + state 19 MB per GPU) is larger than the
+126 MB L2, so no explicit L2 flush is needed between steps.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 131072
+NUM_AGENTS = 2
+MAX_STEPS = 400
+LEVEL, META = "coop_test", "example"
+BOOK = ["TomatoSalad", "TomatoLettuceSalad", "CarrotBanana", "MashedCarrotBanana", "CucumberOnion",
+        "AppleWatermelon", "TomatoLettuceOnionSalad", "no_recipe"]
+METRIC = "env-steps/sec (batched step+feature_vector obs)"
+UNIT = "env-steps/s"
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def workload_config(n_gpus, envs_per_gpu):
+    return {"workload": f"cfg4 shard: {envs_per_gpu} envs/GPU x {n_gpus} GPU, coop_test/example, 2 agents, "
+                        f"per-env recipe pairs from the 8-recipe book, scheme3 uniform random actions, "
+                        f"max_steps {MAX_STEPS}, auto-reset, feature_vector f64 obs",
+            "envs_per_gpu": envs_per_gpu, "num_agents": NUM_AGENTS, "obs_len": 278,
+            "l2": "per-step working set (>600 MB) exceeds the 126 MB L2; no flush needed",
+            "parallelism": f"env-sharded x{n_gpus}, no per-step collective"}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks: sampled with NVML from a thread while the timed region runs
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.stop_flag, self.thread, self.h = [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def stop(self, t0, t1):
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.thread.join()
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        reasons = set()
+        for _, _, rs in inside:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([s[1] for s in inside])) if inside else None,
+                "sm_max_mhz": float(self.max_mhz), "samples": len(inside), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (the reference itself is Python and cannot travel
+# to the GPU box; oracle/cz_oracle.py is its pinned restatement, same language, same structure)
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    wid, n_steps, warm, seed = args
+    import random
+    from oracle.cz_oracle import OracleEnv
+    from cooking_zoo_b200.layout import sample_layout
+    from cooking_zoo_b200.levels import load_level_object, load_meta
+    rng = np.random.default_rng(seed * 1000 + wid)
+    lay_rng = random.Random(seed * 1000 + wid)
+    level, meta = load_level_object(LEVEL), load_meta(META)
+
+    def fresh():
+        rec = [BOOK[int(rng.integers(8))], BOOK[int(rng.integers(8))]]
+        return OracleEnv(sample_layout(level, meta, NUM_AGENTS, lay_rng), rec, MAX_STEPS, end_condition_all_dishes=True)
+
+    env = fresh()
+    acts = rng.integers(0, 5, size=(n_steps + warm, NUM_AGENTS))
+    t0 = None
+    for s in range(n_steps + warm):
+        if s == warm:
+            t0 = time.perf_counter()
+        _, term, trunc, _ = env.step(acts[s])
+        env.observe(0)
+        env.observe(1)
+        if any(term) or any(trunc):
+            env = fresh()
+    return time.perf_counter() - t0
+
+
+def cpu_port_throughput(steps_per_worker, warm, procs=None):
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        t0 = time.perf_counter()
+        times = pool.map(_cpu_worker, [(w, steps_per_worker, warm, 7) for w in range(procs)])
+        wall = time.perf_counter() - t0
+    total = steps_per_worker * procs
+    return total / max(times), procs, wall
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # each "step" = every host core advances its own environment once; bounded so the arm ends in minutes
+    value, procs, wall = cpu_port_throughput(args.steps, args.warmup)
+    ms = 1000.0 * procs / value
+    sample = (f"{procs} processes x ({args.warmup} warm-up + {args.steps} timed) env-steps of the oracle port "
+              f"(oracle/cz_oracle.py), one two-agent coop_test env per process, observe() for both agents")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, ENVS_PER_GPU),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from cooking_zoo_b200 import BatchedCookingEnv
+    from cooking_zoo_b200 import _native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    N, A = args.envs, NUM_AGENTS
+
+    env = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+                            device=str(dev), recipe_pool=BOOK, layout_pool_size=400, layout_seed=0,
+                            auto_reset=True, seed=2026, env_offset=rank * N)
+    L = env.obs_len
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    recipe_ids = torch.randint(0, len(BOOK), (N, 2), generator=g, dtype=torch.uint8)
+    env.reset(recipe_ids=recipe_ids)
+    ring = 16
+    actions = torch.randint(0, 5, (ring, N, A), generator=g, dtype=torch.uint8).to(dev)
+    lib = env.lib
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for s in range(args.warmup):
+        env.step(actions[s % ring])
+    sync_all()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # stats accumulated on device (outside the kernel): episodes finished, recipes completed, return
+    launches0 = lib.cz_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_host0 = time.perf_counter()
+    ev0.record()
+    for s in range(args.steps):
+        env.step(actions[s % ring])
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    t_host1 = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = lib.cz_launch_count() - launches0
+    clocks = sampler.stop(t_host0, t_host1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    ms_per_step = ms_total_max / args.steps
+    value = world * N * args.steps / (ms_total_max / 1e3)
+
+    # optional episode statistics, reduced once with NCCL (not on the per-step path)
+    info = env.info()
+    stats = torch.stack([(env.state[env.tables.num_dyn_slots + A + 5].to(torch.float64)).sum(),
+                         info["recipe_done"].to(torch.float64).sum(), env.reward.sum()])
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+
+    # ---- e2e: the reference-facing call with HOST buffers (cz_step_host), copies inside the timed region
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    h_act = torch.randint(0, 5, (N, A), generator=g, dtype=torch.uint8).pin_memory()
+    h_obs = torch.empty((N, A, L), dtype=torch.float64).pin_memory()
+    h_rew = torch.empty((N, A), dtype=torch.float64).pin_memory()
+    h_term = torch.empty((N, A), dtype=torch.uint8).pin_memory()
+    h_trunc = torch.empty((N, A), dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def host_step():
+        _native.check(lib.cz_step_host(env._handle, env.state.data_ptr(), h_act.data_ptr(), h_obs.data_ptr(),
+                                       h_rew.data_ptr(), h_term.data_ptr(), h_trunc.data_ptr(), N,
+                                       _native.STEP_AUTO_RESET, 2026, rank * N, stream))
+    for _ in range(3):
+        host_step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        host_step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * e2e_steps / (float(te.item()) / 1e3)
+    h2d = N * A
+    d2h = N * A * L * 8 + N * A * 8 + 2 * N * A
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+        state_bytes = env.tables.rows * 4
+        bytes_per_env_step = A * L * 8 + A * 8 + 2 * A + A + 2 * state_bytes
+        achieved = N * bytes_per_env_step / (ms_per_step / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        cpu = None
+        if not args.no_cpu:
+            v, procs, wall = cpu_port_throughput(args.cpu_steps, 200)
+            cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+                   "sample": f"{procs} processes x {args.cpu_steps} env-steps of oracle/cz_oracle.py (Python restatement "
+                             f"of the Python reference), same level/recipes/action distribution, {wall:.1f} s wall"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(world, N),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "bytes_per_env_step": bytes_per_env_step, "kernel": "cz_env_kernel<STEP,TMA>"},
+                "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step)"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "stats": {"episodes_started": float(stats[0]), "recipes_done_now": float(stats[1]),
+                          "last_step_return": float(stats[2])}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-steps", type=int, default=6000, help="oracle env-steps per host process for cpu_baseline")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 6000
+        args.warmup = args.warmup if args.warmup is not None else 200
+        run_reference_arm(args)
+    else:
+        args.steps = args.steps if args.steps is not None else 2000
+        args.warmup = max(3, args.warmup if args.warmup is not None else 50)
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
