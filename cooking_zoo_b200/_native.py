@@ -20,7 +20,9 @@ _P = C.c_void_p
 class TableDesc(C.Structure):
     _fields_ = ([("abi_version", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                  ("num_agents", C.c_int32), ("num_recipes", C.c_int32), ("num_dyn_slots", C.c_int32),
-                 ("num_static_slots", C.c_int32), ("num_types", C.c_int32), ("num_obs_slots", C.c_int32),
+                 ("num_static_slots", C.c_int32), ("num_types", C.c_int32), ("num_comp_slots", C.c_int32),
+                 ("num_obs_segs", C.c_int32), ("num_obs_ranges", C.c_int32), ("obs_table_len", C.c_int32),
+                 ("obs_segs", (C.c_int32 * 3) * 2), ("obs_ranges", (C.c_int32 * 2) * 3),
                  ("obs_len", C.c_int32), ("num_variants", C.c_int32), ("num_layouts", C.c_int32),
                  ("num_book", C.c_int32), ("max_steps", C.c_int32), ("end_all", C.c_int32),
                  ("grace_period", C.c_int32), ("num_switches", C.c_int32), ("num_blocks", C.c_int32),
@@ -28,7 +30,7 @@ class TableDesc(C.Structure):
                  ("reward_time", C.c_double), ("respawn_rate", C.c_double), ("despawn_rate", C.c_double)]
                 + [(n, _P) for n in ("xlut", "ylut", "grid", "static_cells", "scan_order", "special_cells",
                                      "static_masks", "slot_type", "type_flags", "type_base", "type_count",
-                                     "obs_slots", "recipe_nodes", "recipe_len", "pool", "default_recipes")])
+                                     "comp_slots", "obs_table", "recipe_nodes", "recipe_len", "pool", "default_recipes")])
 
 
 # every symbol include/cz_b200.h declares: name -> (restype, argtypes)
@@ -83,7 +85,14 @@ def make_desc(t):
     d.abi_version = ABI_VERSION
     d.width, d.height, d.num_agents, d.num_recipes = t.width, t.height, t.num_agents, t.num_recipes
     d.num_dyn_slots, d.num_static_slots, d.num_types = t.num_dyn_slots, t.num_static_slots, t.num_types
-    d.num_obs_slots, d.obs_len = len(t.obs_slots), t.obs_len
+    d.num_comp_slots, d.obs_len = t.num_comp_slots, t.obs_len
+    d.num_obs_segs, d.num_obs_ranges, d.obs_table_len = t.num_obs_segs, t.num_obs_ranges, t.obs_table_len
+    for k in range(2):
+        for j in range(3):
+            d.obs_segs[k][j] = int(t.obs_segs[k, j])
+    for k in range(3):
+        for j in range(2):
+            d.obs_ranges[k][j] = int(t.obs_ranges[k, j])
     d.num_variants, d.num_layouts, d.num_book = t.num_variants, t.num_layouts, len(t.recipe_names)
     d.max_steps, d.end_all, d.grace_period = t.max_steps, t.end_all, t.grace_period
     d.num_switches, d.num_blocks = t.num_switches, t.num_blocks
@@ -93,7 +102,8 @@ def make_desc(t):
     for name, dtype in (("xlut", np.float64), ("ylut", np.float64), ("grid", np.uint8),
                         ("static_cells", np.uint8), ("scan_order", np.uint8), ("special_cells", np.uint8),
                         ("static_masks", np.uint64), ("slot_type", np.uint8), ("type_flags", np.uint8),
-                        ("type_base", np.uint8), ("type_count", np.uint8), ("obs_slots", np.uint32),
+                        ("type_base", np.uint8), ("type_count", np.uint8), ("comp_slots", np.uint32),
+                        ("obs_table", np.float64),
                         ("recipe_nodes", np.uint32), ("recipe_len", np.uint8), ("pool", np.uint32),
                         ("default_recipes", np.uint8)):
         arr = np.ascontiguousarray(getattr(t, name), dtype=dtype)

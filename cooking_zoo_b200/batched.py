@@ -16,6 +16,25 @@ from . import _native
 from .tables import compile_tables, NUM_MISC, ROW_SBITS, ROW_TINFO, ROW_MARKS, ROW_VARIANT
 
 
+class _LazyInfo:
+    """Mapping view over BatchedCookingEnv.info(): nothing is decoded until a key is read."""
+
+    def __init__(self, env):
+        self._env = env
+
+    def __getitem__(self, key):
+        return self._env.info()[key]
+
+    def keys(self):
+        return ("t", "recipe_done", "active", "error_flags")
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return 4
+
+
 class BatchedCookingEnv:
     def __init__(self, num_envs, level, meta_file, num_agents, max_steps, recipes, agent_visualization=None,
                  obs_spaces=None, end_condition_all_dishes=False, action_scheme="scheme3", render=False,
@@ -58,6 +77,7 @@ class BatchedCookingEnv:
         self.truncated = torch.zeros((N, A), dtype=torch.uint8, device=dev)
         self.error_flags = torch.zeros((N,), dtype=torch.int32, device=dev)
         self._actions = torch.zeros((N, A), dtype=torch.uint8, device=dev)
+        self._info = _LazyInfo(self)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -117,7 +137,7 @@ class BatchedCookingEnv:
                                            self.truncated.data_ptr(), self.error_flags.data_ptr(), self.num_envs,
                                            _native.STEP_AUTO_RESET if self.auto_reset else 0,
                                            self.seed, self.env_offset, self._stream()))
-        return self.obs, self.reward, self.terminated, self.truncated, self.info()
+        return self.obs, self.reward, self.terminated, self.truncated, self._info
 
     def observe(self):
         with torch.cuda.device(self.device):
@@ -126,7 +146,9 @@ class BatchedCookingEnv:
         return self.obs
 
     def info(self):
-        """Lazy views of the info tensors: t[N], recipe_done[N, R], active[N, A]."""
+        """Info tensors decoded from the packed state: t[N], recipe_done[N, R], active[N, A], error_flags[N]
+        (cooking_env.py:248, 329-330).  Decoding launches small torch kernels, so step() returns a lazy
+        mapping (`info["t"]`) instead of calling this on the hot path."""
         t = self.tables
         misc = self.state[t.num_dyn_slots + t.num_agents:]
         agents = self.state[t.num_dyn_slots:t.num_dyn_slots + t.num_agents]

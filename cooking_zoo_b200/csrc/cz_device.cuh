@@ -10,7 +10,11 @@
 
 // ---- device copy of the compiled tables (passed to kernels by value) ------------------
 struct CzDev {
-  int W, H, A, R, D, S, T, n_obs_slots, L, V, P, B, max_steps, end_all, grace, n_switches, n_blocks, rows;
+  int W, H, A, R, D, S, T, L, V, P, B, max_steps, end_all, grace, n_switches, n_blocks, rows;
+  int n_comp, n_segs, n_ranges, tab_len;
+  int segs[2][3];    // table segments of a row: {row offset, length, table offset} (doubles, even)
+  int ranges[3][2];  // computed ranges of a row: {row offset, length}
+  int stage_lo, stage_len;  // span of the computed ranges (what the staging buffer holds)
   double r_node, r_recipe, r_penalty, r_time, respawn, despawn;
   const double* xlut;
   const double* ylut;
@@ -23,7 +27,8 @@ struct CzDev {
   const uint8_t* type_flags;
   const uint8_t* type_base;
   const uint8_t* type_count;
-  const uint32_t* obs_slots;
+  const uint32_t* comp_slots;
+  const double* obs_table;
   const uint32_t* recipe_nodes;
   const uint8_t* recipe_len;
   const uint32_t* pool;

@@ -29,66 +29,77 @@ enum { OBS_TMA = 0, OBS_STG = 1 };
 
 // ---- TMA bulk store helpers (PTX ISA: cp.async.bulk, sm_90+) ------------------------------
 __device__ __forceinline__ void cz_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void cz_bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+__device__ __forceinline__ void cz_bulk_store_nocommit(void* gdst, const void* ssrc, uint32_t bytes) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void cz_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cz_bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-// Fill one observation row (get_feature_vector, cooking_env.py:352-373) into `row` (shared).
-// Lane-per-slot: each lane owns observed slots lane, lane+32, ... and writes that slot's
-// [x, y, flags..., 1] (or zeros for an empty slot) as doubles.
-__device__ __forceinline__ void cz_fill_obs_row(const CzDev& T, const uint32_t* sobj, const uint32_t* sag,
-                                                uint32_t sbits, uint32_t variant, int e, int agent, int lane,
-                                                double* row) {
+// One observation row (get_feature_vector, cooking_env.py:352-373) = table segments + computed slots.
+//
+// Computed slots (dynamic objects, agents, live Switch/Block): one lane per slot writes
+// [x, y, flags..., 1] (or zeros when the slot is empty) as doubles into the staging buffer.
+// The stores are fully unrolled and predicated so lanes with different feature counts do not
+// serialise.  `row` points at staging element 0 == row element T.stage_lo.
+__device__ __forceinline__ void cz_fill_computed(const CzDev& T, const uint32_t* sobj, const uint32_t* sag,
+                                                 uint32_t sbits, uint32_t variant, int e, int agent, int lane,
+                                                 double* row) {
   const uint32_t me = sag[agent * OSTRIDE + e];
   const int ax = me & 7u, ay = (me >> 3) & 7u;
-  for (int q = lane; q < T.n_obs_slots; q += 32) {
-    const uint32_t d = __ldg(T.obs_slots + q);
-    const uint32_t off = d & 0xFFFu, fv = (d >> 12) & 7u, kind = (d >> 15) & 3u, idx = (d >> 17) & 255u;
-    bool present;
-    int x, y;
-    uint32_t fbits;  // features after x, y — bit k = k-th feature, the trailing 1 included
-    int flen;        // number of those features
-    bool self = false;
-    if (kind == 1) {  // dynamic slot
-      uint32_t r = sobj[idx * OSTRIDE + e];
-      present = r & O_PRESENT;
-      x = r & 7u; y = (r >> 3) & 7u;
-      bool chopped = r & O_CHOP, mashed = r & O_MASH;
-      if (fv == FV_ONE) { fbits = 1u; flen = 1; }
-      else if (fv == FV_CHOP) { fbits = (uint32_t)(!chopped) | (uint32_t)chopped << 1 | 4u; flen = 3; }
-      else { fbits = (uint32_t)(!(chopped || mashed)) | (uint32_t)chopped << 1 | (uint32_t)mashed << 2 | 8u; flen = 4; }
-    } else if (kind == 0) {  // static slot
+  for (int q = lane; q < T.n_comp; q += 32) {
+    const uint32_t d = __ldg(T.comp_slots + q);
+    const uint32_t off = d & 0xFFFu, flen = (d >> 12) & 7u, kind = (d >> 15) & 3u, idx = (d >> 17) & 255u;
+    uint32_t rec, fb4;
+    bool present, self = false;
+    if (kind == 1) {  // dynamic object: [!done, chopped, mashed] (world_objects.py:447,555,...)
+      rec = sobj[idx * OSTRIDE + e];
+      present = rec & O_PRESENT;
+      uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+      fb4 = ((c | m) ^ 1u) | c << 1 | m << 2;
+    } else if (kind == 2) {  // agent: one-hot orientation; every agent, active or not (cooking_env.py:356)
+      present = (int)idx < T.A;
+      rec = present ? sag[idx * OSTRIDE + e] : 0u;
+      fb4 = (1u << A_ORI(rec)) >> 1;
+      self = (int)idx == agent;
+    } else {  // live Switch / Block: [switch_active] / [walkable] (world_objects.py:174,221)
       uint32_t cell = __ldg(T.static_cells + variant * T.S + idx);
       present = cell != 0xFFu;
-      x = cell & 7u; y = (cell >> 3) & 7u;
-      fbits = 1u; flen = 1;
-      if (fv == FV_SWITCH || fv == FV_BLOCK) {
-        uint32_t sp = present ? (__ldg(T.grid + variant * 64 + cell) >> 4) : 0u;
-        bool flag = fv == FV_SWITCH ? (sbits & SB_SW_ACTIVE(sp)) : (sbits & SB_BLK_WALK(sp));
-        fbits = (uint32_t)flag | 2u; flen = 2;
-      }
-    } else {  // agent slot: every agent, active or not (cooking_env.py:356)
-      present = (int)idx < T.A;
-      uint32_t r = present ? sag[idx * OSTRIDE + e] : 0u;
-      x = r & 7u; y = (r >> 3) & 7u;
-      uint32_t o = A_ORI(r);
-      fbits = (o >= 1 && o <= 4 ? 1u << (o - 1) : 0u) | 16u; flen = 5;
-      self = (int)idx == agent;
+      rec = present ? cell : 0u;
+      uint32_t g = __ldg(T.grid + variant * 64 + rec);
+      fb4 = ((g & 15u) == ST_SWITCH ? (sbits >> (12 + (g >> 4))) : (sbits >> (16 + (g >> 4)))) & 1u;
     }
-    double* out = row + off;
-    if (present) {
-      // (x - ax) / W as a table of host-divided doubles; the observer's own entry is x / W
-      out[0] = __ldg(T.xlut + (x - (self ? 0 : ax) + T.W - 1));
-      out[1] = __ldg(T.ylut + (y - (self ? 0 : ay) + T.H - 1));
-      for (int k = 0; k < flen; ++k) out[2 + k] = (fbits >> k & 1u) ? 1.0 : 0.0;
-    } else {
-      for (int k = 0; k < flen + 2; ++k) out[k] = 0.0;
+    const int x = rec & 7u, y = (rec >> 3) & 7u;
+    // (x - ax) / W from a table of host-divided doubles; the observer's own entry is x / W (:364-368)
+    double X = __ldg(T.xlut + (x - (self ? 0 : ax) + T.W - 1));
+    double Y = __ldg(T.ylut + (y - (self ? 0 : ay) + T.H - 1));
+    const uint32_t one = 1u << (flen - 1);  // the trailing 1 of every feature vector
+    uint32_t fb = (fb4 & (one - 1u)) | one;
+    if (!present) { X = 0.0; Y = 0.0; fb = 0u; }
+    double* out = row + ((int)off - T.stage_lo);
+    out[0] = X;
+    out[1] = Y;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (k < (int)flen) out[2 + k] = (fb >> k & 1u) ? 1.0 : 0.0;
+  }
+}
+
+// Table segments: runs of static slots depend only on (layout variant, observer cell); copy them
+// from the L1/L2-resident table straight to the row with 128-bit loads and stores.
+__device__ __forceinline__ void cz_copy_table_segments(const CzDev& T, uint32_t variant, uint32_t cell, int lane,
+                                                       double* __restrict__ gdst) {
+  const double* src = T.obs_table + ((size_t)variant * 64 + cell) * T.tab_len;
+#pragma unroll
+  for (int sgi = 0; sgi < 2; ++sgi) {
+    if (sgi < T.n_segs) {
+      const double2* s2 = reinterpret_cast<const double2*>(src + T.segs[sgi][2]);
+      double2* g2 = reinterpret_cast<double2*>(gdst + T.segs[sgi][0]);
+      const int n2 = T.segs[sgi][1] >> 1;
+      for (int k = lane; k < n2; k += 32) g2[k] = __ldg(s2 + k);
     }
   }
 }
@@ -112,8 +123,8 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw) + warp;
-  // staging rows live after the per-warp structs, 2 per warp, 16-byte aligned
-  const size_t row_bytes = ((size_t)T.L * 8 + 15) & ~(size_t)15;
+  // staging rows (the computed span of a row) live after the per-warp structs, 2 per warp, 16-byte aligned
+  const size_t row_bytes = ((size_t)T.stage_len * 8 + 15) & ~(size_t)15;
   unsigned char* stage_base = smem_raw + ((sizeof(WarpSmem) * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15);
   double* stage0 = reinterpret_cast<double*>(stage_base + (size_t)(2 * warp) * row_bytes);
   double* stage1 = reinterpret_cast<double*>(stage_base + (size_t)(2 * warp + 1) * row_bytes);
@@ -216,23 +227,37 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
         double* row = buf ? stage1 : stage0;
         double* gdst = obs + ((size_t)(tile * 32 + le) * A + a) * T.L;
         if (OBS == OBS_TMA) {
-          // the bulk store that last read this buffer (two rows ago) must have drained
+          // the bulk stores that last read this buffer (two rows ago) must have drained
           if (lane == 0) cz_bulk_wait_read<1>();
           __syncwarp();
-          cz_fill_obs_row(T, ws->obj, ws->ag, sb, var, le, a, lane, row);
+          cz_fill_computed(T, ws->obj, ws->ag, sb, var, le, a, lane, row);
           cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
           __syncwarp();
-          if (lane == 0) cz_bulk_store(gdst, row, (uint32_t)(T.L * 8));
-        } else {
-          cz_fill_obs_row(T, ws->obj, ws->ag, sb, var, le, a, lane, row);
-          __syncwarp();
-          if ((T.L & 1) == 0) {  // rows are 16-byte aligned: 128-bit coalesced stores
-            const double2* s2 = reinterpret_cast<const double2*>(row);
-            double2* g2 = reinterpret_cast<double2*>(gdst);
-            for (int k = lane; k < (T.L >> 1); k += 32) g2[k] = s2[k];
-          } else {
-            for (int k = lane; k < T.L; k += 32) gdst[k] = row[k];
+          if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              if (r < T.n_ranges)
+                cz_bulk_store_nocommit(gdst + T.ranges[r][0], row + (T.ranges[r][0] - T.stage_lo), (uint32_t)(T.ranges[r][1] * 8));
+            cz_bulk_commit();
           }
+          cz_copy_table_segments(T, var, A_XY(ws->ag[a * OSTRIDE + le]), lane, gdst);
+        } else {
+          cz_fill_computed(T, ws->obj, ws->ag, sb, var, le, a, lane, row);
+          __syncwarp();
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            if (r < T.n_ranges) {
+              const double* srow = row + (T.ranges[r][0] - T.stage_lo);
+              double* g = gdst + T.ranges[r][0];
+              if ((T.L & 1) == 0) {  // rows and ranges are 16-byte aligned: 128-bit coalesced stores
+                for (int k = lane; k < (T.ranges[r][1] >> 1); k += 32)
+                  reinterpret_cast<double2*>(g)[k] = reinterpret_cast<const double2*>(srow)[k];
+              } else {
+                for (int k = lane; k < T.ranges[r][1]; k += 32) g[k] = srow[k];
+              }
+            }
+          }
+          if ((T.L & 1) == 0) cz_copy_table_segments(T, var, A_XY(ws->ag[a * OSTRIDE + le]), lane, gdst);
           __syncwarp();
         }
         buf ^= 1;
@@ -266,7 +291,7 @@ struct cz_tables {
   int device;
   int obs_path;
   int num_sms;
-  void* allocs[24];
+  void* allocs[32];
   int n_allocs;
   // scratch for cz_step_host
   uint8_t* d_actions; double* d_obs; double* d_reward; uint8_t* d_term; uint8_t* d_trunc;
@@ -287,7 +312,7 @@ static int upload(cz_tables* t, const Tp* host, size_t count, const Tp** out) {
 }
 
 static size_t cz_smem_bytes(const CzDev& T) {
-  size_t row_bytes = ((size_t)T.L * 8 + 15) & ~(size_t)15;
+  size_t row_bytes = ((size_t)T.stage_len * 8 + 15) & ~(size_t)15;
   return ((sizeof(WarpSmem) * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15) + 2 * CZ_WARPS_PER_BLOCK * row_bytes;
 }
 
@@ -330,7 +355,18 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   if (d->obs_len & 1) t->obs_path = OBS_STG;  // bulk copies need 16-byte rows
   CzDev& T = t->dev;
   T.W = d->width; T.H = d->height; T.A = d->num_agents; T.R = d->num_recipes; T.D = d->num_dyn_slots;
-  T.S = d->num_static_slots; T.T = d->num_types; T.n_obs_slots = d->num_obs_slots; T.L = d->obs_len;
+  T.S = d->num_static_slots; T.T = d->num_types; T.L = d->obs_len;
+  T.n_comp = d->num_comp_slots; T.n_segs = d->num_obs_segs; T.n_ranges = d->num_obs_ranges; T.tab_len = d->obs_table_len;
+  if (T.n_segs < 0 || T.n_segs > 2 || T.n_ranges < 0 || T.n_ranges > 3 || T.n_comp < 0 || T.tab_len < 0)
+    { delete t; return cz_fail(CZ_EINVAL, "%s", "bad observation plan"); }
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 3; ++j) T.segs[i][j] = d->obs_segs[i][j];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) T.ranges[i][j] = d->obs_ranges[i][j];
+  T.stage_lo = 0; T.stage_len = 2;
+  if (T.n_ranges > 0) {
+    T.stage_lo = T.ranges[0][0];
+    T.stage_len = T.ranges[T.n_ranges - 1][0] + T.ranges[T.n_ranges - 1][1] - T.stage_lo;
+  }
+  if ((T.L & 1) && T.n_segs > 0) { delete t; return cz_fail(CZ_EINVAL, "%s", "table segments need an even obs_len"); }
   T.V = d->num_variants; T.P = d->num_layouts; T.B = d->num_book; T.max_steps = d->max_steps;
   T.end_all = d->end_all; T.grace = d->grace_period; T.n_switches = d->num_switches; T.n_blocks = d->num_blocks;
   T.rows = T.D + T.A + CZ_NUM_MISC_ROWS;
@@ -349,7 +385,8 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   UP(type_flags, d->type_flags, T.T);
   UP(type_base, d->type_base, T.T);
   UP(type_count, d->type_count, T.T);
-  UP(obs_slots, d->obs_slots, T.n_obs_slots);
+  UP(comp_slots, d->comp_slots, T.n_comp);
+  UP(obs_table, d->obs_table, (size_t)T.V * 64 * T.tab_len);
   UP(recipe_nodes, d->recipe_nodes, (size_t)T.B * CZ_MAX_NODES);
   UP(recipe_len, d->recipe_len, T.B);
   UP(pool, d->pool, (size_t)T.P * T.rows);

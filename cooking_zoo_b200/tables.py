@@ -213,9 +213,109 @@ def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_sche
     t.type_base = np.array(type_base, np.uint8)
     t.type_count = np.array(type_count, np.uint8)
     t.obs_slots = np.array([o | fv << 12 | kind << 15 | idx << 17 for o, fv, kind, idx in obs_slots], np.uint32)
+    _compile_obs_plan(t, obs_slots)
     t.recipe_names = pool_names
     t.recipe_nodes, t.recipe_len = recipe_nodes, recipe_len
     t.default_recipes = np.array([pool_names.index(n) for n in recipes], np.uint8)
     t.pool = pool
     t.static_base = static_base
     return t
+
+
+def _compile_obs_plan(t, obs_slots):
+    """Split an observation row into table segments and computed slots.
+
+    A static slot's features are [(sx-ax)/W, (sy-ay)/H, 1] (world_objects.py:80,123,293,369): a
+    function of the layout variant and the observer's cell only, so whole runs of them are
+    precomputed per (variant, cell) into `obs_table` and copied with 128-bit loads/stores.
+    Block/Switch slots that are empty in every variant are constant zeros and join those runs.
+    Everything else (dynamic objects, agents, live Block/Switch slots) is a "computed" slot:
+    0-11 offset | 12-14 number of features after x,y | 15-16 kind | 17-24 index.
+    """
+    L, V, S = t.obs_len, t.num_variants, t.num_static_slots
+    const = np.zeros(L, bool)          # element comes from the table
+    comp = []
+    for off, fv, kind, idx in obs_slots:
+        n = E.FV_LEN[fv]
+        is_table = kind == 0 and (fv == E.FV_ONE or bool((t.static_cells[:, idx] == 0xFF).all()))
+        if is_table:
+            const[off:off + n] = True
+        else:
+            comp.append((off, n, kind, idx))
+    # maximal runs of table elements, trimmed to 16-byte (2-double) alignment on slot boundaries
+    bounds = sorted({o for o, *_ in obs_slots} | {L})
+    runs, j = [], 0
+    while j < L:
+        if not const[j]:
+            j += 1
+            continue
+        k = j
+        while k < L and const[k]:
+            k += 1
+        a, b = j, k
+        while a < b and a % 2:
+            a = min(x for x in bounds if x > a)
+        while b > a and b % 2:
+            b = max(x for x in bounds if x < b)
+        if b - a >= 2:
+            runs.append((a, b - a))
+        j = k
+    runs = sorted(sorted(runs, key=lambda r: -r[1])[:2]) if L % 2 == 0 else []
+    in_table = np.zeros(L, bool)
+    for a, n in runs:
+        in_table[a:a + n] = True
+    # slots whose elements are not covered by a kept run become computed slots
+    comp = []
+    for off, fv, kind, idx in obs_slots:
+        n = E.FV_LEN[fv]
+        if not in_table[off:off + n].all():
+            assert not in_table[off:off + n].any()
+            comp.append((off, n, kind, idx))
+    # contiguous computed ranges of the row -> one bulk store each
+    ranges, j = [], 0
+    while j < L:
+        if in_table[j]:
+            j += 1
+            continue
+        k = j
+        while k < L and not in_table[k]:
+            k += 1
+        ranges.append((j, k - j))
+        j = k
+    if len(ranges) > 3:
+        raise ValueError("observation layout too fragmented for the row writer")
+    n_tab = sum(n for _, n in runs)
+    table = np.zeros((V, 64, max(n_tab, 2)), np.float64)
+    W, H = t.width, t.height
+    slot_at = {}
+    for off, fv, kind, idx in obs_slots:
+        slot_at[off] = (fv, kind, idx)
+    for v in range(V):
+        for cell in range(64):
+            ax, ay = cell & 7, cell >> 3
+            if ax >= W or ay >= H:
+                continue
+            pos = 0
+            for a, n in runs:
+                for off in range(a, a + n):
+                    if off in slot_at:
+                        fv, kind, idx = slot_at[off]
+                        sc = int(t.static_cells[v, idx])
+                        if sc != 0xFF:
+                            sx, sy = sc & 7, sc >> 3
+                            table[v, cell, pos + off - a:pos + off - a + 3] = ((sx - ax) / W, (sy - ay) / H, 1)
+                pos += n
+    segs = np.zeros((2, 3), np.int32)          # obs start, length, table offset (doubles)
+    pos = 0
+    for k, (a, n) in enumerate(runs):
+        segs[k] = (a, n, pos)
+        pos += n
+    rng_arr = np.zeros((3, 2), np.int32)
+    for k, (a, n) in enumerate(ranges):
+        rng_arr[k] = (a, n)
+    t.obs_table = table
+    t.obs_table_len = max(n_tab, 2)
+    t.obs_segs, t.num_obs_segs = segs, len(runs)
+    t.obs_ranges, t.num_obs_ranges = rng_arr, len(ranges)
+    t.comp_slots = np.array([o | (n - 2) << 12 | kind << 15 | idx << 17 for o, n, kind, idx in comp] or [0], np.uint32)
+    t.num_comp_slots = len(comp)

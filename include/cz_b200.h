@@ -94,7 +94,12 @@ typedef struct cz_table_desc {
   int32_t num_dyn_slots;      /* D */
   int32_t num_static_slots;   /* S: observed static slots (meta order)                      */
   int32_t num_types;          /* dynamic types                                              */
-  int32_t num_obs_slots;      /* entries of obs_slots                                       */
+  int32_t num_comp_slots;     /* entries of comp_slots                                      */
+  int32_t num_obs_segs;       /* table segments of an observation row (0..2)                */
+  int32_t num_obs_ranges;     /* computed ranges of an observation row (1..3)               */
+  int32_t obs_table_len;      /* doubles per (variant, cell) entry of obs_table             */
+  int32_t obs_segs[2][3];     /* {row offset, length, table offset} in doubles, all even    */
+  int32_t obs_ranges[3][2];   /* {row offset, length} of the computed parts of a row        */
   int32_t obs_len;            /* L: doubles per agent observation                           */
   int32_t num_variants;       /* V: distinct static configurations in the layout pool       */
   int32_t num_layouts;        /* P: layout pool size                                        */
@@ -117,7 +122,9 @@ typedef struct cz_table_desc {
   const uint8_t* type_flags;  /* [T] 1 plate | 2 chop | 4 blend | 8 spawn-on-chop           */
   const uint8_t* type_base;   /* [T] first slot of the type                                 */
   const uint8_t* type_count;  /* [T] slots of the type                                      */
-  const uint32_t* obs_slots;  /* [num_obs_slots] 0-11 offset | 12-14 FV layout | 15-16 kind (0 static,1 dynamic,2 agent) | 17-24 index */
+  const uint32_t* comp_slots; /* [num_comp_slots] 0-11 row offset | 12-14 features after x,y |
+                                 15-16 kind (0 static, 1 dynamic, 2 agent) | 17-24 index    */
+  const double* obs_table;    /* [V][64][obs_table_len] static parts of a row per observer cell */
   const uint32_t* recipe_nodes;/* [B][8] 0-7 type | 8 static? | 9-10 cond | 16-23 children  */
   const uint8_t* recipe_len;  /* [B] nodes in the recipe                                    */
   const uint32_t* pool;       /* [P][rows] initial state of every pooled layout             */
