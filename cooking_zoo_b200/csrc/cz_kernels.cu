@@ -23,9 +23,17 @@
 
 #define CZ_WARPS_PER_BLOCK 4
 #define CZ_THREADS (32 * CZ_WARPS_PER_BLOCK)
+#define CZ_MIN_BLOCKS 7  // 28 warps/SM: registers capped at 72, shared memory at 32 KB per block
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
 enum { OBS_TMA = 0, OBS_STG = 1 };
+
+// ---- Ampere-style async copies (LDGSTS) for the 4-byte state words -------------------------
+__device__ __forceinline__ void cz_cp_async4(void* sdst, const void* gsrc) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cz_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- TMA bulk store helpers (PTX ISA: cp.async.bulk, sm_90+) ------------------------------
 __device__ __forceinline__ void cz_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -33,88 +41,109 @@ __device__ __forceinline__ void cz_bulk_store_nocommit(void* gdst, const void* s
   uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cz_bulk_store_s(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cz_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cz_bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-// One observation row (get_feature_vector, cooking_env.py:352-373) = table segments + computed slots.
+// ---- observation rows (get_feature_vector, cooking_env.py:352-373) -----------------------------
+// A row = table segments (static slots: a function of layout variant and observer cell only, copied
+// from the L1/L2-resident obs_table with 128-bit loads/stores) + computed slots (dynamic objects,
+// agents, live Switch/Block) that one lane each writes as [x, y, flags..., 1] doubles into the
+// shared-memory staging rows, which the TMA engine then stores (cp.async.bulk).
 //
-// Computed slots (dynamic objects, agents, live Switch/Block): one lane per slot writes
-// [x, y, flags..., 1] (or zeros when the slot is empty) as doubles into the staging buffer.
-// The stores are fully unrolled and predicated so lanes with different feature counts do not
-// serialise.  `row` points at staging element 0 == row element T.stage_lo.
-__device__ __forceinline__ void cz_fill_computed(const CzDev& T, const uint32_t* sobj, const uint32_t* sag,
-                                                 uint32_t sbits, uint32_t variant, int e, int agent, int lane,
-                                                 double* row) {
-  const uint32_t me = sag[agent * OSTRIDE + e];
-  const int ax = me & 7u, ay = (me >> 3) & 7u;
-  for (int q = lane; q < T.n_comp; q += 32) {
+// Everything that does not change from row to row is decoded once per kernel into LaneSlot.
+struct LaneSlot {
+  int off;        // staging offset (doubles) of the slot owned by this lane, < 0: lane idle
+  uint32_t flen;  // features after x, y (the trailing 1 included)
+  uint32_t kind;  // 0 live static (Switch/Block), 1 dynamic object, 2 agent
+  uint32_t idx;   // static slot / dynamic slot / agent index
+  int t0, t1;     // destination (in double2 units, relative to the row) of table elements lane, lane+32
+};
+
+__device__ __forceinline__ LaneSlot cz_lane_slot(const CzDev& T, int q, int lane) {
+  LaneSlot ls;
+  ls.off = -1; ls.flen = 1; ls.kind = 1; ls.idx = 0;
+  if (q < T.n_comp) {
     const uint32_t d = __ldg(T.comp_slots + q);
-    const uint32_t off = d & 0xFFFu, flen = (d >> 12) & 7u, kind = (d >> 15) & 3u, idx = (d >> 17) & 255u;
-    uint32_t rec, fb4;
-    bool present, self = false;
-    if (kind == 1) {  // dynamic object: [!done, chopped, mashed] (world_objects.py:447,555,...)
-      rec = sobj[idx * OSTRIDE + e];
-      present = rec & O_PRESENT;
-      uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
-      fb4 = ((c | m) ^ 1u) | c << 1 | m << 2;
-    } else if (kind == 2) {  // agent: one-hot orientation; every agent, active or not (cooking_env.py:356)
-      present = (int)idx < T.A;
-      rec = present ? sag[idx * OSTRIDE + e] : 0u;
-      fb4 = (1u << A_ORI(rec)) >> 1;
-      self = (int)idx == agent;
-    } else {  // live Switch / Block: [switch_active] / [walkable] (world_objects.py:174,221)
-      uint32_t cell = __ldg(T.static_cells + variant * T.S + idx);
-      present = cell != 0xFFu;
-      rec = present ? cell : 0u;
-      uint32_t g = __ldg(T.grid + variant * 64 + rec);
-      fb4 = ((g & 15u) == ST_SWITCH ? (sbits >> (12 + (g >> 4))) : (sbits >> (16 + (g >> 4)))) & 1u;
-    }
-    const int x = rec & 7u, y = (rec >> 3) & 7u;
-    // (x - ax) / W from a table of host-divided doubles; the observer's own entry is x / W (:364-368)
-    double X = __ldg(T.xlut + (x - (self ? 0 : ax) + T.W - 1));
-    double Y = __ldg(T.ylut + (y - (self ? 0 : ay) + T.H - 1));
-    const uint32_t one = 1u << (flen - 1);  // the trailing 1 of every feature vector
-    uint32_t fb = (fb4 & (one - 1u)) | one;
-    if (!present) { X = 0.0; Y = 0.0; fb = 0u; }
-    double* out = row + ((int)off - T.stage_lo);
-    out[0] = X;
-    out[1] = Y;
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-      if (k < (int)flen) out[2 + k] = (fb >> k & 1u) ? 1.0 : 0.0;
+    ls.off = (int)(d & 0xFFFu) - T.stage_lo;
+    ls.flen = (d >> 12) & 7u; ls.kind = (d >> 15) & 3u; ls.idx = (d >> 17) & 255u;
   }
+  // table element k (double2 units) -> row position: segment 0 first, then segment 1
+  const int n0 = T.n_segs > 0 ? T.segs[0][1] >> 1 : 0, n1 = T.n_segs > 1 ? T.segs[1][1] >> 1 : 0;
+  ls.t0 = ls.t1 = -1;
+  int k = lane;
+  if (k < n0) ls.t0 = (T.segs[0][0] >> 1) + k; else if (k < n0 + n1) ls.t0 = (T.segs[1][0] >> 1) + k - n0;
+  k = lane + 32;
+  if (k < n0) ls.t1 = (T.segs[0][0] >> 1) + k; else if (k < n0 + n1) ls.t1 = (T.segs[1][0] >> 1) + k - n0;
+  return ls;
 }
 
-// Table segments: runs of static slots depend only on (layout variant, observer cell); copy them
-// from the L1/L2-resident table straight to the row with 128-bit loads and stores.
-__device__ __forceinline__ void cz_copy_table_segments(const CzDev& T, uint32_t variant, uint32_t cell, int lane,
-                                                       double* __restrict__ gdst) {
-  const double* src = T.obs_table + ((size_t)variant * 64 + cell) * T.tab_len;
-#pragma unroll
-  for (int sgi = 0; sgi < 2; ++sgi) {
-    if (sgi < T.n_segs) {
-      const double2* s2 = reinterpret_cast<const double2*>(src + T.segs[sgi][2]);
-      double2* g2 = reinterpret_cast<double2*>(gdst + T.segs[sgi][0]);
-      const int n2 = T.segs[sgi][1] >> 1;
-      for (int k = lane; k < n2; k += 32) g2[k] = __ldg(s2 + k);
-    }
+// Agent-independent part of a computed slot: record (x | y<<3 in the low bits), presence, feature bits.
+__device__ __forceinline__ void cz_slot_state(const CzDev& T, const LaneSlot& ls, const uint32_t* sobj,
+                                              const uint32_t* sag, uint32_t sbits, uint32_t variant, int e,
+                                              uint32_t& xy, uint32_t& fb) {
+  uint32_t rec, fb4;
+  bool present;
+  if (ls.kind == 1) {  // dynamic object: [!done, chopped, mashed] (world_objects.py:447,555,...)
+    rec = sobj[ls.idx * OSTRIDE + e];
+    present = rec & O_PRESENT;
+    uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+    fb4 = ((c | m) ^ 1u) | c << 1 | m << 2;
+  } else if (ls.kind == 2) {  // agent: one-hot orientation; every agent, active or not (cooking_env.py:356)
+    present = (int)ls.idx < T.A;
+    rec = present ? sag[ls.idx * OSTRIDE + e] : 0u;
+    fb4 = (1u << A_ORI(rec)) >> 1;
+  } else {  // live Switch / Block: [switch_active] / [walkable] (world_objects.py:174,221)
+    uint32_t cell = __ldg(T.static_cells + variant * T.S + ls.idx);
+    present = cell != 0xFFu;
+    rec = present ? cell : 0u;
+    uint32_t g = __ldg(T.grid + variant * 64 + rec);
+    fb4 = ((g & 15u) == ST_SWITCH ? (sbits >> (12 + (g >> 4))) : (sbits >> (16 + (g >> 4)))) & 1u;
   }
+  const uint32_t one = 1u << (ls.flen - 1);  // the trailing 1 of every feature vector
+  fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
+  xy = (rec & 63u) | (present ? 64u : 0u);
+}
+
+// Observer-dependent part: (x - ax) / W, (y - ay) / H from shared tables of host-divided doubles
+// (the observer's own entry is x / W, y / H: cooking_env.py:364-368), then the flags.
+__device__ __forceinline__ void cz_slot_store(const LaneSlot& ls, uint32_t xy, uint32_t fb, int ax, int ay, bool self,
+                                              const double* sxl, const double* syl, double* row) {
+  const int x = xy & 7u, y = (xy >> 3) & 7u;
+  double X = sxl[x - (self ? 0 : ax)];
+  double Y = syl[y - (self ? 0 : ay)];
+  if (!(xy & 64u)) { X = 0.0; Y = 0.0; }
+  double* out = row + ls.off;
+  out[0] = X;
+  out[1] = Y;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+    if (k < (int)ls.flen) out[2 + k] = (fb >> k & 1u) ? 1.0 : 0.0;
 }
 
 // shared-memory layout of one warp
-struct WarpSmem {
-  uint32_t obj[CZ_MAX_DYN * OSTRIDE];
-  uint32_t ag[CZ_MAX_AGENTS * OSTRIDE];
-  uint32_t sbits[32];
-  uint32_t variant[32];
-  uint32_t wobs[32];
+struct BlockSmem {
+  double xlut[16];  // k / W for k = -(W-1)..W-1, centred at index W-1
+  double ylut[16];
 };
+// per-warp words: object columns [D][33], agent columns [A][33], then sbits/variant/wobs [32] and misc [6][32]
+struct WarpSmem {
+  uint32_t* obj;
+  uint32_t* ag;
+  uint32_t* sbits;
+  uint32_t* variant;
+  uint32_t* wobs;
+  uint32_t* misc;
+};
+__host__ __device__ inline size_t cz_warp_words(int D, int A) { return (size_t)(D + A) * OSTRIDE + 32 * (3 + CZ_NUM_MISC_ROWS); }
 
-template <int MODE, int OBS>
-__global__ void __launch_bounds__(CZ_THREADS)
+template <int MODE, int OBS, bool SIMPLE>
+__global__ void __launch_bounds__(CZ_THREADS, CZ_MIN_BLOCKS)
 cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __restrict__ actions,
               const int32_t* __restrict__ layout_ids, const uint8_t* __restrict__ recipe_ids,
               const uint8_t* __restrict__ mask, double* __restrict__ obs, double* __restrict__ reward,
@@ -122,12 +151,36 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
               int n_envs, uint32_t flags, uint64_t seed, int64_t env_offset) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpSmem* ws = reinterpret_cast<WarpSmem*>(smem_raw) + warp;
-  // staging rows (the computed span of a row) live after the per-warp structs, 2 per warp, 16-byte aligned
+  BlockSmem* bs = reinterpret_cast<BlockSmem*>(smem_raw);
+  WarpSmem wsv;
+  WarpSmem* ws = &wsv;
+  {
+    uint32_t* base = reinterpret_cast<uint32_t*>(smem_raw + sizeof(BlockSmem)) + (size_t)warp * cz_warp_words(T.D, T.A);
+    wsv.obj = base;
+    wsv.ag = base + T.D * OSTRIDE;
+    wsv.sbits = wsv.ag + T.A * OSTRIDE;
+    wsv.variant = wsv.sbits + 32;
+    wsv.wobs = wsv.variant + 32;
+    wsv.misc = wsv.wobs + 32;
+  }
+  // staging (the computed span of A rows) lives after the per-warp words, 16-byte aligned
   const size_t row_bytes = ((size_t)T.stage_len * 8 + 15) & ~(size_t)15;
-  unsigned char* stage_base = smem_raw + ((sizeof(WarpSmem) * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15);
-  double* stage0 = reinterpret_cast<double*>(stage_base + (size_t)(2 * warp) * row_bytes);
-  double* stage1 = reinterpret_cast<double*>(stage_base + (size_t)(2 * warp + 1) * row_bytes);
+  unsigned char* stage_base = smem_raw + ((sizeof(BlockSmem) + cz_warp_words(T.D, T.A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15);
+  double* stage = reinterpret_cast<double*>(stage_base + (size_t)warp * T.A * row_bytes);
+  const int row_stride = (int)(row_bytes >> 3);
+  if (threadIdx.x < 2 * T.W - 1) bs->xlut[threadIdx.x] = __ldg(T.xlut + threadIdx.x);
+  if (threadIdx.x < 2 * T.H - 1) bs->ylut[threadIdx.x] = __ldg(T.ylut + threadIdx.x);
+  __syncthreads();
+  const double* sxl = bs->xlut + (T.W - 1);
+  const double* syl = bs->ylut + (T.H - 1);
+  const LaneSlot ls = cz_lane_slot(T, lane, lane);
+  // loop invariants of the observation phase
+  const int tab2 = T.tab_len >> 1, L2 = T.L >> 1;
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  const size_t row_gbytes = (size_t)T.L * 8;
+  const uint32_t r0_bytes = (uint32_t)T.ranges[0][1] * 8;
+  const size_t r0_goff = (size_t)T.ranges[0][0] * 8;
+  const uint32_t r0_soff = (uint32_t)(T.ranges[0][0] - T.stage_lo) * 8;
 
   const int n_tiles = (n_envs + 31) >> 5;
   const int warps_total = gridDim.x * CZ_WARPS_PER_BLOCK;
@@ -145,14 +198,17 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
     bool write_obs = valid;
     if (valid) {
       // ---- phase 1: state -> shared columns (coalesced: consecutive lanes, consecutive words)
-      for (int s = 0; s < D; ++s) e.o[s * OSTRIDE] = state[(size_t)s * N + env];
-      for (int i = 0; i < A; ++i) e.ag[i * OSTRIDE] = state[(size_t)(D + i) * N + env];
-      e.sbits = misc[(size_t)CZ_ROW_SBITS * N + env];
-      e.tinfo = misc[(size_t)CZ_ROW_TINFO * N + env];
-      e.marks = misc[(size_t)CZ_ROW_MARKS * N + env];
-      e.variant = misc[(size_t)CZ_ROW_VARIANT * N + env];
-      e.rids = misc[(size_t)CZ_ROW_RECIPES * N + env];
-      e.episode = misc[(size_t)CZ_ROW_EPISODE * N + env];
+      // all words of the environment in flight at once (LDGSTS), one wait
+      for (int s = 0; s < D; ++s) cz_cp_async4(e.o + s * OSTRIDE, state + (size_t)s * N + env);
+      for (int i = 0; i < A; ++i) cz_cp_async4(e.ag + i * OSTRIDE, state + (size_t)(D + i) * N + env);
+      for (int m = 0; m < CZ_NUM_MISC_ROWS; ++m) cz_cp_async4(ws->misc + m * 32 + lane, misc + (size_t)m * N + env);
+      cz_cp_async_wait_all();
+      e.sbits = ws->misc[CZ_ROW_SBITS * 32 + lane];
+      e.tinfo = ws->misc[CZ_ROW_TINFO * 32 + lane];
+      e.marks = ws->misc[CZ_ROW_MARKS * 32 + lane];
+      e.variant = ws->misc[CZ_ROW_VARIANT * 32 + lane];
+      e.rids = ws->misc[CZ_ROW_RECIPES * 32 + lane];
+      e.episode = ws->misc[CZ_ROW_EPISODE * 32 + lane];
 
       bool do_reset = false;
       int layout = 0;
@@ -217,50 +273,84 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
     ws->wobs[lane] = write_obs ? 1u : 0u;
     __syncwarp();
 
-    // ---- phase 4: observation rows, one (environment, agent) at a time, whole warp
-    int buf = 0;
+    // ---- phase 4: observation rows of the tile, one environment (A rows) at a time, whole warp
     const int n_here = min(32, n_envs - tile * 32);
-    for (int le = 0; le < n_here; ++le) {
+    double* genv = obs + (size_t)tile * 32 * A * T.L;
+    const size_t env_doubles = (size_t)A * T.L;
+#pragma unroll 1
+    for (int le = 0; le < n_here; ++le, genv += env_doubles) {
       if (!ws->wobs[le]) continue;
       const uint32_t sb = ws->sbits[le], var = ws->variant[le];
-      for (int a = 0; a < A; ++a) {
-        double* row = buf ? stage1 : stage0;
-        double* gdst = obs + ((size_t)(tile * 32 + le) * A + a) * T.L;
-        if (OBS == OBS_TMA) {
-          // the bulk stores that last read this buffer (two rows ago) must have drained
-          if (lane == 0) cz_bulk_wait_read<1>();
-          __syncwarp();
-          cz_fill_computed(T, ws->obj, ws->ag, sb, var, le, a, lane, row);
-          cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
-          __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-              if (r < T.n_ranges)
-                cz_bulk_store_nocommit(gdst + T.ranges[r][0], row + (T.ranges[r][0] - T.stage_lo), (uint32_t)(T.ranges[r][1] * 8));
-            cz_bulk_commit();
+      uint32_t xy = 0, fb = 0;
+      if (ls.off >= 0) cz_slot_state(T, ls, ws->obj, ws->ag, sb, var, le, xy, fb);
+      const double2* tab = reinterpret_cast<const double2*>(T.obs_table) + (size_t)var * 64 * tab2;
+      if (OBS == OBS_TMA) {
+        // the bulk stores of the previous environment must have finished reading the staging rows
+        if (lane == 0) cz_bulk_wait_read<0>();
+        __syncwarp();
+      }
+      double* row = stage;
+      double2* g2 = reinterpret_cast<double2*>(genv);
+#pragma unroll 1
+      for (int a = 0; a < A; ++a, row += row_stride, g2 += L2) {
+        const uint32_t me = ws->ag[a * OSTRIDE + le];
+        // table segments of this row: loads issued first, the fill below hides their latency
+        const double2* src = tab + (me & 63u) * tab2 + lane;
+        double2 v0, v1;
+        if (ls.t0 >= 0) v0 = __ldg(src);
+        if (ls.t1 >= 0) v1 = __ldg(src + 32);
+        if (ls.off >= 0)
+          cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, ls.kind == 2 && (int)ls.idx == a, sxl, syl, row);
+        if (!SIMPLE) {
+          for (int q = lane + 32; q < T.n_comp; q += 32) {  // more than 32 computed slots: extra passes
+            const LaneSlot l2 = cz_lane_slot(T, q, lane);
+            uint32_t xy2, fb2;
+            cz_slot_state(T, l2, ws->obj, ws->ag, sb, var, le, xy2, fb2);
+            cz_slot_store(l2, xy2, fb2, me & 7u, (me >> 3) & 7u, l2.kind == 2 && (int)l2.idx == a, sxl, syl, row);
           }
-          cz_copy_table_segments(T, var, A_XY(ws->ag[a * OSTRIDE + le]), lane, gdst);
-        } else {
-          cz_fill_computed(T, ws->obj, ws->ag, sb, var, le, a, lane, row);
-          __syncwarp();
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            if (r < T.n_ranges) {
-              const double* srow = row + (T.ranges[r][0] - T.stage_lo);
-              double* g = gdst + T.ranges[r][0];
-              if ((T.L & 1) == 0) {  // rows and ranges are 16-byte aligned: 128-bit coalesced stores
-                for (int k = lane; k < (T.ranges[r][1] >> 1); k += 32)
-                  reinterpret_cast<double2*>(g)[k] = reinterpret_cast<const double2*>(srow)[k];
-              } else {
-                for (int k = lane; k < T.ranges[r][1]; k += 32) g[k] = srow[k];
-              }
+        }
+        if (ls.t0 >= 0) g2[ls.t0] = v0;
+        if (ls.t1 >= 0) g2[ls.t1] = v1;
+        if (!SIMPLE) {
+          for (int k = lane + 64; k < tab2; k += 32) {  // table rows longer than 64 double2
+            const int n0 = T.segs[0][1] >> 1;
+            g2[k < n0 ? (T.segs[0][0] >> 1) + k : (T.segs[1][0] >> 1) + k - n0] = __ldg(src + k - lane);
+          }
+        }
+      }
+      if (OBS == OBS_TMA) {
+        cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) {
+          // one elected lane hands the computed range(s) of the A rows to the TMA engine
+          char* gp = reinterpret_cast<char*>(genv) + r0_goff;
+          uint32_t sp = stage_s + r0_soff;
+#pragma unroll 1
+          for (int a = 0; a < A; ++a, gp += row_gbytes, sp += (uint32_t)row_bytes) {
+            cz_bulk_store_s(gp, sp, r0_bytes);
+            if (!SIMPLE) {
+              for (int r = 1; r < T.n_ranges; ++r)
+                cz_bulk_store_s(gp + (T.ranges[r][0] - T.ranges[0][0]) * 8, sp + (T.ranges[r][0] - T.ranges[0][0]) * 8,
+                                (uint32_t)T.ranges[r][1] * 8);
             }
           }
-          if ((T.L & 1) == 0) cz_copy_table_segments(T, var, A_XY(ws->ag[a * OSTRIDE + le]), lane, gdst);
-          __syncwarp();
+          cz_bulk_commit();
         }
-        buf ^= 1;
+      } else {
+        __syncwarp();
+        for (int a = 0; a < A; ++a) {
+          for (int r = 0; r < T.n_ranges; ++r) {
+            const double* srow = stage + a * row_stride + (T.ranges[r][0] - T.stage_lo);
+            double* g = genv + (size_t)a * T.L + T.ranges[r][0];
+            if ((T.L & 1) == 0) {  // rows and ranges are 16-byte aligned: 128-bit coalesced stores
+              for (int k = lane; k < (T.ranges[r][1] >> 1); k += 32)
+                reinterpret_cast<double2*>(g)[k] = reinterpret_cast<const double2*>(srow)[k];
+            } else {
+              for (int k = lane; k < T.ranges[r][1]; k += 32) g[k] = srow[k];
+            }
+          }
+        }
+        __syncwarp();
       }
     }
     if (OBS == OBS_TMA) {
@@ -290,6 +380,7 @@ struct cz_tables {
   CzDev dev;
   int device;
   int obs_path;
+  int simple;
   int num_sms;
   void* allocs[32];
   int n_allocs;
@@ -313,7 +404,8 @@ static int upload(cz_tables* t, const Tp* host, size_t count, const Tp** out) {
 
 static size_t cz_smem_bytes(const CzDev& T) {
   size_t row_bytes = ((size_t)T.stage_len * 8 + 15) & ~(size_t)15;
-  return ((sizeof(WarpSmem) * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15) + 2 * CZ_WARPS_PER_BLOCK * row_bytes;
+  return ((sizeof(BlockSmem) + cz_warp_words(T.D, T.A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15) +
+         (size_t)CZ_WARPS_PER_BLOCK * T.A * row_bytes;
 }
 
 extern "C" int cz_abi_version(void) { return CZ_ABI_VERSION; }
@@ -395,7 +487,11 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   if (rc != CZ_OK) { cz_tables_destroy(t); return rc; }
   size_t smem = cz_smem_bytes(T);
   if (smem > (size_t)prop.sharedMemPerBlockOptin) { cz_tables_destroy(t); return cz_fail(CZ_ELIMIT, "%s", "obs_len too large for shared memory staging"); }
-#define SET_SMEM(M, O) CZ_CUDA(cudaFuncSetAttribute(cz_env_kernel<M, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+  // the specialised row writer: one lane per computed slot, one computed range, two table loads per lane
+  t->simple = T.n_comp <= 32 && T.n_ranges == 1 && T.tab_len <= 128 && (T.L & 1) == 0;
+#define SET_SMEM(M, O) \
+  CZ_CUDA(cudaFuncSetAttribute(cz_env_kernel<M, O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+  CZ_CUDA(cudaFuncSetAttribute(cz_env_kernel<M, O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
   SET_SMEM(MODE_STEP, OBS_TMA); SET_SMEM(MODE_STEP, OBS_STG);
   SET_SMEM(MODE_RESET, OBS_TMA); SET_SMEM(MODE_RESET, OBS_STG);
   SET_SMEM(MODE_OBSERVE, OBS_TMA); SET_SMEM(MODE_OBSERVE, OBS_STG);
@@ -437,12 +533,12 @@ static int cz_launch(const cz_tables* t, uint32_t* state, const uint8_t* actions
   size_t smem = cz_smem_bytes(t->dev);
   int grid = cz_grid(t, n_envs);
   cudaStream_t s = (cudaStream_t)stream;
-  if (t->obs_path == OBS_TMA)
-    cz_env_kernel<MODE, OBS_TMA><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, actions, layout_ids, recipe_ids, mask, obs,
-                                                               reward, term, trunc, err, n_envs, flags, seed, env_offset);
-  else
-    cz_env_kernel<MODE, OBS_STG><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, actions, layout_ids, recipe_ids, mask, obs,
-                                                               reward, term, trunc, err, n_envs, flags, seed, env_offset);
+#define CZ_GO(O, S)                                                                                                  \
+  cz_env_kernel<MODE, O, S><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, actions, layout_ids, recipe_ids, mask, obs, \
+                                                          reward, term, trunc, err, n_envs, flags, seed, env_offset)
+  if (t->obs_path == OBS_TMA) { if (t->simple) CZ_GO(OBS_TMA, true); else CZ_GO(OBS_TMA, false); }
+  else { if (t->simple) CZ_GO(OBS_STG, true); else CZ_GO(OBS_STG, false); }
+#undef CZ_GO
   g_launches.fetch_add(1);
   CZ_CUDA(cudaGetLastError());
   return CZ_OK;
