@@ -168,28 +168,31 @@ class BatchedCookingEnv:
         t = self.tables
         st = self.state.cpu().numpy().astype(np.uint32)
         D, A, W = t.num_dyn_slots, t.num_agents, t.width
+        canon = t.canon_of_dev          # device slots are the compacted live slots (tables.py)
         envs = range(self.num_envs) if env is None else [env]
         out = []
         for e in envs:
             o = st[:D, e]
-            objs = np.zeros((D, 9), np.int16)
+            live = np.zeros((D, 9), np.int16)
             pres = (o >> 6) & 1
             ck = (o >> 10) & 3
             cid = (o >> 12) & 31
             x, y = o & 7, (o >> 3) & 7
-            objs[:, 0] = pres
-            objs[:, 1], objs[:, 2] = x, y
-            objs[:, 3] = (o >> 7) & 1
-            objs[:, 4] = ((o >> 8) & 1) * 2
-            objs[:, 5] = (o >> 9) & 1
-            objs[:, 6] = ck
-            objs[:, 7] = np.where(ck == 1, y * W + x, cid)
-            objs[:, 8] = (o >> 17) & 63
-            objs[pres == 0] = 0
+            live[:, 0] = pres
+            live[:, 1], live[:, 2] = x, y
+            live[:, 3] = (o >> 7) & 1
+            live[:, 4] = ((o >> 8) & 1) * 2
+            live[:, 5] = (o >> 9) & 1
+            live[:, 6] = ck
+            live[:, 7] = np.where(ck == 1, y * W + x, np.where(ck == 2, canon[np.minimum(cid, D - 1)], cid))
+            live[:, 8] = (o >> 17) & 63
+            live[pres == 0] = 0
+            objs = np.zeros((t.num_canon_slots, 9), np.int16)
+            objs[canon] = live
             a = st[D:D + A, e]
             agents = np.zeros((A, 6), np.int16)
             agents[:, 0], agents[:, 1], agents[:, 2] = a & 7, (a >> 3) & 7, (a >> 6) & 7
-            agents[:, 3] = np.where((a >> 9) & 1, (a >> 10) & 31, -1)
+            agents[:, 3] = np.where((a >> 9) & 1, canon[np.minimum((a >> 10) & 31, D - 1)], -1)
             agents[:, 4], agents[:, 5] = (a >> 15) & 1, a >> 16
             misc = st[D + A:, e]
             sb, var = int(misc[ROW_SBITS]), int(misc[ROW_VARIANT])

@@ -26,7 +26,8 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB, SRC]
+    extra = os.environ.get("CZ_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", LIB, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

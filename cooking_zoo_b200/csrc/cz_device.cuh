@@ -33,6 +33,27 @@ struct CzDev {
   const uint8_t* recipe_len;
   const uint32_t* pool;
   const uint8_t* default_recipes;
+  const void* blob;  // BlockSmem image (LUTs + SmemTabs), built by cz_tables_create
+};
+
+// Small lookup tables staged in shared memory by every block (with 214 KB of shared memory in
+// use the L1 is only ~14 KB, so a __ldg of these is an L2 round trip in the middle of a
+// dependent chain).  Kernels instantiated with FAST=true require V <= CZ_SV and B <= CZ_SB and
+// read the shared copy; FAST=false reads global memory.
+#define CZ_SV 4
+#define CZ_SB 16
+struct SmemTabs {
+  uint64_t static_masks[CZ_SV][8];
+  uint32_t recipe_nodes[CZ_SB][CZ_MAX_NODES];
+  uint8_t grid[CZ_SV][64];
+  uint8_t scan_order[CZ_SV][CZ_MAX_DYN];
+  uint8_t special_cells[CZ_SV][4 * CZ_MAX_SPECIAL];
+  uint8_t static_cells[CZ_SV][CZ_MAX_STATIC_SLOTS];
+  uint8_t slot_tf[CZ_MAX_DYN];  // type_flags[slot_type[s]]
+  uint8_t slot_type[CZ_MAX_DYN];
+  uint8_t type_base[CZ_MAX_TYPES];
+  uint8_t type_count[CZ_MAX_TYPES];
+  uint8_t recipe_len[CZ_SB];
 };
 
 // static kinds (grid low nibble) — cooking_zoo_b200/entities.py ST_*
@@ -74,12 +95,27 @@ enum { FV_NONE = 0, FV_ONE, FV_CHOP, FV_CHOPBLEND, FV_AGENT, FV_SWITCH, FV_BLOCK
 #define TI_DONE (1u << 20)
 #define TI_NLIVE(x) (((x) >> 21) & 7u)
 
+#define TAB_GRID(v, c) (FAST ? (uint32_t)st->grid[v][c] : (uint32_t)__ldg(T.grid + (v) * 64 + (c)))
+#define TAB_SCAN(v, k) (FAST ? (uint32_t)st->scan_order[v][k] : (uint32_t)__ldg(T.scan_order + (v) * T.D + (k)))
+#define TAB_SPECIAL(v, kind, k) \
+  (FAST ? (uint32_t)st->special_cells[v][(kind) * CZ_MAX_SPECIAL + (k)] \
+               : (uint32_t)__ldg(T.special_cells + ((v) * 4 + (kind)) * CZ_MAX_SPECIAL + (k)))
+#define TAB_SCELL(v, i) (FAST ? (uint32_t)st->static_cells[v][i] : (uint32_t)__ldg(T.static_cells + (v) * T.S + (i)))
+#define TAB_SMASK(v, k) (FAST ? st->static_masks[v][k] : __ldg(T.static_masks + (v) * 8 + (k)))
+#define TAB_RNODE(b, k) (FAST ? st->recipe_nodes[b][k] : __ldg(T.recipe_nodes + (b) * CZ_MAX_NODES + (k)))
+#define TAB_RLEN(b) (FAST ? (uint32_t)st->recipe_len[b] : (uint32_t)__ldg(T.recipe_len + (b)))
+#define TAB_TF(s) (FAST ? (uint32_t)st->slot_tf[s] : (uint32_t)__ldg(T.type_flags + __ldg(T.slot_type + (s))))
+#define TAB_STYPE(s) (FAST ? (uint32_t)st->slot_type[s] : (uint32_t)__ldg(T.slot_type + (s)))
+#define TAB_TBASE(t) (FAST ? (int)st->type_base[t] : (int)__ldg(T.type_base + (t)))
+#define TAB_TCOUNT(t) (FAST ? (int)st->type_count[t] : (int)__ldg(T.type_count + (t)))
+
 #define OSTRIDE 33  // shared-memory column stride (words): lane-per-env and lane-per-slot are both conflict-free
 
 // Per-lane view of one environment.  Object records live in a shared-memory column.
 struct EnvRegs {
   uint32_t* o;   // &sobj[lane]; dynamic slot s at o[s * OSTRIDE]
   uint32_t* ag;  // &sag[lane];  agent i at ag[i * OSTRIDE]
+  const SmemTabs* st;
   uint32_t sbits, tinfo, marks, variant, rids, episode, err;
 };
 
@@ -91,9 +127,11 @@ __device__ __forceinline__ uint64_t cz_mix(uint64_t seed, uint64_t env, uint64_t
   return z ^ (z >> 31);
 }
 
+template <bool FAST>
 __device__ __forceinline__ bool cz_walkable(const CzDev& T, const EnvRegs& e, uint32_t cell) {
   // StaticObject.walkable (world_objects.py:20,148,199): Floor and Switch always, Block by state
-  uint32_t g = __ldg(T.grid + e.variant * 64 + cell);
+  const SmemTabs* st = e.st;
+  uint32_t g = TAB_GRID(e.variant, cell);
   uint32_t kind = g & 15u;
   if (kind == ST_FLOOR || kind == ST_SWITCH) return true;
   if (kind == ST_BLOCK) return (e.sbits & SB_BLK_WALK(g >> 4)) != 0;
@@ -110,9 +148,11 @@ __device__ __forceinline__ bool cz_agent_on(const CzDev& T, const EnvRegs& e, ui
 
 // Move a dynamic object (and, for a Plate, its content) — Object.move_to / Plate.move_to
 // (abstract_classes.py:21-22, world_objects.py:393-396).
+template <bool FAST>
 __device__ __forceinline__ void cz_move_obj(const CzDev& T, EnvRegs& e, uint32_t s, uint32_t xy) {
   e.o[s * OSTRIDE] = O_WITH_XY(e.o[s * OSTRIDE], xy);
-  if (__ldg(T.type_flags + __ldg(T.slot_type + s)) & TF_PLATE) {
+  const SmemTabs* st = e.st;
+  if (TAB_TF(s) & TF_PLATE) {
     for (int k = 0; k < T.D; ++k) {
       uint32_t r = e.o[k * OSTRIDE];
       if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == s) e.o[k * OSTRIDE] = O_WITH_XY(r, xy);
@@ -144,22 +184,23 @@ __device__ __forceinline__ uint32_t cz_plate_count_clear_free(const CzDev& T, En
 
 // resolve_interaction -> resolve_execute_action | resolve_primary_interaction -> attempt_merge
 // (action_scheme3.py:37-43, cooking_world.py:114-136, 156-170, 243-261).
+template <bool FAST>
 __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, uint32_t cell) {
   const uint32_t agent_rec = e.ag[i * OSTRIDE];
-  const uint32_t g = __ldg(T.grid + e.variant * 64 + cell);
+  const SmemTabs* st = e.st;
+  const uint32_t g = TAB_GRID(e.variant, cell);
   const uint32_t kind = g & 15u, sp = g >> 4;
   // one pass in scan order over the dynamic objects at the faced cell (cooking_world.py:232-241)
   int n_dyn = 0, last = -1, first_free = -1, n_plates = 0, plate = -1, n_content = 0;
   bool any_not_done = false;
-  const uint8_t* scan = T.scan_order + e.variant * T.D;
   for (int k = 0; k < T.D; ++k) {
-    int s = __ldg(scan + k);
+    int s = TAB_SCAN(e.variant, k);
     uint32_t r = e.o[s * OSTRIDE];
     if (!(r & O_PRESENT) || O_XY(r) != cell) continue;
     ++n_dyn;
     last = s;
     if (first_free < 0 && (r & O_FREE)) first_free = s;
-    if (__ldg(T.type_flags + __ldg(T.slot_type + s)) & TF_PLATE) {
+    if (TAB_TF(s) & TF_PLATE) {
       ++n_plates;
       plate = s;
     } else if (!(r & (O_CHOP | O_MASH))) {
@@ -182,14 +223,14 @@ __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, u
         }
         if (s < 0) break;
         uint32_t r = e.o[s * OSTRIDE];
-        uint32_t tid = __ldg(T.slot_type + s);
-        uint32_t tf = __ldg(T.type_flags + tid);
+        uint32_t tid = TAB_STYPE(s);
+        uint32_t tf = TAB_TF(s);
         if (!(tf & TF_CHOP)) return;
         if (r & O_CHOP) continue;  // ChopFood.chop / Bread.chop: already chopped -> not executed
         e.o[s * OSTRIDE] = r | O_CHOP;
         e.sbits &= ~SB_CUT_READY(sp);
         if (tf & TF_SPAWN) {  // Bread.chop spawns a chopped twin (world_objects.py:738-745)
-          int base = __ldg(T.type_base + tid), cnt = __ldg(T.type_count + tid);
+          int base = TAB_TBASE(tid), cnt = TAB_TCOUNT(tid);
           int slot = -1;
           for (int k = base; k < base + cnt; ++k)
             if (slot < 0 && !(e.o[k * OSTRIDE] & O_PRESENT)) slot = k;
@@ -227,7 +268,7 @@ __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, u
     if (O_CK(r) != CK_STATIC) return;  // `object_to_grab in static_object.content`
     cz_remove_from_static(T, e, cell, O_POS(r));
     e.o[gs * OSTRIDE] = O_WITH_CONT(r, CK_HELD, i, 0);
-    cz_move_obj(T, e, gs, axy);  // Agent.grab (world_objects.py:786-788)
+    cz_move_obj<FAST>(T, e, gs, axy);  // Agent.grab (world_objects.py:786-788)
     e.ag[i * OSTRIDE] = (agent_rec & ~(0x3Fu << 9)) | (1u << 9) | ((uint32_t)gs << 10);
     return;
   }
@@ -235,7 +276,7 @@ __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, u
   // ---- attempt_merge (cooking_world.py:243-261)
   const uint32_t h = A_HOLD(agent_rec);
   const uint32_t hr = e.o[h * OSTRIDE];
-  const uint32_t htf = __ldg(T.type_flags + __ldg(T.slot_type + h));
+  const uint32_t htf = TAB_TF(h);
   const uint32_t dropped = agent_rec & ~(0x3Fu << 9);
   if (n_plates == 1) {
     // Plate.accepts: Food and done and room (world_objects.py:408-409)
@@ -249,7 +290,7 @@ __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, u
     }
   } else if ((htf & TF_PLATE) && n_dyn > 0) {
     uint32_t pr = e.o[last * OSTRIDE];
-    uint32_t ptf = __ldg(T.type_flags + __ldg(T.slot_type + last));
+    uint32_t ptf = TAB_TF(last);
     if ((ptf & (TF_CHOP | TF_BLEND)) && (pr & (O_CHOP | O_MASH))) {
       uint32_t n = cz_plate_count_clear_free(T, e, h, false);
       if (n < 64) {
@@ -269,7 +310,7 @@ __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, u
       if (kind == ST_CUTBOARD) e.sbits |= SB_CUT_READY(sp);
       if (kind == ST_BLENDER) e.sbits |= SB_BL_READY(sp);
       e.o[h * OSTRIDE] = O_WITH_CONT(hr, CK_STATIC, 0, n_content) | O_FREE;
-      cz_move_obj(T, e, h, cell);
+      cz_move_obj<FAST>(T, e, h, cell);
       e.ag[i * OSTRIDE] = dropped;
     }
   }
@@ -290,31 +331,43 @@ __device__ __forceinline__ void cz_refresh_static_free(const CzDev& T, EnvRegs& 
   }
 }
 
+// Cells holding an object that satisfies one recipe node on its own (type + condition):
+// the `for obj in world.world_objects[node.name]` loop of Recipe.update_recipe_state
+// (recipe.py:83-87) with check_conditions' attribute test (:96-98).  Out of line: it is called
+// for every node of every recipe and would otherwise be replicated by the unrolled caller.
+__device__ __noinline__ uint64_t cz_node_mask(const uint32_t* o, uint32_t node, uint64_t static_mask, int base, int cnt) {
+  const uint32_t ty = node & 255u;
+  if (node & 256u) return static_mask;
+  if (ty == 255u) return 0;  // a type the meta file does not know: no such object can exist
+  const uint32_t cond = (node >> 9) & 3u;
+  const uint32_t need = O_PRESENT | (cond == 1 ? O_CHOP : (cond == 2 ? O_MASH : 0u));
+  uint64_t mask = 0;
+  for (int s = base; s < base + cnt; ++s) {
+    uint32_t r = o[s * OSTRIDE];
+    if ((r & need) == need) mask |= 1ull << O_XY(r);
+  }
+  return mask;
+}
+
 // Recipe.update_recipe_state as cell bitmasks (recipe.py:77-104): node mask = cells holding an
-// object of the node's type that meets its condition, ANDed with every child's mask.
+// object of the node's type that meets its condition, ANDed with every child's mask (children
+// come later in node_list, so the list is walked back to front).
+template <bool FAST>
 __device__ __forceinline__ uint32_t cz_recipe_marks(const CzDev& T, const EnvRegs& e, uint32_t rid) {
+  const SmemTabs* st = e.st;
   uint64_t m[CZ_MAX_NODES];
-  const int n = __ldg(T.recipe_len + rid);
+  const int n = TAB_RLEN(rid);
   uint32_t marks = 0;
 #pragma unroll
   for (int k = CZ_MAX_NODES - 1; k >= 0; --k) {
     m[k] = 0;
     if (k < n) {
-      uint32_t node = __ldg(T.recipe_nodes + rid * CZ_MAX_NODES + k);
-      uint64_t mask = 0;
-      uint32_t ty = node & 255u;
-      if (node & 256u) {
-        mask = __ldg(T.static_masks + e.variant * 8 + (ty & 7u));
-      } else if (ty != 255u) {
-        uint32_t cond = (node >> 9) & 3u;
-        uint32_t need = cond == 1 ? O_CHOP : (cond == 2 ? O_MASH : 0u);
-        int base = __ldg(T.type_base + ty), cnt = __ldg(T.type_count + ty);
-        for (int s = base; s < base + cnt; ++s) {
-          uint32_t r = e.o[s * OSTRIDE];
-          if ((r & O_PRESENT) && (r & need) == need) mask |= 1ull << O_XY(r);
-        }
-      }
-      uint32_t kids = node >> 16;
+      const uint32_t node = TAB_RNODE(rid, k);
+      const bool is_static = node & 256u, known = (node & 255u) != 255u;
+      uint64_t mask = cz_node_mask(e.o, node, is_static ? TAB_SMASK(e.variant, node & 7u) : 0ull,
+                                   (!is_static && known) ? TAB_TBASE(node & 255u) : 0,
+                                   (!is_static && known) ? TAB_TCOUNT(node & 255u) : 0);
+      const uint32_t kids = node >> 16;
 #pragma unroll
       for (int j = k + 1; j < CZ_MAX_NODES; ++j)
         if (kids & (1u << j)) mask &= m[j];
@@ -327,10 +380,12 @@ __device__ __forceinline__ uint32_t cz_recipe_marks(const CzDev& T, const EnvReg
 
 // CookingEnvironment.accumulated_step (cooking_env.py:243-269) for one environment.
 // Writes reward f64[A], terminated u8[A], truncated u8[A] of this environment.
+template <bool FAST>
 __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const uint32_t act_packed,
                                             double* __restrict__ reward, uint8_t* __restrict__ term_out,
                                             uint8_t* __restrict__ trunc_out) {
   const int A = T.A;
+  const SmemTabs* st = e.st;
   const uint32_t t = TI_T(e.tinfo) + 1;  // :244
   uint32_t active = 0;
   for (int i = 0; i < A; ++i)
@@ -356,7 +411,7 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
     }
     // check_collisions, first loop (:206-216)
     uint32_t tgt = ai ? faced : A_XY(rec);
-    bool w = cz_walkable(T, e, tgt);
+    bool w = cz_walkable<FAST>(T, e, tgt);
     uint32_t endc = (w ? tgt : A_XY(rec)) | (w ? 0x40u : 0u);
     apack |= ai << (8 * i);
     fpack |= faced << (8 * i);
@@ -379,17 +434,17 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
     uint32_t rec = e.ag[i * OSTRIDE];
     uint32_t ai = (cancel >> i & 1u) ? 0u : ((apack >> (8 * i)) & 255u);
     uint32_t tgt = ai ? ((fpack >> (8 * i)) & 63u) : A_XY(rec);
-    if (cz_walkable(T, e, tgt)) {  // resolve_walking_action (:26-34)
+    if (cz_walkable<FAST>(T, e, tgt)) {  // resolve_walking_action (:26-34)
       rec = (rec & ~63u) | tgt;
       e.ag[i * OSTRIDE] = rec;
-      if (A_HAS(rec)) cz_move_obj(T, e, A_HOLD(rec), tgt);  // Agent.move_to (world_objects.py:793-796)
-      uint32_t g = __ldg(T.grid + e.variant * 64 + tgt);
+      if (A_HAS(rec)) cz_move_obj<FAST>(T, e, A_HOLD(rec), tgt);  // Agent.move_to (world_objects.py:793-796)
+      uint32_t g = TAB_GRID(e.variant, tgt);
       if ((g & 15u) == ST_SWITCH) {  // Switch.add_content (:159-163)
         e.sbits ^= SB_SW_ACTIVE(g >> 4);
         pressed |= 1u << (g >> 4);
       }
     } else if (ai) {
-      cz_interact(T, e, i, tgt);
+      cz_interact<FAST>(T, e, i, tgt);
       dirty = (dirty & ~(0xFFu << (8 * i))) | (tgt << (8 * i));
     }
   }
@@ -398,7 +453,7 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
   if (e.sbits & (0xFu << 8)) {  // some blender is switched on: Blender.process (world_objects.py:321-335)
     for (int k = 0; k < CZ_MAX_SPECIAL; ++k) {
       if (!(e.sbits & SB_BL_TOGGLE(k))) continue;
-      uint32_t cell = __ldg(T.special_cells + (e.variant * 4 + 1) * CZ_MAX_SPECIAL + k);
+      uint32_t cell = TAB_SPECIAL(e.variant, 1, k);
       if (cell == 0xFFu) continue;
       int n = 0;
       bool all_mashed = true;
@@ -425,8 +480,8 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
   if (pressed) {
     uint32_t blocks = 0, n_sw = 0;
     for (int k = 0; k < CZ_MAX_SPECIAL; ++k) {
-      if (__ldg(T.special_cells + (e.variant * 4 + 3) * CZ_MAX_SPECIAL + k) != 0xFFu) blocks |= SB_BLK_WALK(k);
-      if (__ldg(T.special_cells + (e.variant * 4 + 2) * CZ_MAX_SPECIAL + k) != 0xFFu) ++n_sw;
+      if (TAB_SPECIAL(e.variant, 3, k) != 0xFFu) blocks |= SB_BLK_WALK(k);
+      if (TAB_SPECIAL(e.variant, 2, k) != 0xFFu) ++n_sw;
     }
     if (n_sw > 1) e.err |= CZ_ERR_SWITCH_LINK;
     for (int k = 0; k < CZ_MAX_SPECIAL; ++k)
@@ -456,7 +511,7 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
   for (int r = 0; r < T.R; ++r) {
     uint32_t rid = (e.rids >> (8 * r)) & 255u;
     uint32_t before = (e.marks >> (8 * r)) & 255u;
-    uint32_t after = cz_recipe_marks(T, e, rid);
+    uint32_t after = cz_recipe_marks<FAST>(T, e, rid);
     new_marks |= after << (8 * r);
     bool was = before & 1u, now = after & 1u;
     int delta = __popc(after) - __popc(before);  // sum(goals_before) - sum(goals_after)

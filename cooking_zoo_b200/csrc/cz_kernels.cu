@@ -23,7 +23,9 @@
 
 #define CZ_WARPS_PER_BLOCK 4
 #define CZ_THREADS (32 * CZ_WARPS_PER_BLOCK)
+#ifndef CZ_MIN_BLOCKS
 #define CZ_MIN_BLOCKS 7  // 28 warps/SM: registers capped at 72, shared memory at 32 KB per block
+#endif
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
 enum { OBS_TMA = 0, OBS_STG = 1 };
@@ -52,23 +54,27 @@ __device__ __forceinline__ void cz_bulk_wait_read() {
 
 // ---- observation rows (get_feature_vector, cooking_env.py:352-373) -----------------------------
 // A row = table segments (static slots: a function of layout variant and observer cell only, copied
-// from the L1/L2-resident obs_table with 128-bit loads/stores) + computed slots (dynamic objects,
-// agents, live Switch/Block) that one lane each writes as [x, y, flags..., 1] doubles into the
-// shared-memory staging rows, which the TMA engine then stores (cp.async.bulk).
+// from the L2-resident obs_table with 128-bit loads/stores) + computed slots (dynamic objects,
+// agents, live Switch/Block) written as [x, y, flags..., 1] doubles into shared-memory staging rows
+// that the TMA engine stores (cp.async.bulk).  Slots that can never be occupied are not listed: the
+// staging rows are zero-filled once and only the listed slots are rewritten.
 //
-// Everything that does not change from row to row is decoded once per kernel into LaneSlot.
+// Everything that does not change from row to row is decoded once per kernel into LaneSlot.  In the
+// FAST instantiation a lane owns one (observer, slot) pair, so all A rows of an environment are
+// filled in a single pass; otherwise a lane owns one slot and loops over the observers.
 struct LaneSlot {
-  int off;        // staging offset (doubles) of the slot owned by this lane, < 0: lane idle
+  int off;        // staging offset (doubles, inside its row) of the slot owned by this lane, < 0: idle
+  int agent;      // FAST: the observer (row) this lane writes
   uint32_t flen;  // features after x, y (the trailing 1 included)
   uint32_t kind;  // 0 live static (Switch/Block), 1 dynamic object, 2 agent
   uint32_t idx;   // static slot / dynamic slot / agent index
-  int t0, t1;     // destination (in double2 units, relative to the row) of table elements lane, lane+32
+  int t0, t1;     // destination (double2 units, relative to the row) of table elements lane, lane+32
 };
 
-__device__ __forceinline__ LaneSlot cz_lane_slot(const CzDev& T, int q, int lane) {
+__device__ __forceinline__ LaneSlot cz_lane_slot(const CzDev& T, int q, int agent, int lane) {
   LaneSlot ls;
-  ls.off = -1; ls.flen = 1; ls.kind = 1; ls.idx = 0;
-  if (q < T.n_comp) {
+  ls.off = -1; ls.agent = agent; ls.flen = 1; ls.kind = 1; ls.idx = 0;
+  if (q >= 0 && q < T.n_comp) {
     const uint32_t d = __ldg(T.comp_slots + q);
     ls.off = (int)(d & 0xFFFu) - T.stage_lo;
     ls.flen = (d >> 12) & 7u; ls.kind = (d >> 15) & 3u; ls.idx = (d >> 17) & 255u;
@@ -83,10 +89,11 @@ __device__ __forceinline__ LaneSlot cz_lane_slot(const CzDev& T, int q, int lane
   return ls;
 }
 
-// Agent-independent part of a computed slot: record (x | y<<3 in the low bits), presence, feature bits.
-__device__ __forceinline__ void cz_slot_state(const CzDev& T, const LaneSlot& ls, const uint32_t* sobj,
-                                              const uint32_t* sag, uint32_t sbits, uint32_t variant, int e,
-                                              uint32_t& xy, uint32_t& fb) {
+// Observer-independent part of a computed slot: cell (x | y<<3, bit 6 = present) and feature bits.
+template <bool FAST>
+__device__ __forceinline__ void cz_slot_state(const CzDev& T, const SmemTabs* st, const LaneSlot& ls,
+                                              const uint32_t* sobj, const uint32_t* sag, uint32_t sbits,
+                                              uint32_t variant, int e, uint32_t& xy, uint32_t& fb) {
   uint32_t rec, fb4;
   bool present;
   if (ls.kind == 1) {  // dynamic object: [!done, chopped, mashed] (world_objects.py:447,555,...)
@@ -99,10 +106,10 @@ __device__ __forceinline__ void cz_slot_state(const CzDev& T, const LaneSlot& ls
     rec = present ? sag[ls.idx * OSTRIDE + e] : 0u;
     fb4 = (1u << A_ORI(rec)) >> 1;
   } else {  // live Switch / Block: [switch_active] / [walkable] (world_objects.py:174,221)
-    uint32_t cell = __ldg(T.static_cells + variant * T.S + ls.idx);
+    uint32_t cell = TAB_SCELL(variant, ls.idx);
     present = cell != 0xFFu;
     rec = present ? cell : 0u;
-    uint32_t g = __ldg(T.grid + variant * 64 + rec);
+    uint32_t g = TAB_GRID(variant, rec);
     fb4 = ((g & 15u) == ST_SWITCH ? (sbits >> (12 + (g >> 4))) : (sbits >> (16 + (g >> 4)))) & 1u;
   }
   const uint32_t one = 1u << (ls.flen - 1);  // the trailing 1 of every feature vector
@@ -111,7 +118,8 @@ __device__ __forceinline__ void cz_slot_state(const CzDev& T, const LaneSlot& ls
 }
 
 // Observer-dependent part: (x - ax) / W, (y - ay) / H from shared tables of host-divided doubles
-// (the observer's own entry is x / W, y / H: cooking_env.py:364-368), then the flags.
+// (the observer's own entry is x / W, y / H: cooking_env.py:364-368), then the flags as doubles
+// (1.0 = 0x3FF00000'00000000).
 __device__ __forceinline__ void cz_slot_store(const LaneSlot& ls, uint32_t xy, uint32_t fb, int ax, int ay, bool self,
                                               const double* sxl, const double* syl, double* row) {
   const int x = xy & 7u, y = (xy >> 3) & 7u;
@@ -123,68 +131,65 @@ __device__ __forceinline__ void cz_slot_store(const LaneSlot& ls, uint32_t xy, u
   out[1] = Y;
 #pragma unroll
   for (int k = 0; k < 5; ++k)
-    if (k < (int)ls.flen) out[2 + k] = (fb >> k & 1u) ? 1.0 : 0.0;
+    if (k < (int)ls.flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, (fb >> k & 1u) ? 0x3FF00000u : 0u);
 }
 
-// shared-memory layout of one warp
+// Image of the read-only part of a block's shared memory, built on the host (cz_tables_create) and
+// copied by every block with one 16-byte load per thread.
 struct BlockSmem {
-  double xlut[16];  // k / W for k = -(W-1)..W-1, centred at index W-1
+  double xlut[16];  // k / W for k = -(W-1)..W-1
   double ylut[16];
+  SmemTabs tabs;
 };
-// per-warp words: object columns [D][33], agent columns [A][33], then sbits/variant/wobs [32] and misc [6][32]
+// per-warp words: object columns [D][33], agent columns [A][33], then sbits/variant/wobs [32]
 struct WarpSmem {
   uint32_t* obj;
   uint32_t* ag;
   uint32_t* sbits;
   uint32_t* variant;
   uint32_t* wobs;
-  uint32_t* misc;
 };
-__host__ __device__ inline size_t cz_warp_words(int D, int A) { return (size_t)(D + A) * OSTRIDE + 32 * (3 + CZ_NUM_MISC_ROWS); }
+__host__ __device__ inline size_t cz_warp_words(int D, int A) { return (size_t)(D + A) * OSTRIDE + 32 * 3; }
+__host__ __device__ inline size_t cz_block_smem_head() { return (sizeof(BlockSmem) + 15) & ~(size_t)15; }
 
-template <int MODE, int OBS, bool SIMPLE>
+template <int MODE, int OBS, bool FAST>
 __global__ void __launch_bounds__(CZ_THREADS, CZ_MIN_BLOCKS)
-cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __restrict__ actions,
+cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, const uint8_t* __restrict__ actions,
               const int32_t* __restrict__ layout_ids, const uint8_t* __restrict__ recipe_ids,
               const uint8_t* __restrict__ mask, double* __restrict__ obs, double* __restrict__ reward,
               uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint32_t* __restrict__ errflags,
               int n_envs, uint32_t flags, uint64_t seed, int64_t env_offset) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = T.D, A = T.A;
   BlockSmem* bs = reinterpret_cast<BlockSmem*>(smem_raw);
   WarpSmem wsv;
   WarpSmem* ws = &wsv;
   {
-    uint32_t* base = reinterpret_cast<uint32_t*>(smem_raw + sizeof(BlockSmem)) + (size_t)warp * cz_warp_words(T.D, T.A);
+    uint32_t* base = reinterpret_cast<uint32_t*>(smem_raw + cz_block_smem_head()) + (size_t)warp * cz_warp_words(D, A);
     wsv.obj = base;
-    wsv.ag = base + T.D * OSTRIDE;
-    wsv.sbits = wsv.ag + T.A * OSTRIDE;
+    wsv.ag = base + D * OSTRIDE;
+    wsv.sbits = wsv.ag + A * OSTRIDE;
     wsv.variant = wsv.sbits + 32;
     wsv.wobs = wsv.variant + 32;
-    wsv.misc = wsv.wobs + 32;
   }
   // staging (the computed span of A rows) lives after the per-warp words, 16-byte aligned
   const size_t row_bytes = ((size_t)T.stage_len * 8 + 15) & ~(size_t)15;
-  unsigned char* stage_base = smem_raw + ((sizeof(BlockSmem) + cz_warp_words(T.D, T.A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15);
-  double* stage = reinterpret_cast<double*>(stage_base + (size_t)warp * T.A * row_bytes);
+  unsigned char* stage_base = smem_raw + ((cz_block_smem_head() + cz_warp_words(D, A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15);
+  double* stage = reinterpret_cast<double*>(stage_base + (size_t)warp * A * row_bytes);
   const int row_stride = (int)(row_bytes >> 3);
-  if (threadIdx.x < 2 * T.W - 1) bs->xlut[threadIdx.x] = __ldg(T.xlut + threadIdx.x);
-  if (threadIdx.x < 2 * T.H - 1) bs->ylut[threadIdx.x] = __ldg(T.ylut + threadIdx.x);
-  __syncthreads();
+  // read-only block image: one 16-byte load per thread
+  for (int i = threadIdx.x; i < (int)(sizeof(BlockSmem) / 16); i += CZ_THREADS)
+    reinterpret_cast<uint4*>(bs)[i] = __ldg(reinterpret_cast<const uint4*>(T.blob) + i);
+  // never-occupied slots stay zero: the staging rows are cleared once and only live slots are rewritten
+  for (int i = lane; i < A * row_stride; i += 32) stage[i] = 0.0;
+  const SmemTabs* st = &bs->tabs;
   const double* sxl = bs->xlut + (T.W - 1);
   const double* syl = bs->ylut + (T.H - 1);
-  const LaneSlot ls = cz_lane_slot(T, lane, lane);
-  // loop invariants of the observation phase
-  const int tab2 = T.tab_len >> 1, L2 = T.L >> 1;
-  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
-  const size_t row_gbytes = (size_t)T.L * 8;
-  const uint32_t r0_bytes = (uint32_t)T.ranges[0][1] * 8;
-  const size_t r0_goff = (size_t)T.ranges[0][0] * 8;
-  const uint32_t r0_soff = (uint32_t)(T.ranges[0][0] - T.stage_lo) * 8;
+  __syncthreads();
 
   const int n_tiles = (n_envs + 31) >> 5;
   const int warps_total = gridDim.x * CZ_WARPS_PER_BLOCK;
-  const int D = T.D, A = T.A;
   const size_t N = (size_t)n_envs;
   uint32_t* misc = state + (size_t)(D + A) * N;
 
@@ -194,21 +199,25 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
     EnvRegs e;
     e.o = ws->obj + lane;
     e.ag = ws->ag + lane;
+    e.st = st;
     e.err = 0;
+    e.sbits = 0; e.variant = 0;
     bool write_obs = valid;
     if (valid) {
-      // ---- phase 1: state -> shared columns (coalesced: consecutive lanes, consecutive words)
-      // all words of the environment in flight at once (LDGSTS), one wait
+      // ---- phase 1: state -> shared columns (coalesced: consecutive lanes, consecutive words);
+      // every word of the environment is in flight at once (LDGSTS + plain loads), one wait
       for (int s = 0; s < D; ++s) cz_cp_async4(e.o + s * OSTRIDE, state + (size_t)s * N + env);
       for (int i = 0; i < A; ++i) cz_cp_async4(e.ag + i * OSTRIDE, state + (size_t)(D + i) * N + env);
-      for (int m = 0; m < CZ_NUM_MISC_ROWS; ++m) cz_cp_async4(ws->misc + m * 32 + lane, misc + (size_t)m * N + env);
+      e.sbits = misc[(size_t)CZ_ROW_SBITS * N + env];
+      e.tinfo = misc[(size_t)CZ_ROW_TINFO * N + env];
+      e.marks = misc[(size_t)CZ_ROW_MARKS * N + env];
+      e.variant = misc[(size_t)CZ_ROW_VARIANT * N + env];
+      e.rids = misc[(size_t)CZ_ROW_RECIPES * N + env];
+      e.episode = misc[(size_t)CZ_ROW_EPISODE * N + env];
+      uint32_t act = 0;
+      if (MODE == MODE_STEP)
+        for (int i = 0; i < A; ++i) act |= (uint32_t)actions[(size_t)env * A + i] << (8 * i);
       cz_cp_async_wait_all();
-      e.sbits = ws->misc[CZ_ROW_SBITS * 32 + lane];
-      e.tinfo = ws->misc[CZ_ROW_TINFO * 32 + lane];
-      e.marks = ws->misc[CZ_ROW_MARKS * 32 + lane];
-      e.variant = ws->misc[CZ_ROW_VARIANT * 32 + lane];
-      e.rids = ws->misc[CZ_ROW_RECIPES * 32 + lane];
-      e.episode = ws->misc[CZ_ROW_EPISODE * 32 + lane];
 
       bool do_reset = false;
       int layout = 0;
@@ -239,7 +248,7 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
         e.variant = __ldg(src + D + A + CZ_ROW_VARIANT);
         e.episode += 1;
         uint32_t marks = 0;
-        for (int r = 0; r < T.R; ++r) marks |= cz_recipe_marks(T, e, (e.rids >> (8 * r)) & 255u) << (8 * r);
+        for (int r = 0; r < T.R; ++r) marks |= cz_recipe_marks<FAST>(T, e, (e.rids >> (8 * r)) & 255u) << (8 * r);
         e.marks = marks;
         if (MODE == MODE_STEP) {
           for (int i = 0; i < A; ++i) {
@@ -250,9 +259,7 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
         }
       } else if (MODE == MODE_STEP) {
         // ---- phase 2: one accumulated_step per lane
-        uint32_t act = 0;
-        for (int i = 0; i < A; ++i) act |= (uint32_t)actions[(size_t)env * A + i] << (8 * i);
-        cz_step_env(T, e, act, reward + (size_t)env * A, term + (size_t)env * A, trunc + (size_t)env * A);
+        cz_step_env<FAST>(T, e, act, reward + (size_t)env * A, term + (size_t)env * A, trunc + (size_t)env * A);
       }
 
       // ---- phase 3: shared columns -> state
@@ -274,6 +281,18 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
     __syncwarp();
 
     // ---- phase 4: observation rows of the tile, one environment (A rows) at a time, whole warp
+    // Its invariants are derived here, from an opaque copy of the lane id, so that they are not
+    // hoisted above the dynamics (where they would be spilled: registers are capped for 28 warps/SM).
+    int lane_o = lane;
+    asm volatile("" : "+r"(lane_o));
+    const LaneSlot ls = FAST ? cz_lane_slot(T, lane_o < A * T.n_comp ? lane_o % T.n_comp : -1, lane_o / T.n_comp, lane_o)
+                             : cz_lane_slot(T, lane_o, 0, lane_o);
+    const int tab2 = T.tab_len >> 1, L2 = T.L >> 1;
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const size_t row_gbytes = (size_t)T.L * 8;
+    const uint32_t r0_bytes = (uint32_t)T.ranges[0][1] * 8;
+    const size_t r0_goff = (size_t)T.ranges[0][0] * 8;
+    const uint32_t r0_soff = (uint32_t)(T.ranges[0][0] - T.stage_lo) * 8;
     const int n_here = min(32, n_envs - tile * 32);
     double* genv = obs + (size_t)tile * 32 * A * T.L;
     const size_t env_doubles = (size_t)A * T.L;
@@ -281,40 +300,58 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
     for (int le = 0; le < n_here; ++le, genv += env_doubles) {
       if (!ws->wobs[le]) continue;
       const uint32_t sb = ws->sbits[le], var = ws->variant[le];
+      const double2* tab = reinterpret_cast<const double2*>(T.obs_table) + (size_t)var * 64 * tab2 + lane;
+      // prefetch the table segments of the first two rows (their L2 latency hides behind the slot decode)
+      const uint32_t meA = ws->ag[le], meB = A > 1 ? ws->ag[OSTRIDE + le] : meA;
+      double2 vA0, vA1, vB0, vB1;
+      {
+        const double2* srcA = tab + (meA & 63u) * tab2;
+        const double2* srcB = tab + (meB & 63u) * tab2;
+        if (ls.t0 >= 0) { vA0 = __ldg(srcA); vB0 = __ldg(srcB); }
+        if (ls.t1 >= 0) { vA1 = __ldg(srcA + 32); vB1 = __ldg(srcB + 32); }
+      }
       uint32_t xy = 0, fb = 0;
-      if (ls.off >= 0) cz_slot_state(T, ls, ws->obj, ws->ag, sb, var, le, xy, fb);
-      const double2* tab = reinterpret_cast<const double2*>(T.obs_table) + (size_t)var * 64 * tab2;
+      if (ls.off >= 0) cz_slot_state<FAST>(T, st, ls, ws->obj, ws->ag, sb, var, le, xy, fb);
       if (OBS == OBS_TMA) {
         // the bulk stores of the previous environment must have finished reading the staging rows
         if (lane == 0) cz_bulk_wait_read<0>();
         __syncwarp();
       }
+      if (FAST) {  // one pass: this lane's (observer, slot) pair
+        if (ls.off >= 0) {
+          const uint32_t me = ls.agent == 0 ? meA : (ls.agent == 1 ? meB : ws->ag[ls.agent * OSTRIDE + le]);
+          cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, ls.kind == 2 && (int)ls.idx == ls.agent, sxl, syl,
+                        stage + ls.agent * row_stride);
+        }
+      }
       double* row = stage;
       double2* g2 = reinterpret_cast<double2*>(genv);
 #pragma unroll 1
       for (int a = 0; a < A; ++a, row += row_stride, g2 += L2) {
-        const uint32_t me = ws->ag[a * OSTRIDE + le];
-        // table segments of this row: loads issued first, the fill below hides their latency
-        const double2* src = tab + (me & 63u) * tab2 + lane;
-        double2 v0, v1;
-        if (ls.t0 >= 0) v0 = __ldg(src);
-        if (ls.t1 >= 0) v1 = __ldg(src + 32);
-        if (ls.off >= 0)
-          cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, ls.kind == 2 && (int)ls.idx == a, sxl, syl, row);
-        if (!SIMPLE) {
-          for (int q = lane + 32; q < T.n_comp; q += 32) {  // more than 32 computed slots: extra passes
-            const LaneSlot l2 = cz_lane_slot(T, q, lane);
+        const uint32_t me = a == 0 ? meA : (a == 1 ? meB : ws->ag[a * OSTRIDE + le]);
+        double2 v0 = a == 0 ? vA0 : vB0, v1 = a == 0 ? vA1 : vB1;
+        if (a >= 2) {  // more than two agents: no prefetch
+          const double2* src = tab + (me & 63u) * tab2;
+          if (ls.t0 >= 0) v0 = __ldg(src);
+          if (ls.t1 >= 0) v1 = __ldg(src + 32);
+        }
+        if (!FAST) {  // one lane per slot, as many passes as it takes
+          if (ls.off >= 0)
+            cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, ls.kind == 2 && (int)ls.idx == a, sxl, syl, row);
+          for (int q = lane + 32; q < T.n_comp; q += 32) {
+            const LaneSlot l2 = cz_lane_slot(T, q, 0, lane);
             uint32_t xy2, fb2;
-            cz_slot_state(T, l2, ws->obj, ws->ag, sb, var, le, xy2, fb2);
+            cz_slot_state<FAST>(T, st, l2, ws->obj, ws->ag, sb, var, le, xy2, fb2);
             cz_slot_store(l2, xy2, fb2, me & 7u, (me >> 3) & 7u, l2.kind == 2 && (int)l2.idx == a, sxl, syl, row);
           }
         }
         if (ls.t0 >= 0) g2[ls.t0] = v0;
         if (ls.t1 >= 0) g2[ls.t1] = v1;
-        if (!SIMPLE) {
+        if (!FAST) {
+          const double2* src = tab + (me & 63u) * tab2 - lane;
           for (int k = lane + 64; k < tab2; k += 32) {  // table rows longer than 64 double2
             const int n0 = T.segs[0][1] >> 1;
-            g2[k < n0 ? (T.segs[0][0] >> 1) + k : (T.segs[1][0] >> 1) + k - n0] = __ldg(src + k - lane);
+            g2[k < n0 ? (T.segs[0][0] >> 1) + k : (T.segs[1][0] >> 1) + k - n0] = __ldg(src + k);
           }
         }
       }
@@ -328,7 +365,7 @@ cz_env_kernel(const CzDev T, uint32_t* __restrict__ state, const uint8_t* __rest
 #pragma unroll 1
           for (int a = 0; a < A; ++a, gp += row_gbytes, sp += (uint32_t)row_bytes) {
             cz_bulk_store_s(gp, sp, r0_bytes);
-            if (!SIMPLE) {
+            if (!FAST) {
               for (int r = 1; r < T.n_ranges; ++r)
                 cz_bulk_store_s(gp + (T.ranges[r][0] - T.ranges[0][0]) * 8, sp + (T.ranges[r][0] - T.ranges[0][0]) * 8,
                                 (uint32_t)T.ranges[r][1] * 8);
@@ -404,7 +441,7 @@ static int upload(cz_tables* t, const Tp* host, size_t count, const Tp** out) {
 
 static size_t cz_smem_bytes(const CzDev& T) {
   size_t row_bytes = ((size_t)T.stage_len * 8 + 15) & ~(size_t)15;
-  return ((sizeof(BlockSmem) + cz_warp_words(T.D, T.A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15) +
+  return ((cz_block_smem_head() + cz_warp_words(T.D, T.A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15) +
          (size_t)CZ_WARPS_PER_BLOCK * T.A * row_bytes;
 }
 
@@ -445,6 +482,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   const char* p = getenv("CZ_OBS_PATH");
   t->obs_path = (p && !strcmp(p, "stg")) ? OBS_STG : OBS_TMA;
   if (d->obs_len & 1) t->obs_path = OBS_STG;  // bulk copies need 16-byte rows
+  static_assert(sizeof(BlockSmem) % 16 == 0, "block image is copied in 16-byte units");
   CzDev& T = t->dev;
   T.W = d->width; T.H = d->height; T.A = d->num_agents; T.R = d->num_recipes; T.D = d->num_dyn_slots;
   T.S = d->num_static_slots; T.T = d->num_types; T.L = d->obs_len;
@@ -459,6 +497,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     T.stage_len = T.ranges[T.n_ranges - 1][0] + T.ranges[T.n_ranges - 1][1] - T.stage_lo;
   }
   if ((T.L & 1) && T.n_segs > 0) { delete t; return cz_fail(CZ_EINVAL, "%s", "table segments need an even obs_len"); }
+
   T.V = d->num_variants; T.P = d->num_layouts; T.B = d->num_book; T.max_steps = d->max_steps;
   T.end_all = d->end_all; T.grace = d->grace_period; T.n_switches = d->num_switches; T.n_blocks = d->num_blocks;
   T.rows = T.D + T.A + CZ_NUM_MISC_ROWS;
@@ -484,11 +523,36 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   UP(pool, d->pool, (size_t)T.P * T.rows);
   UP(default_recipes, d->default_recipes, T.R);
 #undef UP
+  if (rc == CZ_OK) {  // read-only shared-memory image of a block: LUTs + the small tables
+    static BlockSmem img;
+    memset(&img, 0, sizeof(img));
+    for (int i = 0; i < 2 * T.W - 1; ++i) img.xlut[i] = d->xlut[i];
+    for (int i = 0; i < 2 * T.H - 1; ++i) img.ylut[i] = d->ylut[i];
+    SmemTabs& w = img.tabs;
+    const int nv = T.V < CZ_SV ? T.V : CZ_SV, nb = T.B < CZ_SB ? T.B : CZ_SB;
+    for (int v = 0; v < nv; ++v) {
+      for (int k = 0; k < 8; ++k) w.static_masks[v][k] = d->static_masks[v * 8 + k];
+      for (int c = 0; c < 64; ++c) w.grid[v][c] = d->grid[v * 64 + c];
+      for (int k = 0; k < T.D; ++k) w.scan_order[v][k] = d->scan_order[v * T.D + k];
+      for (int k = 0; k < 4 * CZ_MAX_SPECIAL; ++k) w.special_cells[v][k] = d->special_cells[v * 4 * CZ_MAX_SPECIAL + k];
+      for (int k = 0; k < T.S; ++k) w.static_cells[v][k] = d->static_cells[v * T.S + k];
+    }
+    for (int b = 0; b < nb; ++b) {
+      for (int k = 0; k < CZ_MAX_NODES; ++k) w.recipe_nodes[b][k] = d->recipe_nodes[b * CZ_MAX_NODES + k];
+      w.recipe_len[b] = d->recipe_len[b];
+    }
+    for (int i = 0; i < T.D; ++i) { w.slot_type[i] = d->slot_type[i]; w.slot_tf[i] = d->type_flags[d->slot_type[i]]; }
+    for (int i = 0; i < T.T; ++i) { w.type_base[i] = d->type_base[i]; w.type_count[i] = d->type_count[i]; }
+    const BlockSmem* dimg = nullptr;
+    rc = upload(t, &img, 1, &dimg);
+    T.blob = dimg;
+  }
   if (rc != CZ_OK) { cz_tables_destroy(t); return rc; }
   size_t smem = cz_smem_bytes(T);
   if (smem > (size_t)prop.sharedMemPerBlockOptin) { cz_tables_destroy(t); return cz_fail(CZ_ELIMIT, "%s", "obs_len too large for shared memory staging"); }
   // the specialised row writer: one lane per computed slot, one computed range, two table loads per lane
-  t->simple = T.n_comp <= 32 && T.n_ranges == 1 && T.tab_len <= 128 && (T.L & 1) == 0;
+  t->simple = T.A * T.n_comp <= 32 && T.n_comp > 0 && T.n_ranges == 1 && T.tab_len <= 128 && (T.L & 1) == 0 &&
+              T.V <= CZ_SV && T.B <= CZ_SB;
 #define SET_SMEM(M, O) \
   CZ_CUDA(cudaFuncSetAttribute(cz_env_kernel<M, O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
   CZ_CUDA(cudaFuncSetAttribute(cz_env_kernel<M, O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))

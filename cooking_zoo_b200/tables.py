@@ -155,6 +155,30 @@ def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_sche
         pool[li, D + num_agents + ROW_VARIANT] = variant_of[key]
     V = len(variants)
 
+    # ---- slot compaction: a dynamic slot no pooled layout fills (and whose type cannot spawn) is
+    # always empty, so it does not exist on the device.  Device slots keep canonical order.
+    occupied = ((pool[:, :D] >> 6) & 1).any(axis=0)
+    for tid, (b, c) in enumerate(zip(type_base, type_count)):
+        if E.entity(dyn_types[tid]).flags & E.TF_SPAWN and occupied[b:b + c].any():
+            occupied[b:b + c] = True          # Bread.chop appends a twin (world_objects.py:738-745)
+    if not occupied.any():
+        occupied[0] = True
+    canon_of_dev = np.flatnonzero(occupied)
+    dev_of_canon = np.full(D, -1, np.int64)
+    dev_of_canon[canon_of_dev] = np.arange(len(canon_of_dev))
+    D_canon, D = D, len(canon_of_dev)
+    canon_type_base, canon_type_count = type_base, type_count
+    type_count = [int(occupied[b:b + c].sum()) for b, c in zip(canon_type_base, canon_type_count)]
+    type_base = [int(occupied[:b].sum()) for b in canon_type_base]
+    for b, c in zip(canon_type_base, canon_type_count):
+        live = occupied[b:b + c]
+        assert not (~live[:-1] & live[1:]).any(), "live slots of a type must be a prefix"
+    rows = D + num_agents + NUM_MISC
+    pool = np.concatenate([pool[:, canon_of_dev], pool[:, D_canon:]], axis=1)
+    variants = [(g, sc, dev_of_canon[sn[occupied[sn]]].astype(np.uint8), sp, m) for g, sc, sn, sp, m in variants]
+    obs_slots = [(o, fv, kind, (int(dev_of_canon[idx]) if kind == 1 else idx)) for o, fv, kind, idx in obs_slots
+                 if not (kind == 1 and dev_of_canon[idx] < 0)]
+
     # ---- recipes ---------------------------------------------------------------------
     book = active_book()
     pool_names = list(recipe_pool) if recipe_pool is not None else []
@@ -187,6 +211,7 @@ def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_sche
     t.level_object, t.meta, t.layouts = level_object, meta, layouts
     t.width, t.height, t.num_agents, t.num_recipes = W, H, num_agents, len(recipes)
     t.num_dyn_slots, t.num_static_slots, t.num_types = D, S, len(dyn_types)
+    t.num_canon_slots, t.canon_of_dev, t.dev_of_canon = D_canon, canon_of_dev, dev_of_canon
     t.obs_len, t.rows, t.num_variants, t.num_layouts = L, rows, V, len(layouts)
     t.max_steps, t.end_all, t.grace_period = int(max_steps), int(bool(end_condition_all_dishes)), int(grace_period)
     t.reward_scheme = rs
@@ -213,12 +238,12 @@ def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_sche
     t.type_base = np.array(type_base, np.uint8)
     t.type_count = np.array(type_count, np.uint8)
     t.obs_slots = np.array([o | fv << 12 | kind << 15 | idx << 17 for o, fv, kind, idx in obs_slots], np.uint32)
-    _compile_obs_plan(t, obs_slots)
     t.recipe_names = pool_names
     t.recipe_nodes, t.recipe_len = recipe_nodes, recipe_len
     t.default_recipes = np.array([pool_names.index(n) for n in recipes], np.uint8)
     t.pool = pool
     t.static_base = static_base
+    _compile_obs_plan(t, obs_slots)
     return t
 
 
@@ -264,12 +289,18 @@ def _compile_obs_plan(t, obs_slots):
     in_table = np.zeros(L, bool)
     for a, n in runs:
         in_table[a:a + n] = True
-    # slots whose elements are not covered by a kept run become computed slots
+    # slots whose elements are not covered by a kept run become computed slots; a slot that can
+    # never be occupied (no pooled layout fills it and its type cannot spawn) is left out: the
+    # kernel zero-fills the staging rows once and only rewrites the listed slots
     comp = []
     for off, fv, kind, idx in obs_slots:
         n = E.FV_LEN[fv]
         if not in_table[off:off + n].all():
             assert not in_table[off:off + n].any()
+            if kind == 2 and idx >= t.num_agents:
+                continue
+            if kind == 0 and bool((t.static_cells[:, idx] == 0xFF).all()):
+                continue
             comp.append((off, n, kind, idx))
     # contiguous computed ranges of the row -> one bulk store each
     ranges, j = [], 0
