@@ -380,11 +380,11 @@ __device__ __forceinline__ uint32_t cz_recipe_marks(const CzDev& T, const EnvReg
 
 // CookingEnvironment.accumulated_step (cooking_env.py:243-269) for one environment.
 // Writes reward f64[A], terminated u8[A], truncated u8[A] of this environment.
-template <bool FAST>
+template <bool FAST, int NA>
 __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const uint32_t act_packed,
                                             double* __restrict__ reward, uint8_t* __restrict__ term_out,
                                             uint8_t* __restrict__ trunc_out) {
-  const int A = T.A;
+  const int A = NA ? NA : T.A;  // compile-time agent count in the specialised kernels
   const SmemTabs* st = e.st;
   const uint32_t t = TI_T(e.tinfo) + 1;  // :244
   uint32_t active = 0;

@@ -134,13 +134,6 @@ __device__ __forceinline__ void cz_slot_store(const LaneSlot& ls, uint32_t xy, u
     if (k < (int)ls.flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, (fb >> k & 1u) ? 0x3FF00000u : 0u);
 }
 
-// Image of the read-only part of a block's shared memory, built on the host (cz_tables_create) and
-// copied by every block with one 16-byte load per thread.
-struct BlockSmem {
-  double xlut[16];  // k / W for k = -(W-1)..W-1
-  double ylut[16];
-  SmemTabs tabs;
-};
 // per-warp words: object columns [D][33], agent columns [A][33], then sbits/variant/wobs [32]
 struct WarpSmem {
   uint32_t* obj;
@@ -149,19 +142,106 @@ struct WarpSmem {
   uint32_t* variant;
   uint32_t* wobs;
 };
+
+// Observation phase of the specialised kernels (NA agents known at compile time; one lane per
+// (observer, slot) pair; one computed range; at most 64 table double2 per row).
+// Software pipeline over the tile's environments: the table segments of environment le+1 are
+// requested (LDG) right after environment le's staging rows went to the TMA engine and are stored
+// one iteration later, so neither the L2 latency nor the proxy fence's drain sits on the critical path.
+template <int NA>
+__device__ __forceinline__ void cz_obs_phase_fast(const CzDev& T, const SmemTabs* st, const WarpSmem* ws, const double* sxl,
+                                                  const double* syl, double* stage, uint32_t stage_s, int row_stride,
+                                                  uint32_t row_bytes, double* genv, int n_here, int lane, int tab2, int L2,
+                                                  size_t row_gbytes, uint32_t r0_bytes, size_t r0_goff, uint32_t r0_soff) {
+  constexpr int NP = NA < 2 ? NA : 2;  // rows whose table segments are prefetched
+  const LaneSlot ls = cz_lane_slot(T, lane < NA * T.n_comp ? lane % T.n_comp : -1, lane / T.n_comp, lane);
+  const double2* tab0 = reinterpret_cast<const double2*>(T.obs_table) + lane;
+  const size_t var_stride = (size_t)64 * tab2;
+  const bool self = ls.kind == 2 && (int)ls.idx == ls.agent;
+  const uint32_t* my_me = ws->ag + ls.agent * OSTRIDE;  // the observer of this lane's pair
+  double* my_row = stage + ls.agent * row_stride;
+
+  double2 v0[NP], v1[NP];
+  {  // prefetch for the first environment
+    const double2* tab = tab0 + (size_t)ws->variant[0] * var_stride;
+#pragma unroll
+    for (int a = 0; a < NP; ++a) {
+      const double2* src = tab + (ws->ag[a * OSTRIDE] & 63u) * tab2;
+      if (ls.t0 >= 0) v0[a] = __ldg(src);
+      if (ls.t1 >= 0) v1[a] = __ldg(src + 32);
+    }
+  }
+#pragma unroll 1
+  for (int le = 0; le < n_here; ++le, genv += (size_t)NA * T.L) {
+    const bool w = ws->wobs[le] != 0;
+    const uint32_t sb = ws->sbits[le], var = ws->variant[le];
+    uint32_t xy = 0, fb = 0;
+    if (ls.off >= 0) cz_slot_state<true>(T, st, ls, ws->obj, ws->ag, sb, var, le, xy, fb);
+    const uint32_t me = my_me[le];
+    // the bulk stores of the previous environment must have finished reading the staging rows
+    if (lane == 0) cz_bulk_wait_read<0>();
+    __syncwarp();
+    if (ls.off >= 0) cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, self, sxl, syl, my_row);
+    cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0 && w) {  // one elected lane hands the computed range of the NA rows to the TMA engine
+      char* gp = reinterpret_cast<char*>(genv) + r0_goff;
+      uint32_t sp = stage_s + r0_soff;
+#pragma unroll
+      for (int a = 0; a < NA; ++a, gp += row_gbytes, sp += row_bytes) cz_bulk_store_s(gp, sp, r0_bytes);
+      cz_bulk_commit();
+    }
+    // table segments: rows 0..NP-1 were requested one iteration ago
+    double2* g2 = reinterpret_cast<double2*>(genv);
+    if (w) {
+#pragma unroll
+      for (int a = 0; a < NP; ++a) {
+        if (ls.t0 >= 0) g2[a * L2 + ls.t0] = v0[a];
+        if (ls.t1 >= 0) g2[a * L2 + ls.t1] = v1[a];
+      }
+#pragma unroll
+      for (int a = NP; a < NA; ++a) {  // more than two agents: loaded and stored here
+        const double2* src = tab0 + (size_t)var * var_stride + (ws->ag[a * OSTRIDE + le] & 63u) * tab2;
+        if (ls.t0 >= 0) g2[a * L2 + ls.t0] = __ldg(src);
+        if (ls.t1 >= 0) g2[a * L2 + ls.t1] = __ldg(src + 32);
+      }
+    }
+    if (le + 1 < n_here) {  // request the table segments of the next environment
+      const double2* tab = tab0 + (size_t)ws->variant[le + 1] * var_stride;
+#pragma unroll
+      for (int a = 0; a < NP; ++a) {
+        const double2* src = tab + (ws->ag[a * OSTRIDE + le + 1] & 63u) * tab2;
+        if (ls.t0 >= 0) v0[a] = __ldg(src);
+        if (ls.t1 >= 0) v1[a] = __ldg(src + 32);
+      }
+    }
+  }
+  if (lane == 0) cz_bulk_wait_read<0>();  // staging and columns are reused by the next tile
+}
+
+// Image of the read-only part of a block's shared memory, built on the host (cz_tables_create) and
+// copied by every block with one 16-byte load per thread.
+struct BlockSmem {
+  double xlut[16];  // k / W for k = -(W-1)..W-1
+  double ylut[16];
+  SmemTabs tabs;
+};
 __host__ __device__ inline size_t cz_warp_words(int D, int A) { return (size_t)(D + A) * OSTRIDE + 32 * 3; }
 __host__ __device__ inline size_t cz_block_smem_head() { return (sizeof(BlockSmem) + 15) & ~(size_t)15; }
 
-template <int MODE, int OBS, bool FAST>
+template <int MODE, int OBS, int NA>
 __global__ void __launch_bounds__(CZ_THREADS, CZ_MIN_BLOCKS)
 cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, const uint8_t* __restrict__ actions,
               const int32_t* __restrict__ layout_ids, const uint8_t* __restrict__ recipe_ids,
               const uint8_t* __restrict__ mask, double* __restrict__ obs, double* __restrict__ reward,
               uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint32_t* __restrict__ errflags,
               int n_envs, uint32_t flags, uint64_t seed, int64_t env_offset) {
+  // NA = 0: generic kernel (run-time agent count, tables in global memory, any observation plan)
+  // NA > 0: specialised kernel for NA agents (tables in shared memory, packed observation lanes)
+  constexpr bool FAST = NA != 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = T.D, A = T.A;
+  const int D = T.D, A = FAST ? NA : T.A;
   BlockSmem* bs = reinterpret_cast<BlockSmem*>(smem_raw);
   WarpSmem wsv;
   WarpSmem* ws = &wsv;
@@ -259,7 +339,7 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
         }
       } else if (MODE == MODE_STEP) {
         // ---- phase 2: one accumulated_step per lane
-        cz_step_env<FAST>(T, e, act, reward + (size_t)env * A, term + (size_t)env * A, trunc + (size_t)env * A);
+        cz_step_env<FAST, NA>(T, e, act, reward + (size_t)env * A, term + (size_t)env * A, trunc + (size_t)env * A);
       }
 
       // ---- phase 3: shared columns -> state
@@ -285,74 +365,57 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
     // hoisted above the dynamics (where they would be spilled: registers are capped for 28 warps/SM).
     int lane_o = lane;
     asm volatile("" : "+r"(lane_o));
-    const LaneSlot ls = FAST ? cz_lane_slot(T, lane_o < A * T.n_comp ? lane_o % T.n_comp : -1, lane_o / T.n_comp, lane_o)
-                             : cz_lane_slot(T, lane_o, 0, lane_o);
+    const int n_here = min(32, n_envs - tile * 32);
+    double* genv = obs + (size_t)tile * 32 * A * T.L;
+    const size_t env_doubles = (size_t)A * T.L;
     const int tab2 = T.tab_len >> 1, L2 = T.L >> 1;
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     const size_t row_gbytes = (size_t)T.L * 8;
     const uint32_t r0_bytes = (uint32_t)T.ranges[0][1] * 8;
     const size_t r0_goff = (size_t)T.ranges[0][0] * 8;
     const uint32_t r0_soff = (uint32_t)(T.ranges[0][0] - T.stage_lo) * 8;
-    const int n_here = min(32, n_envs - tile * 32);
-    double* genv = obs + (size_t)tile * 32 * A * T.L;
-    const size_t env_doubles = (size_t)A * T.L;
+    if constexpr (FAST) {
+      cz_obs_phase_fast<NA>(T, st, ws, sxl, syl, stage, stage_s, row_stride, (uint32_t)row_bytes, genv, n_here, lane_o, tab2, L2,
+                            row_gbytes, r0_bytes, r0_goff, r0_soff);
+      __syncwarp();
+      continue;
+    } else {
+    const LaneSlot ls = cz_lane_slot(T, lane_o, 0, lane_o);
 #pragma unroll 1
     for (int le = 0; le < n_here; ++le, genv += env_doubles) {
       if (!ws->wobs[le]) continue;
       const uint32_t sb = ws->sbits[le], var = ws->variant[le];
       const double2* tab = reinterpret_cast<const double2*>(T.obs_table) + (size_t)var * 64 * tab2 + lane;
-      // prefetch the table segments of the first two rows (their L2 latency hides behind the slot decode)
-      const uint32_t meA = ws->ag[le], meB = A > 1 ? ws->ag[OSTRIDE + le] : meA;
-      double2 vA0, vA1, vB0, vB1;
-      {
-        const double2* srcA = tab + (meA & 63u) * tab2;
-        const double2* srcB = tab + (meB & 63u) * tab2;
-        if (ls.t0 >= 0) { vA0 = __ldg(srcA); vB0 = __ldg(srcB); }
-        if (ls.t1 >= 0) { vA1 = __ldg(srcA + 32); vB1 = __ldg(srcB + 32); }
-      }
       uint32_t xy = 0, fb = 0;
-      if (ls.off >= 0) cz_slot_state<FAST>(T, st, ls, ws->obj, ws->ag, sb, var, le, xy, fb);
+      if (ls.off >= 0) cz_slot_state<false>(T, st, ls, ws->obj, ws->ag, sb, var, le, xy, fb);
       if (OBS == OBS_TMA) {
         // the bulk stores of the previous environment must have finished reading the staging rows
         if (lane == 0) cz_bulk_wait_read<0>();
         __syncwarp();
       }
-      if (FAST) {  // one pass: this lane's (observer, slot) pair
-        if (ls.off >= 0) {
-          const uint32_t me = ls.agent == 0 ? meA : (ls.agent == 1 ? meB : ws->ag[ls.agent * OSTRIDE + le]);
-          cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, ls.kind == 2 && (int)ls.idx == ls.agent, sxl, syl,
-                        stage + ls.agent * row_stride);
-        }
-      }
       double* row = stage;
       double2* g2 = reinterpret_cast<double2*>(genv);
 #pragma unroll 1
       for (int a = 0; a < A; ++a, row += row_stride, g2 += L2) {
-        const uint32_t me = a == 0 ? meA : (a == 1 ? meB : ws->ag[a * OSTRIDE + le]);
-        double2 v0 = a == 0 ? vA0 : vB0, v1 = a == 0 ? vA1 : vB1;
-        if (a >= 2) {  // more than two agents: no prefetch
-          const double2* src = tab + (me & 63u) * tab2;
-          if (ls.t0 >= 0) v0 = __ldg(src);
-          if (ls.t1 >= 0) v1 = __ldg(src + 32);
-        }
-        if (!FAST) {  // one lane per slot, as many passes as it takes
-          if (ls.off >= 0)
-            cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, ls.kind == 2 && (int)ls.idx == a, sxl, syl, row);
-          for (int q = lane + 32; q < T.n_comp; q += 32) {
-            const LaneSlot l2 = cz_lane_slot(T, q, 0, lane);
-            uint32_t xy2, fb2;
-            cz_slot_state<FAST>(T, st, l2, ws->obj, ws->ag, sb, var, le, xy2, fb2);
-            cz_slot_store(l2, xy2, fb2, me & 7u, (me >> 3) & 7u, l2.kind == 2 && (int)l2.idx == a, sxl, syl, row);
-          }
+        const uint32_t me = ws->ag[a * OSTRIDE + le];
+        const double2* src = tab + (me & 63u) * tab2;
+        double2 v0, v1;
+        if (ls.t0 >= 0) v0 = __ldg(src);
+        if (ls.t1 >= 0) v1 = __ldg(src + 32);
+        // one lane per slot, as many passes as it takes
+        if (ls.off >= 0)
+          cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, ls.kind == 2 && (int)ls.idx == a, sxl, syl, row);
+        for (int q = lane + 32; q < T.n_comp; q += 32) {
+          const LaneSlot l2 = cz_lane_slot(T, q, 0, lane);
+          uint32_t xy2, fb2;
+          cz_slot_state<false>(T, st, l2, ws->obj, ws->ag, sb, var, le, xy2, fb2);
+          cz_slot_store(l2, xy2, fb2, me & 7u, (me >> 3) & 7u, l2.kind == 2 && (int)l2.idx == a, sxl, syl, row);
         }
         if (ls.t0 >= 0) g2[ls.t0] = v0;
         if (ls.t1 >= 0) g2[ls.t1] = v1;
-        if (!FAST) {
-          const double2* src = tab + (me & 63u) * tab2 - lane;
-          for (int k = lane + 64; k < tab2; k += 32) {  // table rows longer than 64 double2
-            const int n0 = T.segs[0][1] >> 1;
-            g2[k < n0 ? (T.segs[0][0] >> 1) + k : (T.segs[1][0] >> 1) + k - n0] = __ldg(src + k);
-          }
+        for (int k = lane + 64; k < tab2; k += 32) {  // table rows longer than 64 double2
+          const int n0 = T.segs[0][1] >> 1;
+          g2[k < n0 ? (T.segs[0][0] >> 1) + k : (T.segs[1][0] >> 1) + k - n0] = __ldg(src - lane + k);
         }
       }
       if (OBS == OBS_TMA) {
@@ -365,11 +428,9 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
 #pragma unroll 1
           for (int a = 0; a < A; ++a, gp += row_gbytes, sp += (uint32_t)row_bytes) {
             cz_bulk_store_s(gp, sp, r0_bytes);
-            if (!FAST) {
-              for (int r = 1; r < T.n_ranges; ++r)
-                cz_bulk_store_s(gp + (T.ranges[r][0] - T.ranges[0][0]) * 8, sp + (T.ranges[r][0] - T.ranges[0][0]) * 8,
-                                (uint32_t)T.ranges[r][1] * 8);
-            }
+            for (int r = 1; r < T.n_ranges; ++r)
+              cz_bulk_store_s(gp + (T.ranges[r][0] - T.ranges[0][0]) * 8, sp + (T.ranges[r][0] - T.ranges[0][0]) * 8,
+                              (uint32_t)T.ranges[r][1] * 8);
           }
           cz_bulk_commit();
         }
@@ -394,6 +455,7 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
       if (lane == 0) cz_bulk_wait_read<0>();  // staging and columns are reused by the next tile
     }
     __syncwarp();
+    }
   }
 }
 
@@ -550,15 +612,21 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   if (rc != CZ_OK) { cz_tables_destroy(t); return rc; }
   size_t smem = cz_smem_bytes(T);
   if (smem > (size_t)prop.sharedMemPerBlockOptin) { cz_tables_destroy(t); return cz_fail(CZ_ELIMIT, "%s", "obs_len too large for shared memory staging"); }
-  // the specialised row writer: one lane per computed slot, one computed range, two table loads per lane
+  // the specialised kernels: one lane per (observer, slot) pair, one computed range, two table loads per
+  // lane, small tables resident in shared memory
   t->simple = T.A * T.n_comp <= 32 && T.n_comp > 0 && T.n_ranges == 1 && T.tab_len <= 128 && (T.L & 1) == 0 &&
-              T.V <= CZ_SV && T.B <= CZ_SB;
-#define SET_SMEM(M, O) \
-  CZ_CUDA(cudaFuncSetAttribute(cz_env_kernel<M, O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-  CZ_CUDA(cudaFuncSetAttribute(cz_env_kernel<M, O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
-  SET_SMEM(MODE_STEP, OBS_TMA); SET_SMEM(MODE_STEP, OBS_STG);
-  SET_SMEM(MODE_RESET, OBS_TMA); SET_SMEM(MODE_RESET, OBS_STG);
-  SET_SMEM(MODE_OBSERVE, OBS_TMA); SET_SMEM(MODE_OBSERVE, OBS_STG);
+              T.V <= CZ_SV && T.B <= CZ_SB && t->obs_path == OBS_TMA;
+  {
+    const char* g = getenv("CZ_GENERIC");
+    if (g && g[0] == '1') t->simple = 0;
+  }
+#define SET_SMEM(K) CZ_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+#define SET_MODE(M)                                                                                    \
+  SET_SMEM((cz_env_kernel<M, OBS_TMA, 0>)); SET_SMEM((cz_env_kernel<M, OBS_STG, 0>));                   \
+  SET_SMEM((cz_env_kernel<M, OBS_TMA, 1>)); SET_SMEM((cz_env_kernel<M, OBS_TMA, 2>));                   \
+  SET_SMEM((cz_env_kernel<M, OBS_TMA, 3>)); SET_SMEM((cz_env_kernel<M, OBS_TMA, 4>))
+  SET_MODE(MODE_STEP); SET_MODE(MODE_RESET); SET_MODE(MODE_OBSERVE);
+#undef SET_MODE
 #undef SET_SMEM
   *out = t;
   return CZ_OK;
@@ -597,11 +665,21 @@ static int cz_launch(const cz_tables* t, uint32_t* state, const uint8_t* actions
   size_t smem = cz_smem_bytes(t->dev);
   int grid = cz_grid(t, n_envs);
   cudaStream_t s = (cudaStream_t)stream;
-#define CZ_GO(O, S)                                                                                                  \
-  cz_env_kernel<MODE, O, S><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, actions, layout_ids, recipe_ids, mask, obs, \
-                                                          reward, term, trunc, err, n_envs, flags, seed, env_offset)
-  if (t->obs_path == OBS_TMA) { if (t->simple) CZ_GO(OBS_TMA, true); else CZ_GO(OBS_TMA, false); }
-  else { if (t->simple) CZ_GO(OBS_STG, true); else CZ_GO(OBS_STG, false); }
+#define CZ_GO(O, NA)                                                                                                  \
+  cz_env_kernel<MODE, O, NA><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, actions, layout_ids, recipe_ids, mask, obs, \
+                                                           reward, term, trunc, err, n_envs, flags, seed, env_offset)
+  if (t->simple) {
+    switch (t->dev.A) {
+      case 1: CZ_GO(OBS_TMA, 1); break;
+      case 2: CZ_GO(OBS_TMA, 2); break;
+      case 3: CZ_GO(OBS_TMA, 3); break;
+      default: CZ_GO(OBS_TMA, 4); break;
+    }
+  } else if (t->obs_path == OBS_TMA) {
+    CZ_GO(OBS_TMA, 0);
+  } else {
+    CZ_GO(OBS_STG, 0);
+  }
 #undef CZ_GO
   g_launches.fetch_add(1);
   CZ_CUDA(cudaGetLastError());
