@@ -33,12 +33,19 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 # (SURVEY.md Appendix E16).  Moves are (dx,dy)->action: 1 left, 2 right, 3 down, 4 up.
 
 
+def _path(p):
+    """levels / meta files named by a repo-relative .json path are resolved against the repo root"""
+    return os.path.join(ROOT, p) if p.endswith(".json") else p
+
+
 def record(cfg, seeds, T, policy, teleports=None):
     traces = []
     for seed in seeds:
-        env = RefEnv(seed, cfg["level"], cfg["meta_file"], cfg["num_agents"], cfg["max_steps"],
+        env = RefEnv(seed, _path(cfg["level"]), _path(cfg["meta_file"]), cfg["num_agents"], cfg["max_steps"],
                      cfg["recipes"], end_condition_all_dishes=cfg["end_all"],
                      reward_scheme=cfg.get("reward_scheme"))
+        if hasattr(policy, "bind"):
+            policy.bind(env, cfg)
         A = cfg["num_agents"]
         rng = np.random.default_rng(1000 + seed)
         tr = {"layout": env.layout(), "actions": np.zeros((T, A), np.int8),
@@ -114,6 +121,27 @@ def sticky(rng, t, A, prev):
     return np.where(keep & (t > 0), prev, new)
 
 
+class Heuristic:
+    """The reference's own scripted cook (cooking_agents/cooking_agent.py) on the live object graph,
+    with an epsilon of uniform actions: the only streams here that finish recipes."""
+
+    def __init__(self, eps):
+        self.eps = eps
+
+    def bind(self, env, cfg):
+        from cooking_zoo.cooking_agents.cooking_agent import CookingAgent
+        self.env = env
+        self.cooks = [CookingAgent(cfg["recipes"][i], f"agent-{i + 1}") for i in range(cfg["num_agents"])]
+
+    def __call__(self, rng, t, A, prev):
+        from collections import defaultdict
+        sym = defaultdict(list)
+        sym.update(self.env.env.world.world_objects)
+        sym["Agent"] = self.env.env.world.agents
+        act = np.array([int(c.step(sym)) for c in self.cooks])
+        return np.where(rng.random(A) < self.eps, rng.integers(0, 5, size=A), act)
+
+
 def scripted(seq):
     def pol(rng, t, A, prev):
         return np.array(seq[t] if t < len(seq) else [0] * A)
@@ -142,6 +170,35 @@ def main():
     for k in range(0, 8, 2):
         cfg = dict(base, num_agents=2, recipes=book[k:k + 2], end_all=False, max_steps=200)
         save(f"book_{k}", cfg, record(cfg, range(400 + k, 402 + k), 200, sticky), 200)
+    # heuristic cooks: recipes get completed -> bonus reward, termination (any / all dishes)
+    cfgh = dict(base, num_agents=2, recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=False, max_steps=200)
+    save("heuristic_any", cfgh, record(cfgh, range(500, 506), 200, Heuristic(0.1)), 200)
+    cfgh2 = dict(base, num_agents=2, recipes=["TomatoSalad", "AppleWatermelon"], end_all=True, max_steps=300)
+    save("heuristic_all", cfgh2, record(cfgh2, range(510, 516), 300, Heuristic(0.05)), 300)
+    cfgh1 = dict(base, num_agents=1, recipes=["TomatoLettuceSalad"], end_all=False, max_steps=200)
+    save("heuristic_cfg1", cfgh1, record(cfgh1, range(520, 524), 200, Heuristic(0.0)), 200)
+    # node rewards + penalty: a completed dish picked up again (recipe_undone)
+    cfgp = dict(cfgh2, end_all=True, reward_scheme={"recipe_reward": 20, "max_time_penalty": -5,
+                                                   "recipe_penalty": -40, "recipe_node_reward": 2})
+    save("heuristic_nodes", cfgp, record(cfgp, range(530, 534), 300, Heuristic(0.15)), 300)
+    # Switch / Block level
+    cfgs = dict(base, level="switch_test", num_agents=2, recipes=["TomatoLettuceSalad", "CarrotBanana"],
+                end_all=True, max_steps=300)
+    save("switch_uniform", cfgs, record(cfgs, range(600, 606), 300, sticky), 300)
+    # open 4-agent kitchen (custom level + meta by path): agent-agent collisions, three/four agents
+    cfg4a = dict(base, level="tests/golden/levels/open4.json", meta_file="tests/golden/levels/meta4.json",
+                 num_agents=4, recipes=["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"],
+                 end_all=True, max_steps=250)
+    save("open4_agents4", cfg4a, record(cfg4a, range(700, 706), 250, sticky), 250)
+    cfg3a = dict(cfg4a, num_agents=3, recipes=["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad"])
+    save("open4_agents3", cfg3a, record(cfg3a, range(710, 714), 250, uniform), 250)
+    # tiny 4-agent room: crowded, constant collisions; exercises the NA=3/4 specialised kernels
+    cfgt = dict(base, level="tests/golden/levels/tiny4.json", meta_file="tests/golden/levels/meta4.json",
+                num_agents=4, recipes=["TomatoSalad", "TomatoSalad", "no_recipe", "no_recipe"], end_all=False,
+                max_steps=150)
+    save("tiny4_agents4", cfgt, record(cfgt, range(720, 726), 150, uniform), 150)
+    cfgt3 = dict(cfgt, num_agents=3, recipes=["TomatoSalad", "no_recipe", "no_recipe"])
+    save("tiny4_agents3", cfgt3, record(cfgt3, range(730, 734), 150, sticky), 150)
 
 
 if __name__ == "__main__":

@@ -13,11 +13,17 @@ def golden_files():
     return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
 def load_golden(path):
     z = np.load(path)
     g = {k: z[k] for k in z.files}
     g["config"] = json.loads(str(g["config"]))
     g["layouts"] = json.loads(str(g["layouts"]))
+    for key in ("level", "meta_file"):        # repo-relative .json paths (custom levels)
+        if g["config"][key].endswith(".json"):
+            g["config"][key] = os.path.join(ROOT, g["config"][key])
     return g
 
 
