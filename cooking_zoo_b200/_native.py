@@ -30,7 +30,8 @@ class TableDesc(C.Structure):
                  ("reward_time", C.c_double), ("respawn_rate", C.c_double), ("despawn_rate", C.c_double)]
                 + [(n, _P) for n in ("xlut", "ylut", "grid", "static_cells", "scan_order", "special_cells",
                                      "static_masks", "slot_type", "type_flags", "type_base", "type_count",
-                                     "comp_slots", "obs_table", "recipe_nodes", "recipe_len", "pool", "default_recipes")])
+                                     "comp_slots", "obs_table", "recipe_nodes", "recipe_len", "pool", "default_recipes",
+                                     "spawn_x", "spawn_y", "spawn_n")])
 
 
 # every symbol include/cz_b200.h declares: name -> (restype, argtypes)
@@ -39,6 +40,7 @@ SIGNATURES = {
     "cz_last_error": (C.c_char_p, []),
     "cz_launch_count": (C.c_uint64, []),
     "cz_layout_draw": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint64]),
+    "cz_spawn_uniform": (C.c_double, [C.c_uint64] * 5),
     "cz_tables_create": (C.c_int, [C.POINTER(TableDesc), C.c_int, C.POINTER(_P)]),
     "cz_tables_destroy": (C.c_int, [_P]),
     "cz_state_rows": (C.c_int, [_P]),
@@ -105,7 +107,8 @@ def make_desc(t):
                         ("type_base", np.uint8), ("type_count", np.uint8), ("comp_slots", np.uint32),
                         ("obs_table", np.float64),
                         ("recipe_nodes", np.uint32), ("recipe_len", np.uint8), ("pool", np.uint32),
-                        ("default_recipes", np.uint8)):
+                        ("default_recipes", np.uint8), ("spawn_x", np.uint8), ("spawn_y", np.uint8),
+                        ("spawn_n", np.uint8)):
         arr = np.ascontiguousarray(getattr(t, name), dtype=dtype)
         keep.append(arr)
         setattr(d, name, arr.ctypes.data)

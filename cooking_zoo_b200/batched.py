@@ -50,8 +50,6 @@ class BatchedCookingEnv:
                                       "raises AttributeError in the reference itself)")
         if render:
             raise NotImplementedError("rendering is out of scope")
-        if agent_respawn_rate != 0.0 or agent_despawn_rate != 0.0:
-            raise NotImplementedError("agent despawn/respawn needs host-supplied uniforms (not built yet)")
         self.lib = _native.load_library()       # raises when the CUDA library is missing
         if not torch.cuda.is_available():
             raise _native.NativeError("BatchedCookingEnv needs a CUDA device (there is no CPU fallback)")

@@ -33,6 +33,9 @@ struct CzDev {
   const uint8_t* recipe_len;
   const uint32_t* pool;
   const uint8_t* default_recipes;
+  const uint8_t* spawn_x;
+  const uint8_t* spawn_y;
+  const uint8_t* spawn_n;
   const void* blob;  // BlockSmem image (LUTs + SmemTabs), built by cz_tables_create
 };
 
@@ -136,6 +139,16 @@ __device__ __forceinline__ bool cz_walkable(const CzDev& T, const EnvRegs& e, ui
   if (kind == ST_FLOOR || kind == ST_SWITCH) return true;
   if (kind == ST_BLOCK) return (e.sbits & SB_BLK_WALK(g >> 4)) != 0;
   return false;
+}
+
+// c-th uniform draw of environment `env` in step `t` of episode `episode` (cz_spawn_uniform)
+__host__ __device__ __forceinline__ double cz_uniform(uint64_t seed, uint64_t env, uint64_t episode, uint64_t t, uint64_t c) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (env + 1) + 0xD1B54A32D192ED03ull * (episode + 1) +
+               0x8CB92BA72F3D8DD7ull * (t + 1) + 0xF1357AEA2E62A9C5ull * (c + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
 }
 
 __device__ __forceinline__ bool cz_agent_on(const CzDev& T, const EnvRegs& e, uint32_t cell) {
@@ -383,7 +396,7 @@ __device__ __forceinline__ uint32_t cz_recipe_marks(const CzDev& T, const EnvReg
 template <bool FAST, int NA>
 __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const uint32_t act_packed,
                                             double* __restrict__ reward, uint8_t* __restrict__ term_out,
-                                            uint8_t* __restrict__ trunc_out) {
+                                            uint8_t* __restrict__ trunc_out, uint64_t seed, uint64_t genv) {
   const int A = NA ? NA : T.A;  // compile-time agent count in the specialised kernels
   const SmemTabs* st = e.st;
   const uint32_t t = TI_T(e.tinfo) + 1;  // :244
@@ -487,10 +500,46 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
     for (int k = 0; k < CZ_MAX_SPECIAL; ++k)
       if (pressed >> k & 1u) e.sbits ^= blocks;
   }
-  // ---- handle_agent_spawn (cooking_world.py:267-277): grace countdown; the draws that follow
-  // change nothing at the default rates 0.0 (despawn/respawn with host uniforms: see DESIGN.md)
-  for (int i = 0; i < A; ++i)
-    if (A_GRACE(e.ag[i * OSTRIDE]) > 0) e.ag[i * OSTRIDE] -= 1u << 16;
+  // ---- handle_agent_spawn (cooking_world.py:267-277).  At the default rates 0.0 the reference's
+  // draws change nothing, so only the grace countdown remains.
+  if (T.respawn > 0.0 || T.despawn > 0.0) {
+    uint32_t c = 0;  // draws consumed by this environment this step
+    for (int i = 0; i < A; ++i) {
+      uint32_t rec = e.ag[i * OSTRIDE];
+      if (A_GRACE(rec) > 0) { e.ag[i * OSTRIDE] = rec - (1u << 16); continue; }
+      const bool act_i = active >> i & 1u;
+      if (__popc(active) > 1 && act_i) {  // short-circuit order of :273-274: the draw happens only here
+        if (cz_uniform(seed, genv, e.episode, t, c++) < T.despawn) {
+          if (!A_HAS(rec)) {  // despawn_agent :279-284: no-op while holding
+            active &= ~(1u << i);
+            changed |= 1u << i;
+          }
+        }
+      } else if (!act_i) {
+        if (cz_uniform(seed, genv, e.episode, t, c++) < T.respawn) {  // respawn_agent :286-290
+          active |= 1u << i;
+          changed |= 1u << i;
+          const int nx = __ldg(T.spawn_n + 2 * i), ny = __ldg(T.spawn_n + 2 * i + 1);
+          uint32_t cell = A_XY(rec);
+          bool found = false;
+          for (int tries = 0; tries < 1002 && !found; ++tries) {  // parsing.generate_location :154-167
+            int x = __ldg(T.spawn_x + 8 * i + min(nx - 1, (int)(cz_uniform(seed, genv, e.episode, t, c++) * nx)));
+            int y = __ldg(T.spawn_y + 8 * i + min(ny - 1, (int)(cz_uniform(seed, genv, e.episode, t, c++) * ny)));
+            uint32_t cand = (uint32_t)(x | y << 3);
+            if (x < T.W && y < T.H && (TAB_GRID(e.variant, cand) & 15u) == ST_FLOOR && !cz_agent_on(T, e, cand)) {
+              cell = cand;
+              found = true;
+            }
+          }
+          if (!found) e.err |= CZ_ERR_SPAWN_LOC;
+          e.ag[i * OSTRIDE] = (rec & 0xFFC0u) | cell | ((uint32_t)T.grace << 16);
+        }
+      }
+    }
+  } else {
+    for (int i = 0; i < A; ++i)
+      if (A_GRACE(e.ag[i * OSTRIDE]) > 0) e.ag[i * OSTRIDE] -= 1u << 16;
+  }
 
   uint32_t relevant = active | changed;  // compute_relevant_agents :292
 

@@ -339,7 +339,8 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
         }
       } else if (MODE == MODE_STEP) {
         // ---- phase 2: one accumulated_step per lane
-        cz_step_env<FAST, NA>(T, e, act, reward + (size_t)env * A, term + (size_t)env * A, trunc + (size_t)env * A);
+        cz_step_env<FAST, NA>(T, e, act, reward + (size_t)env * A, term + (size_t)env * A, trunc + (size_t)env * A, seed,
+                              (uint64_t)(env_offset + env));
       }
 
       // ---- phase 3: shared columns -> state
@@ -518,6 +519,10 @@ extern "C" uint64_t cz_layout_draw(uint64_t seed, uint64_t env, uint64_t episode
   return z ^ (z >> 31);
 }
 
+extern "C" double cz_spawn_uniform(uint64_t seed, uint64_t env, uint64_t episode, uint64_t t, uint64_t c) {
+  return cz_uniform(seed, env, episode, t, c);
+}
+
 extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** out) {
   if (!d || !out) return cz_fail(CZ_EINVAL, "%s", "null argument");
   *out = nullptr;
@@ -584,6 +589,9 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   UP(recipe_len, d->recipe_len, T.B);
   UP(pool, d->pool, (size_t)T.P * T.rows);
   UP(default_recipes, d->default_recipes, T.R);
+  UP(spawn_x, d->spawn_x, (size_t)T.A * 8);
+  UP(spawn_y, d->spawn_y, (size_t)T.A * 8);
+  UP(spawn_n, d->spawn_n, (size_t)T.A * 2);
 #undef UP
   if (rc == CZ_OK) {  // read-only shared-memory image of a block: LUTs + the small tables
     static BlockSmem img;

@@ -242,6 +242,15 @@ def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_sche
     t.recipe_nodes, t.recipe_len = recipe_nodes, recipe_len
     t.default_recipes = np.array([pool_names.index(n) for n in recipes], np.uint8)
     t.pool = pool
+    # spawn ranges of every agent (parsing.py:147): respawn picks from the lists of its level entry
+    t.spawn_x = np.zeros((num_agents, 8), np.uint8)
+    t.spawn_y = np.zeros((num_agents, 8), np.uint8)
+    t.spawn_n = np.ones((num_agents, 2), np.uint8)
+    for i, (xs, ys) in enumerate(layouts[0].get("agent_spawn", [])[:num_agents]):
+        if len(xs) > 8 or len(ys) > 8:
+            raise ValueError("agent spawn lists longer than 8 entries are not supported")
+        t.spawn_x[i, :len(xs)], t.spawn_y[i, :len(ys)] = xs, ys
+        t.spawn_n[i] = (len(xs), len(ys))
     t.static_base = static_base
     _compile_obs_plan(t, obs_slots)
     return t

@@ -129,6 +129,9 @@ typedef struct cz_table_desc {
   const uint8_t* recipe_len;  /* [B] nodes in the recipe                                    */
   const uint32_t* pool;       /* [P][rows] initial state of every pooled layout             */
   const uint8_t* default_recipes; /* [R] recipe index per slot when no per-env ids are given */
+  const uint8_t* spawn_x;     /* [A][8] X_POSITION list of the agent's spawn entry (parsing.py:147)  */
+  const uint8_t* spawn_y;     /* [A][8] Y_POSITION list                                      */
+  const uint8_t* spawn_n;     /* [A][2] lengths of the two lists                             */
 } cz_table_desc;
 
 typedef struct cz_tables cz_tables;
@@ -170,6 +173,13 @@ int cz_step_host(cz_tables* t, uint32_t* state_dev, const uint8_t* actions_host,
 
 /* The counter-based draw used by auto-reset (splitmix64 finaliser over seed, env, episode). */
 uint64_t cz_layout_draw(uint64_t seed, uint64_t global_env, uint64_t episode);
+
+/* Randomness of handle_agent_spawn (cooking_world/cooking_world.py:267-290).  The reference draws
+ * np.random.random() for despawn/respawn and random.sample(list, 1) for the respawn cell from
+ * global generators; here the c-th draw consumed by environment g in step t of its episode is the
+ * uniform double cz_spawn_uniform(seed, g, episode, t, c) in [0, 1), and a list pick is
+ * list[floor(u * len)].  Parity harnesses patch the reference's call sites to read this stream. */
+double cz_spawn_uniform(uint64_t seed, uint64_t global_env, uint64_t episode, uint64_t t, uint64_t c);
 
 /* Number of kernels launched by this library since load (the bench's gpu_launches claim). */
 uint64_t cz_launch_count(void);

@@ -183,6 +183,39 @@ def _refresh_free(content):
 _DELTA = {1: (-1, 0), 2: (1, 0), 3: (0, 1), 4: (0, -1)}     # cooking_world.py:172-184
 
 
+_M64 = (1 << 64) - 1
+
+
+def spawn_uniform(seed, env, episode, t, c):
+    """The shared counter-based stream that stands in for the reference's global RNG draws in
+    handle_agent_spawn (include/cz_b200.h: cz_spawn_uniform): splitmix64 finaliser -> [0, 1)."""
+    z = (seed + 0x9E3779B97F4A7C15 * (env + 1) + 0xD1B54A32D192ED03 * (episode + 1)
+         + 0x8CB92BA72F3D8DD7 * (t + 1) + 0xF1357AEA2E62A9C5 * (c + 1)) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    z ^= z >> 31
+    return (z >> 11) * (1.0 / 9007199254740992.0)
+
+
+class SpawnStream:
+    """Draw c = 0, 1, 2 ... of (seed, env, episode, t); `begin_step(t)` rewinds c."""
+
+    def __init__(self, seed, env, episode=1):
+        self.seed, self.env, self.episode = seed, env, episode
+        self.t = self.c = 0
+
+    def begin_step(self, t):
+        self.t, self.c = t, 0
+
+    def uniform(self):
+        u = spawn_uniform(self.seed, self.env, self.episode, self.t, self.c)
+        self.c += 1
+        return u
+
+    def choice(self, seq):
+        return seq[min(len(seq) - 1, int(self.uniform() * len(seq)))]
+
+
 class OracleEnv:
     """One environment.  `layout` is the plain-data dict produced by
     oracle/ref_dump.describe_layout or cooking_zoo_b200.layout.Layout.to_dict()."""
@@ -192,7 +225,7 @@ class OracleEnv:
 
     def __init__(self, layout, recipes, max_steps, reward_scheme=None,
                  end_condition_all_dishes=False, agent_respawn_rate=0.0, grace_period=20,
-                 agent_despawn_rate=0.0, uniform=None, choice=None):
+                 agent_despawn_rate=0.0, spawn_stream=None):
         self.layout = layout
         self.recipe_names = list(recipes)
         self.max_steps = max_steps
@@ -201,8 +234,7 @@ class OracleEnv:
         self.respawn_rate = agent_respawn_rate
         self.despawn_rate = agent_despawn_rate
         self.grace_period = grace_period
-        self.uniform = uniform          # () -> float in [0,1): stands in for np.random.random
-        self.choice = choice            # (list) -> element: stands in for random.sample(l, 1)[0]
+        self.spawn_stream = spawn_stream   # SpawnStream: stands in for np.random.random / random.sample
         self.error = 0                  # bit flags: "the reference would have raised here"
         self.events = {}                # branch-coverage counters for the test-suite
         self.reset()
@@ -278,6 +310,8 @@ class OracleEnv:
     def step(self, actions):
         """actions: one entry per agent slot (entries of inactive agents are ignored)."""
         self.t += 1                                               # cooking_env.py:244
+        if self.spawn_stream is not None:
+            self.spawn_stream.begin_step(self.t)
         active_start = list(self.active)
         self._world_step([int(a) for a in actions])
         self._rewards(active_start)
@@ -521,14 +555,14 @@ class OracleEnv:
                 self.agents[i].x, self.agents[i].y = self._spawn_location(i)
 
     def _u(self):
-        return self.uniform() if self.uniform is not None else 1.0
+        return self.spawn_stream.uniform() if self.spawn_stream is not None else 1.0
 
     def _spawn_location(self, i):
         """parsing.generate_location (parsing.py:154-167)."""
         xs, ys = self.spawn_ranges[i]
         for _ in range(1002):
-            x = self.choice(xs)
-            y = self.choice(ys)
+            x = self.spawn_stream.choice(xs)
+            y = self.spawn_stream.choice(ys)
             st = self.static_at.get((x, y))
             if st is not None and st.type == "Floor" and not self._agent_on((x, y)):
                 return int(x), int(y)

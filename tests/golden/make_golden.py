@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle.ref_harness import RefEnv  # noqa: E402
+from oracle.cz_oracle import SpawnStream  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -40,10 +41,14 @@ def _path(p):
 
 def record(cfg, seeds, T, policy, teleports=None):
     traces = []
-    for seed in seeds:
+    for n_trace, seed in enumerate(seeds):
+        spawn = cfg.get("spawn")      # {"respawn", "despawn", "grace", "seed"}: trace n is environment n of the stream
         env = RefEnv(seed, _path(cfg["level"]), _path(cfg["meta_file"]), cfg["num_agents"], cfg["max_steps"],
                      cfg["recipes"], end_condition_all_dishes=cfg["end_all"],
-                     reward_scheme=cfg.get("reward_scheme"))
+                     reward_scheme=cfg.get("reward_scheme"),
+                     **({} if not spawn else dict(agent_respawn_rate=spawn["respawn"], agent_despawn_rate=spawn["despawn"],
+                                                 grace_period=spawn["grace"],
+                                                 spawn_stream=SpawnStream(spawn["seed"], n_trace, 1))))
         if hasattr(policy, "bind"):
             policy.bind(env, cfg)
         A = cfg["num_agents"]
@@ -65,13 +70,21 @@ def record(cfg, seeds, T, policy, teleports=None):
             act = policy(rng, t, A, prev)
             prev = act
             tr["actions"][t] = act
-            r, te, tu, re_ = env.step(act)
+            try:
+                r, te, tu, re_ = env.step(act)
+            except IndexError:
+                # truncation with a despawned agent raises in the reference
+                # (cooking_env.py:337/348); the trace ends before that step
+                length = t
+                break
             rew.append(r); term.append(te); trunc.append(tu); rel.append(re_)
             st = env.export_state()
             for k in keys:
                 hist[k].append(st[k])
             obs.append(env.observe_all())
-            if te.any() or tu.any():
+            # the episode ends on termination or when the clock runs out; a despawning agent is
+            # truncated individually (cooking_env.py:346-349) and the environment carries on
+            if te.any() or env.env.t >= cfg["max_steps"]:
                 length = t + 1
                 break
         tr["length"] = length
@@ -199,6 +212,11 @@ def main():
     save("tiny4_agents4", cfgt, record(cfgt, range(720, 726), 150, uniform), 150)
     cfgt3 = dict(cfgt, num_agents=3, recipes=["TomatoSalad", "no_recipe", "no_recipe"])
     save("tiny4_agents3", cfgt3, record(cfgt3, range(730, 734), 150, sticky), 150)
+    # agent despawn / respawn (BASELINE config 5): randomness from the shared stream
+    cfgsp = dict(cfg2, max_steps=10000, spawn={"respawn": 0.3, "despawn": 0.1, "grace": 2, "seed": 4242})
+    save("spawn_cfg2", cfgsp, record(cfgsp, range(800, 808), 300, sticky), 300)
+    cfgsp4 = dict(cfg4a, max_steps=10000, spawn={"respawn": 0.2, "despawn": 0.15, "grace": 3, "seed": 77})
+    save("spawn_open4", cfgsp4, record(cfgsp4, range(810, 816), 200, uniform), 200)
 
 
 if __name__ == "__main__":

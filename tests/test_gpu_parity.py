@@ -11,6 +11,10 @@ pytestmark = pytest.mark.gpu
 
 def _make(n, cfg, **kw):
     from cooking_zoo_b200 import BatchedCookingEnv
+    sp = cfg.get("spawn")
+    if sp:   # trace k is environment k of the shared spawn stream (episode 1 = after the first reset)
+        kw = dict(kw, agent_respawn_rate=sp["respawn"], agent_despawn_rate=sp["despawn"], grace_period=sp["grace"],
+                  seed=sp["seed"])
     return BatchedCookingEnv(n, cfg["level"], cfg["meta_file"], cfg["num_agents"], cfg["max_steps"],
                              cfg["recipes"], end_condition_all_dishes=cfg["end_all"],
                              reward_scheme=cfg["reward_scheme"], **kw)

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from oracle.cz_oracle import OracleEnv, NUM_GOALS, RECIPES, make_recipe
+from oracle.cz_oracle import OracleEnv, NUM_GOALS, RECIPES, make_recipe, SpawnStream, spawn_uniform
 from tests.replay import (golden_files, load_golden, assert_state_equal, assert_obs_equal, bits)
 
 
@@ -12,8 +12,11 @@ def test_oracle_replays_golden(path):
     cfg = g["config"]
     A = cfg["num_agents"]
     for n, layout in enumerate(g["layouts"]):
+        sp = cfg.get("spawn")
+        kw = {} if not sp else dict(agent_respawn_rate=sp["respawn"], agent_despawn_rate=sp["despawn"],
+                                    grace_period=sp["grace"], spawn_stream=SpawnStream(sp["seed"], n, 1))
         env = OracleEnv(layout, cfg["recipes"], cfg["max_steps"], reward_scheme=cfg["reward_scheme"],
-                        end_condition_all_dishes=cfg["end_all"])
+                        end_condition_all_dishes=cfg["end_all"], **kw)
         ctx = f"{path} trace {n} reset"
         assert_state_equal({k: g[k][n, 0] for k in ("agents", "objs", "statics", "marks")}, env.export_state(), ctx)
         assert_obs_equal(g["obs"][n, 0], np.stack([env.observe(i) for i in range(A)]), ctx)
@@ -41,3 +44,12 @@ def test_book_spot_values():
     assert [n.id for n in tls] == [18, 11, 2, 0]
     cb = make_recipe("CarrotBanana")
     assert [n.id for n in cb] == [20, 13, 8, 6]
+
+
+def test_spawn_stream_matches_the_library():
+    """oracle.spawn_uniform restates cz_spawn_uniform (include/cz_b200.h) bit for bit"""
+    from cooking_zoo_b200 import _native
+    lib = _native.load_library()
+    for args in [(0, 0, 0, 0, 0), (4242, 3, 1, 17, 2), (2**63 + 5, 10**6, 40, 399, 1001)]:
+        assert lib.cz_spawn_uniform(*args) == spawn_uniform(*args)
+        assert 0.0 <= spawn_uniform(*args) < 1.0
