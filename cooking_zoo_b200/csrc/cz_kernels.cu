@@ -29,6 +29,9 @@
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
 enum { OBS_TMA = 0, OBS_STG = 1 };
+#ifndef CZ_STAGE_SETS
+#define CZ_STAGE_SETS 1  // sets of staging rows per warp (2 = double buffered; measured: no gain, profiles/r01_notes.md)
+#endif
 
 // ---- Ampere-style async copies (LDGSTS) for the 4-byte state words -------------------------
 __device__ __forceinline__ void cz_cp_async4(void* sdst, const void* gsrc) {
@@ -146,9 +149,11 @@ struct WarpSmem {
 // Observation phase of the specialised kernels (NA agents known at compile time; one lane per
 // (observer, slot) pair; one computed range; at most 64 table double2 per row).
 // Software pipeline over the tile's environments: the table segments of environment le+1 are
-// requested (LDG) right after environment le's staging rows went to the TMA engine and are stored
-// one iteration later, so neither the L2 latency nor the proxy fence's drain sits on the critical path.
-template <int NA>
+// requested (LDG) right after environment le's staging rows were handed off and are stored one
+// iteration later, so neither the L2 latency nor the proxy fence's drain sits on the critical path.
+// OBS_TMA: the staging rows are double buffered (NBUF sets of NA rows) and go out through the TMA
+// engine; OBS_STG: the lanes copy them out with 128-bit stores.
+template <int NA, int OBS>
 __device__ __forceinline__ void cz_obs_phase_fast(const CzDev& T, const SmemTabs* st, const WarpSmem* ws, const double* sxl,
                                                   const double* syl, double* stage, uint32_t stage_s, int row_stride,
                                                   uint32_t row_bytes, double* genv, int n_here, int lane, int tab2, int L2,
@@ -159,7 +164,8 @@ __device__ __forceinline__ void cz_obs_phase_fast(const CzDev& T, const SmemTabs
   const size_t var_stride = (size_t)64 * tab2;
   const bool self = ls.kind == 2 && (int)ls.idx == ls.agent;
   const uint32_t* my_me = ws->ag + ls.agent * OSTRIDE;  // the observer of this lane's pair
-  double* my_row = stage + ls.agent * row_stride;
+  const int set_stride = NA * row_stride;               // doubles between the two staging sets
+  const int r0_off2 = (int)(r0_goff >> 4), r0_n2 = (int)(r0_bytes >> 4);
 
   double2 v0[NP], v1[NP];
   {  // prefetch for the first environment
@@ -171,25 +177,42 @@ __device__ __forceinline__ void cz_obs_phase_fast(const CzDev& T, const SmemTabs
       if (ls.t1 >= 0) v1[a] = __ldg(src + 32);
     }
   }
+  int buf = 0;
 #pragma unroll 1
-  for (int le = 0; le < n_here; ++le, genv += (size_t)NA * T.L) {
+  for (int le = 0; le < n_here; ++le, genv += (size_t)NA * T.L, buf = (buf + 1) % CZ_STAGE_SETS) {
     const bool w = ws->wobs[le] != 0;
     const uint32_t sb = ws->sbits[le], var = ws->variant[le];
     uint32_t xy = 0, fb = 0;
     if (ls.off >= 0) cz_slot_state<true>(T, st, ls, ws->obj, ws->ag, sb, var, le, xy, fb);
     const uint32_t me = my_me[le];
-    // the bulk stores of the previous environment must have finished reading the staging rows
-    if (lane == 0) cz_bulk_wait_read<0>();
-    __syncwarp();
-    if (ls.off >= 0) cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, self, sxl, syl, my_row);
-    cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
-    __syncwarp();
-    if (lane == 0 && w) {  // one elected lane hands the computed range of the NA rows to the TMA engine
-      char* gp = reinterpret_cast<char*>(genv) + r0_goff;
-      uint32_t sp = stage_s + r0_soff;
+    double* set = stage + (OBS == OBS_TMA ? buf * set_stride : 0);
+    if (OBS == OBS_TMA) {
+      // the bulk stores that last read this staging set must have drained
+      if (lane == 0) cz_bulk_wait_read<CZ_STAGE_SETS - 1>();
+      __syncwarp();
+    }
+    if (ls.off >= 0) cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, self, sxl, syl, set + ls.agent * row_stride);
+    if (OBS == OBS_TMA) {
+      cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
+      __syncwarp();
+      if (lane == 0 && w) {  // one elected lane hands the computed range of the NA rows to the TMA engine
+        char* gp = reinterpret_cast<char*>(genv) + r0_goff;
+        uint32_t sp = stage_s + r0_soff + (uint32_t)(buf * set_stride) * 8u;
 #pragma unroll
-      for (int a = 0; a < NA; ++a, gp += row_gbytes, sp += row_bytes) cz_bulk_store_s(gp, sp, r0_bytes);
-      cz_bulk_commit();
+        for (int a = 0; a < NA; ++a, gp += row_gbytes, sp += row_bytes) cz_bulk_store_s(gp, sp, r0_bytes);
+      }
+      if (lane == 0) cz_bulk_commit();
+    } else {
+      __syncwarp();
+      if (w) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          const double2* s2 = reinterpret_cast<const double2*>(set + a * row_stride) + (r0_soff >> 4);
+          double2* g2r = reinterpret_cast<double2*>(genv) + a * L2 + r0_off2;
+          for (int k = lane; k < r0_n2; k += 32) g2r[k] = s2[k];
+        }
+      }
+      __syncwarp();
     }
     // table segments: rows 0..NP-1 were requested one iteration ago
     double2* g2 = reinterpret_cast<double2*>(genv);
@@ -216,7 +239,9 @@ __device__ __forceinline__ void cz_obs_phase_fast(const CzDev& T, const SmemTabs
       }
     }
   }
-  if (lane == 0) cz_bulk_wait_read<0>();  // staging and columns are reused by the next tile
+  if (OBS == OBS_TMA) {
+    if (lane == 0) cz_bulk_wait_read<0>();  // staging and columns are reused by the next tile
+  }
 }
 
 // Image of the read-only part of a block's shared memory, built on the host (cz_tables_create) and
@@ -256,13 +281,13 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
   // staging (the computed span of A rows) lives after the per-warp words, 16-byte aligned
   const size_t row_bytes = ((size_t)T.stage_len * 8 + 15) & ~(size_t)15;
   unsigned char* stage_base = smem_raw + ((cz_block_smem_head() + cz_warp_words(D, A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15);
-  double* stage = reinterpret_cast<double*>(stage_base + (size_t)warp * A * row_bytes);
+  double* stage = reinterpret_cast<double*>(stage_base + (size_t)warp * CZ_STAGE_SETS * A * row_bytes);
   const int row_stride = (int)(row_bytes >> 3);
   // read-only block image: one 16-byte load per thread
   for (int i = threadIdx.x; i < (int)(sizeof(BlockSmem) / 16); i += CZ_THREADS)
     reinterpret_cast<uint4*>(bs)[i] = __ldg(reinterpret_cast<const uint4*>(T.blob) + i);
   // never-occupied slots stay zero: the staging rows are cleared once and only live slots are rewritten
-  for (int i = lane; i < A * row_stride; i += 32) stage[i] = 0.0;
+  for (int i = lane; i < CZ_STAGE_SETS * A * row_stride; i += 32) stage[i] = 0.0;
   const SmemTabs* st = &bs->tabs;
   const double* sxl = bs->xlut + (T.W - 1);
   const double* syl = bs->ylut + (T.H - 1);
@@ -376,7 +401,7 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
     const size_t r0_goff = (size_t)T.ranges[0][0] * 8;
     const uint32_t r0_soff = (uint32_t)(T.ranges[0][0] - T.stage_lo) * 8;
     if constexpr (FAST) {
-      cz_obs_phase_fast<NA>(T, st, ws, sxl, syl, stage, stage_s, row_stride, (uint32_t)row_bytes, genv, n_here, lane_o, tab2, L2,
+      cz_obs_phase_fast<NA, OBS>(T, st, ws, sxl, syl, stage, stage_s, row_stride, (uint32_t)row_bytes, genv, n_here, lane_o, tab2, L2,
                             row_gbytes, r0_bytes, r0_goff, r0_soff);
       __syncwarp();
       continue;
@@ -505,7 +530,7 @@ static int upload(cz_tables* t, const Tp* host, size_t count, const Tp** out) {
 static size_t cz_smem_bytes(const CzDev& T) {
   size_t row_bytes = ((size_t)T.stage_len * 8 + 15) & ~(size_t)15;
   return ((cz_block_smem_head() + cz_warp_words(T.D, T.A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15) +
-         (size_t)CZ_WARPS_PER_BLOCK * T.A * row_bytes;
+         (size_t)CZ_WARPS_PER_BLOCK * CZ_STAGE_SETS * T.A * row_bytes;
 }
 
 extern "C" int cz_abi_version(void) { return CZ_ABI_VERSION; }
@@ -623,7 +648,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   // the specialised kernels: one lane per (observer, slot) pair, one computed range, two table loads per
   // lane, small tables resident in shared memory
   t->simple = T.A * T.n_comp <= 32 && T.n_comp > 0 && T.n_ranges == 1 && T.tab_len <= 128 && (T.L & 1) == 0 &&
-              T.V <= CZ_SV && T.B <= CZ_SB && t->obs_path == OBS_TMA;
+              T.V <= CZ_SV && T.B <= CZ_SB;
   {
     const char* g = getenv("CZ_GENERIC");
     if (g && g[0] == '1') t->simple = 0;
@@ -632,7 +657,9 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
 #define SET_MODE(M)                                                                                    \
   SET_SMEM((cz_env_kernel<M, OBS_TMA, 0>)); SET_SMEM((cz_env_kernel<M, OBS_STG, 0>));                   \
   SET_SMEM((cz_env_kernel<M, OBS_TMA, 1>)); SET_SMEM((cz_env_kernel<M, OBS_TMA, 2>));                   \
-  SET_SMEM((cz_env_kernel<M, OBS_TMA, 3>)); SET_SMEM((cz_env_kernel<M, OBS_TMA, 4>))
+  SET_SMEM((cz_env_kernel<M, OBS_TMA, 3>)); SET_SMEM((cz_env_kernel<M, OBS_TMA, 4>));                   \
+  SET_SMEM((cz_env_kernel<M, OBS_STG, 1>)); SET_SMEM((cz_env_kernel<M, OBS_STG, 2>));                   \
+  SET_SMEM((cz_env_kernel<M, OBS_STG, 3>)); SET_SMEM((cz_env_kernel<M, OBS_STG, 4>))
   SET_MODE(MODE_STEP); SET_MODE(MODE_RESET); SET_MODE(MODE_OBSERVE);
 #undef SET_MODE
 #undef SET_SMEM
@@ -676,12 +703,19 @@ static int cz_launch(const cz_tables* t, uint32_t* state, const uint8_t* actions
 #define CZ_GO(O, NA)                                                                                                  \
   cz_env_kernel<MODE, O, NA><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, actions, layout_ids, recipe_ids, mask, obs, \
                                                            reward, term, trunc, err, n_envs, flags, seed, env_offset)
-  if (t->simple) {
+  if (t->simple && t->obs_path == OBS_TMA) {
     switch (t->dev.A) {
       case 1: CZ_GO(OBS_TMA, 1); break;
       case 2: CZ_GO(OBS_TMA, 2); break;
       case 3: CZ_GO(OBS_TMA, 3); break;
       default: CZ_GO(OBS_TMA, 4); break;
+    }
+  } else if (t->simple) {
+    switch (t->dev.A) {
+      case 1: CZ_GO(OBS_STG, 1); break;
+      case 2: CZ_GO(OBS_STG, 2); break;
+      case 3: CZ_GO(OBS_STG, 3); break;
+      default: CZ_GO(OBS_STG, 4); break;
     }
   } else if (t->obs_path == OBS_TMA) {
     CZ_GO(OBS_TMA, 0);
