@@ -260,6 +260,52 @@ def run_gpu_arm(args):
     h2d = N * A
     d2h = N * A * L * 8 + N * A * 8 + 2 * N * A
 
+    # ---- BASELINE config 3 (4096 two-agent envs on one GPU): launch-bound, reported beside the headline
+    cfg3 = None
+    if rank == 0 and world == 1 and not args.no_cfg3:
+        n3 = 4096
+        env3 = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+                                 device=str(dev), layout_pool_size=400, layout_seed=0, auto_reset=True, seed=7)
+        env3.reset()
+        act3 = torch.randint(0, 5, (ring, n3, A), generator=g, dtype=torch.uint8).to(dev)
+        for s in range(20):
+            env3.step(act3[s % ring])
+        torch.cuda.synchronize(dev)
+        k3 = 2000
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for s in range(k3):
+            env3.step(act3[s % ring])
+        a1.record()
+        torch.cuda.synchronize(dev)
+        per_launch = n3 * k3 / (a0.elapsed_time(a1) / 1e3)
+        # the same launches captured once in a CUDA graph (one graph = `ring` steps) and replayed
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for s in range(ring):
+                env3.step(act3[s])
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                for s in range(ring):
+                    env3.step(act3[s])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for _ in range(5):
+            graph.replay()
+        torch.cuda.synchronize(dev)
+        reps = 200
+        a0.record()
+        for _ in range(reps):
+            graph.replay()
+        a1.record()
+        torch.cuda.synchronize(dev)
+        graphed = n3 * ring * reps / (a0.elapsed_time(a1) / 1e3)
+        cfg3 = {"workload": "cfg3: 4096 two-agent coop_test envs, 1 GPU, random actions, feature_vector obs",
+                "per_launch_env_steps_per_s": per_launch, "cuda_graph_env_steps_per_s": graphed,
+                "note": "20 MB per step: launch/latency bound, not HBM bound"}
+        env3.close()
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -288,8 +334,9 @@ def run_gpu_arm(args):
                              "bytes_per_env_step": bytes_per_env_step, "kernel": "cz_env_kernel<STEP,TMA>"},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step)"},
-                "gpu_launches": int(launches), "clocks": clocks,
+                        "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step)",
+                        "host_link_gbs": (h2d + d2h) * e2e_value / N / 1e9 / world},
+                "gpu_launches": int(launches), "clocks": clocks, "cfg3": cfg3,
                 "stats": {"episodes_started": float(stats[0]), "recipes_done_now": float(stats[1]),
                           "last_step_return": float(stats[2])}}
         print(json.dumps(line))
@@ -307,6 +354,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-steps", type=int, default=6000, help="oracle env-steps per host process for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 6000

@@ -1,0 +1,137 @@
+"""GPU, BASELINE full size (131072 two-agent environments, the per-GPU shard of config 4): properties that
+do not need the oracle to run at that size, plus a sampled lockstep against it."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.cz_oracle import OracleEnv
+from tests.replay import assert_obs_equal, bits
+
+pytestmark = pytest.mark.gpu
+N = 131072
+BOOK = ["TomatoSalad", "TomatoLettuceSalad", "CarrotBanana", "MashedCarrotBanana", "CucumberOnion",
+        "AppleWatermelon", "TomatoLettuceOnionSalad", "no_recipe"]
+
+
+def _env(n=N, **kw):
+    from cooking_zoo_b200 import BatchedCookingEnv
+    return BatchedCookingEnv(n, "coop_test", "example", 2, 400, BOOK[1:3], end_condition_all_dishes=True,
+                             recipe_pool=BOOK, layout_pool_size=400, layout_seed=0, **kw)
+
+
+def _actions(steps, n, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randint(0, 5, (steps, n, 2), generator=g, dtype=torch.uint8).cuda()
+
+
+def _recipe_ids(n, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randint(0, len(BOOK), (n, 2), generator=g, dtype=torch.uint8)
+
+
+def _check_invariants(env):
+    """Structural invariants of the packed state (include/cz_b200.h), evaluated with torch on the device:
+    every object sits in exactly one container, held objects agree with their holder, content positions of
+    a container are 0..n-1, exactly the last item of a container is `free`, positions are inside the level."""
+    t = env.tables
+    D, A = t.num_dyn_slots, t.num_agents
+    st = env.state.to(torch.int64) & 0xFFFFFFFF
+    o, ag = st[:D], st[D:D + A]
+    pres = (o >> 6) & 1
+    x, y = o & 7, (o >> 3) & 7
+    ck, cid, pos, free = (o >> 10) & 3, (o >> 12) & 31, (o >> 17) & 63, (o >> 9) & 1
+    assert bool(((x < t.width) & (y < t.height))[pres == 1].all())
+    assert bool((ck[pres == 1] <= 2).all())
+    # held objects: the named agent holds exactly this slot and stands on the same cell
+    has, hold = (ag >> 9) & 1, (ag >> 10) & 31
+    slots = torch.arange(D, device=st.device)[:, None]
+    for i in range(A):
+        held_by_i = (pres == 1) & (ck == 0) & (cid == i)
+        assert bool((held_by_i.sum(0) == has[i]).all())
+        assert bool((held_by_i == ((slots == hold[i][None, :]) & (has[i] == 1)[None, :])).all())
+        same_cell = ((o & 63) == (ag[i] & 63)[None, :])
+        assert bool(same_cell[held_by_i].all())
+    # plate content: the container is a present plate, shares its cell, positions are a permutation
+    tf = torch.as_tensor(t.type_flags[t.slot_type[:D]].astype(np.int64), device=st.device)
+    in_plate = (pres == 1) & (ck == 2)
+    plate_idx = torch.where(in_plate, cid, torch.zeros_like(cid))
+    plate_rec = torch.gather(o, 0, plate_idx)
+    assert bool(((tf[plate_idx] & 1) == 1)[in_plate].all()) and bool((((plate_rec >> 6) & 1) == 1)[in_plate].all())
+    assert bool(((plate_rec & 63) == (o & 63))[in_plate].all())
+    for p in torch.nonzero(torch.as_tensor((t.type_flags[t.slot_type[:D]] & 1) == 1)).flatten().tolist():
+        members = in_plate & (cid == p)
+        n = members.sum(0)
+        assert bool((torch.where(members, pos, torch.zeros_like(pos)).sum(0) == n * (n - 1) // 2).all())
+        last = members & (pos == (n - 1)[None, :])
+        assert bool((free[members] == last[members].to(free.dtype)).all())
+    # static content: at most two items per cell (Cutboard + spawned Bread), the top one is free
+    in_static = (pres == 1) & (ck == 1)
+    cell = o & 63
+    for c in range(64):
+        m = in_static & (cell == c)
+        n = m.sum(0)
+        if int(n.max()) == 0:
+            continue
+        assert int(n.max()) <= 2
+        last = m & (pos == (n - 1)[None, :])
+        assert bool((last.sum(0) == (n > 0)).all())
+        assert bool((free[m] == last[m].to(free.dtype)).all())
+    # conservation: nothing but Bread changes its population (Bread.chop spawns a twin)
+    return pres
+
+
+def test_fullsize_sampled_lockstep_invariants_and_idempotence():
+    env = _env()
+    rid = _recipe_ids(N, 1)
+    lids = env.default_layout_ids()
+    obs0 = env.reset(layout_ids=lids, recipe_ids=rid).clone()
+    pres0 = _check_invariants(env).clone()
+    picks = np.linspace(0, N - 1, 48).astype(int)
+    oracles = {int(k): OracleEnv(env.tables.layouts[lids[k]], [BOOK[int(r)] for r in rid[k]], 400,
+                                 end_condition_all_dishes=True) for k in picks}
+    for k, orc in oracles.items():
+        assert_obs_equal(np.stack([orc.observe(i) for i in range(2)]), obs0[k].cpu().numpy(), f"env {k} reset")
+    acts = _actions(60, N, 2)
+    for t in range(60):
+        obs, rew, term, trunc, _ = env.step(acts[t])
+        a = acts[t].cpu().numpy()
+        o, r = obs[picks].cpu().numpy(), rew[picks].cpu().numpy()
+        for j, k in enumerate(picks):
+            rr, te, tu, _ = oracles[int(k)].step(a[k])
+            assert np.array_equal(bits(rr), bits(r[j])), (k, t)
+            assert_obs_equal(np.stack([oracles[int(k)].observe(i) for i in range(2)]), o[j], f"env {k} step {t}")
+    pres = _check_invariants(env)
+    tb = env.tables
+    bread = slice(int(tb.type_base[tb.dyn_types.index("Bread")]), int(tb.type_base[tb.dyn_types.index("Bread")]) + 4)
+    keep = torch.ones(tb.num_dyn_slots, dtype=torch.bool, device=pres.device)
+    keep[bread] = False
+    assert torch.equal(pres[keep], pres0[keep])                       # populations conserved
+    assert bool((pres[bread].sum(0) >= pres0[bread].sum(0)).all())     # Bread only ever multiplies
+    assert int(env.error_flags.abs().sum()) == 0
+    stepped = env.obs.clone()
+    assert torch.equal(stepped.view(torch.int64), env.observe().view(torch.int64))   # obs == f(state)
+
+
+def test_fullsize_determinism_and_halves():
+    """same seeds -> bit-identical outputs; the two halves stepped as separate shards reproduce the whole"""
+    rid = _recipe_ids(N, 3)
+    acts = _actions(25, N, 4)
+    runs = []
+    for _ in range(2):
+        env = _env(auto_reset=True, seed=5)
+        env.reset(recipe_ids=rid)
+        for t in range(25):
+            obs, rew, term, trunc, _ = env.step(acts[t])
+        runs.append((obs.clone(), rew.clone(), env.state.clone()))
+        del env
+    assert torch.equal(runs[0][0].view(torch.int64), runs[1][0].view(torch.int64))
+    assert torch.equal(runs[0][2], runs[1][2])
+    h = N // 2
+    lo = _env(h, auto_reset=True, seed=5)
+    hi = _env(h, auto_reset=True, seed=5, env_offset=h)
+    lo.reset(recipe_ids=rid[:h]); hi.reset(recipe_ids=rid[h:])
+    for t in range(25):
+        o1, r1, *_ = lo.step(acts[t, :h].contiguous())
+        o2, r2, *_ = hi.step(acts[t, h:].contiguous())
+    assert torch.equal(torch.cat([o1, o2]).view(torch.int64), runs[0][0].view(torch.int64))
+    assert torch.equal(torch.cat([r1, r2]).view(torch.int64), runs[0][1].view(torch.int64))
