@@ -179,16 +179,11 @@ def run_gpu_arm(args):
     dev = torch.device(f"cuda:{local}")
     N, A = args.envs, NUM_AGENTS
 
-    env = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
-                            device=str(dev), recipe_pool=BOOK, layout_pool_size=400, layout_seed=0,
-                            auto_reset=True, seed=2026, env_offset=rank * N)
-    L = env.obs_len
+    L = None
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     recipe_ids = torch.randint(0, len(BOOK), (N, 2), generator=g, dtype=torch.uint8)
-    env.reset(recipe_ids=recipe_ids)
     ring = 16
     actions = torch.randint(0, 5, (ring, N, A), generator=g, dtype=torch.uint8).to(dev)
-    lib = env.lib
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -196,31 +191,50 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for s in range(args.warmup):
-        env.step(actions[s % ring])
-    sync_all()
+    def timed_run(pipelined, sample_clocks):
+        """W warm-up + K timed steps of one mode; returns (env, ms_total max over ranks, launches, clocks)."""
+        env = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+                                device=str(dev), recipe_pool=BOOK, layout_pool_size=400, layout_seed=0,
+                                auto_reset=True, seed=2026, env_offset=rank * N, pipelined=pipelined)
+        env.reset(recipe_ids=recipe_ids)
+        for s in range(args.warmup):
+            env.step(actions[s % ring])
+        env.wait()
+        sync_all()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        launches0 = env.lib.cz_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        t_host0 = time.perf_counter()
+        ev0.record()
+        for s in range(args.steps):
+            env.step(actions[s % ring])
+        env.wait()      # pipelined mode: order the internal streams before the closing event (no-op otherwise)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        t_host1 = time.perf_counter()
+        launches = env.lib.cz_launch_count() - launches0
+        clocks = sampler.stop(t_host0, t_host1) if sampler else None
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return env, float(t.item()), launches, clocks
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    # stats accumulated on device (outside the kernel): episodes finished, recipes completed, return
-    launches0 = lib.cz_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    t_host0 = time.perf_counter()
-    ev0.record()
-    for s in range(args.steps):
-        env.step(actions[s % ring])
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    t_host1 = time.perf_counter()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = lib.cz_launch_count() - launches0
-    clocks = sampler.stop(t_host0, t_host1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
+    # in-place step (one fused kernel per step) first, then the pipelined throughput mode (the headline)
+    env_s, ms_sync, launches_sync, _ = timed_run(False, False)
+    sync_value = world * N * args.steps / (ms_sync / 1e3)
+    L = env_s.obs_len
+    if args.mode == "sync":
+        env, ms_total_max, launches, clocks = timed_run(False, True)
+    else:
+        env_s.close()
+        del env_s
+        torch.cuda.empty_cache()
+        env, ms_total_max, launches, clocks = timed_run(True, True)
+    lib = env.lib
     ms_per_step = ms_total_max / args.steps
     value = world * N * args.steps / (ms_total_max / 1e3)
 
@@ -239,6 +253,9 @@ def run_gpu_arm(args):
     h_term = torch.empty((N, A), dtype=torch.uint8).pin_memory()
     h_trunc = torch.empty((N, A), dtype=torch.uint8).pin_memory()
     stream = torch.cuda.current_stream(dev).cuda_stream
+
+    env.wait()
+    torch.cuda.synchronize(dev)
 
     def host_step():
         _native.check(lib.cz_step_host(env._handle, env.state.data_ptr(), h_act.data_ptr(), h_obs.data_ptr(),
@@ -331,12 +348,19 @@ def run_gpu_arm(args):
                 "config": workload_config(world, N),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "bytes_per_env_step": bytes_per_env_step, "kernel": "cz_env_kernel<STEP,TMA>"},
+                             "bytes_per_env_step": bytes_per_env_step,
+                             "kernel": ("cz_obs_envs_kernel (+ cz_env_kernel<STEP,dynamics-only> overlapped)"
+                                        if args.mode == "pipelined" else "cz_env_kernel<STEP,TMA> (fused)")},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step)",
                         "host_link_gbs": (h2d + d2h) * e2e_value / N / 1e9 / world},
                 "gpu_launches": int(launches), "clocks": clocks, "cfg3": cfg3,
+                "mode": args.mode,
+                "sync_step": {"value": sync_value, "ms_per_step": ms_sync / args.steps,
+                              "frac": N * bytes_per_env_step / (ms_sync / args.steps / 1e3) / 1e9 / peak,
+                              "gpu_launches": int(launches_sync),
+                              "note": "in-place cz_step: one fused kernel per step, outputs ordered on the caller's stream"},
                 "stats": {"episodes_started": float(stats[0]), "recipes_done_now": float(stats[1]),
                           "last_step_return": float(stats[2])}}
         print(json.dumps(line))
@@ -355,6 +379,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6000, help="oracle env-steps per host process for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true")
+    ap.add_argument("--mode", default="pipelined", choices=["pipelined", "sync"],
+                    help="pipelined (default): throughput mode, the dynamics of step k+1 overlap the observation "
+                         "writes of step k (two kernels, two streams, ping-pong state); sync: one fused kernel per step")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 6000

@@ -40,7 +40,7 @@ class BatchedCookingEnv:
                  obs_spaces=None, end_condition_all_dishes=False, action_scheme="scheme3", render=False,
                  reward_scheme=None, agent_respawn_rate=0.0, grace_period=20, agent_despawn_rate=0.0, *,
                  device="cuda:0", recipe_pool=None, layout_pool_size=256, layout_seed=0, layouts=None,
-                 auto_reset=False, seed=0, env_offset=0):
+                 auto_reset=False, seed=0, env_offset=0, pipelined=False):
         obs_spaces = obs_spaces or ["feature_vector"] * num_agents
         if any(o != "feature_vector" for o in obs_spaces):
             raise NotImplementedError("the batched entry point builds feature_vector observations only "
@@ -68,7 +68,10 @@ class BatchedCookingEnv:
         self._handle = handle
         N, A, L = self.num_envs, self.num_agents, self.obs_len
         dev = self.device
-        self.state = torch.zeros((t.rows, N), dtype=torch.int32, device=dev)
+        # pipelined throughput mode: two state matrices (ping-pong), see cz_step_pipelined in cz_b200.h
+        self.pipelined = bool(pipelined)
+        self._state2 = torch.zeros((2 if self.pipelined else 1, t.rows, N), dtype=torch.int32, device=dev)
+        self.state = self._state2[0]
         self.obs = torch.zeros((N, A, L), dtype=torch.float64, device=dev)
         self.reward = torch.zeros((N, A), dtype=torch.float64, device=dev)
         self.terminated = torch.zeros((N, A), dtype=torch.uint8, device=dev)
@@ -118,6 +121,9 @@ class BatchedCookingEnv:
                                             rid.data_ptr() if rid is not None else None,
                                             mk.data_ptr() if mk is not None else None,
                                             self.obs.data_ptr(), N, self._stream()))
+            if self.pipelined:
+                torch.cuda.current_stream(self.device).synchronize()
+                _native.check(self.lib.cz_pipeline_reset(self._handle, 0))
         return self.obs
 
     def step(self, actions):
@@ -129,6 +135,8 @@ class BatchedCookingEnv:
         if a.dtype != torch.uint8 or a.device != self.device or not a.is_contiguous():
             self._actions.copy_(a)
             a = self._actions
+        if self.pipelined:
+            return self._step_pipelined(a)
         with torch.cuda.device(self.device):
             _native.check(self.lib.cz_step(self._handle, self.state.data_ptr(), a.data_ptr(), self.obs.data_ptr(),
                                            self.reward.data_ptr(), self.terminated.data_ptr(),
@@ -136,6 +144,21 @@ class BatchedCookingEnv:
                                            _native.STEP_AUTO_RESET if self.auto_reset else 0,
                                            self.seed, self.env_offset, self._stream()))
         return self.obs, self.reward, self.terminated, self.truncated, self._info
+
+    def _step_pipelined(self, a):
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.cz_step_pipelined(
+                self._handle, self._state2.data_ptr(), a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
+                self.terminated.data_ptr(), self.truncated.data_ptr(), self.error_flags.data_ptr(), self.num_envs,
+                _native.STEP_AUTO_RESET if self.auto_reset else 0, self.seed, self.env_offset, self._stream()))
+        self.state = self._state2[self.lib.cz_pipeline_current(self._handle)]
+        return self.obs, self.reward, self.terminated, self.truncated, self._info
+
+    def wait(self):
+        """Pipelined mode: order everything enqueued so far before later work on torch's current stream."""
+        if self.pipelined:
+            with torch.cuda.device(self.device):
+                _native.check(self.lib.cz_pipeline_wait(self._handle, self._stream()))
 
     def observe(self):
         with torch.cuda.device(self.device):

@@ -15,6 +15,9 @@ struct CzDev {
   int segs[2][3];    // table segments of a row: {row offset, length, table offset} (doubles, even)
   int ranges[3][2];  // computed ranges of a row: {row offset, length}
   int stage_lo, stage_len;  // span of the computed ranges (what the staging buffer holds)
+  // per-lane constants of the packed (observer, slot) layout, filled by cz_tables_create
+  const int4* lane_map;  // [32] {computed-slot descriptor or -1, observer, t0, t1}: global memory (dynamic indexing of kernel
+                         // parameters would force a local-memory copy of the whole struct)
   double r_node, r_recipe, r_penalty, r_time, respawn, despawn;
   const double* xlut;
   const double* ylut;

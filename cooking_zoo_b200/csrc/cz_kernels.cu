@@ -28,7 +28,7 @@
 #endif
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
-enum { OBS_TMA = 0, OBS_STG = 1 };
+enum { OBS_TMA = 0, OBS_STG = 1, OBS_NONE = 2 };  // OBS_NONE: dynamics only (pipelined step: the observe kernel follows)
 #ifndef CZ_STAGE_SETS
 #define CZ_STAGE_SETS 1  // sets of staging rows per warp (2 = double buffered; measured: no gain, profiles/r01_notes.md)
 #endif
@@ -92,22 +92,39 @@ __device__ __forceinline__ LaneSlot cz_lane_slot(const CzDev& T, int q, int agen
   return ls;
 }
 
+// The same from the host-prepared per-lane maps (packed (observer, slot) layout of the specialised kernels).
+__device__ __forceinline__ LaneSlot cz_lane_slot_packed(const CzDev& T, int lane) {
+  LaneSlot ls;
+  const int4 lm = __ldg(T.lane_map + lane);
+  ls.off = -1; ls.agent = lm.y; ls.flen = 1; ls.kind = 1; ls.idx = 0;
+  if (lm.x >= 0) {
+    const uint32_t d = (uint32_t)lm.x;
+    ls.off = (int)(d & 0xFFFu) - T.stage_lo;
+    ls.flen = (d >> 12) & 7u; ls.kind = (d >> 15) & 3u; ls.idx = (d >> 17) & 255u;
+  }
+  ls.t0 = lm.z;
+  ls.t1 = lm.w;
+  return ls;
+}
+
 // Observer-independent part of a computed slot: cell (x | y<<3, bit 6 = present) and feature bits.
+// Agent columns follow the object columns in shared memory, so dynamic objects and agents are
+// decoded by the same instruction stream (no divergence between the two kinds of lane).
 template <bool FAST>
 __device__ __forceinline__ void cz_slot_state(const CzDev& T, const SmemTabs* st, const LaneSlot& ls,
                                               const uint32_t* sobj, const uint32_t* sag, uint32_t sbits,
                                               uint32_t variant, int e, uint32_t& xy, uint32_t& fb) {
   uint32_t rec, fb4;
   bool present;
-  if (ls.kind == 1) {  // dynamic object: [!done, chopped, mashed] (world_objects.py:447,555,...)
-    rec = sobj[ls.idx * OSTRIDE + e];
-    present = rec & O_PRESENT;
-    uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
-    fb4 = ((c | m) ^ 1u) | c << 1 | m << 2;
-  } else if (ls.kind == 2) {  // agent: one-hot orientation; every agent, active or not (cooking_env.py:356)
-    present = (int)ls.idx < T.A;
-    rec = present ? sag[ls.idx * OSTRIDE + e] : 0u;
-    fb4 = (1u << A_ORI(rec)) >> 1;
+  if (ls.kind != 0) {
+    // dynamic object: [!done, chopped, mashed] (world_objects.py:447,555,...);
+    // agent: one-hot orientation; every agent, active or not (cooking_env.py:356)
+    const bool is_agent = ls.kind == 2;
+    const bool exists = !is_agent || (int)ls.idx < T.A;
+    rec = exists ? (is_agent ? sag : sobj)[ls.idx * OSTRIDE + e] : 0u;
+    present = is_agent ? exists : (rec & O_PRESENT) != 0;
+    const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+    fb4 = is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2);
   } else {  // live Switch / Block: [switch_active] / [walkable] (world_objects.py:174,221)
     uint32_t cell = TAB_SCELL(variant, ls.idx);
     present = cell != 0xFFu;
@@ -159,7 +176,7 @@ __device__ __forceinline__ void cz_obs_phase_fast(const CzDev& T, const SmemTabs
                                                   uint32_t row_bytes, double* genv, int n_here, int lane, int tab2, int L2,
                                                   size_t row_gbytes, uint32_t r0_bytes, size_t r0_goff, uint32_t r0_soff) {
   constexpr int NP = NA < 2 ? NA : 2;  // rows whose table segments are prefetched
-  const LaneSlot ls = cz_lane_slot(T, lane < NA * T.n_comp ? lane % T.n_comp : -1, lane / T.n_comp, lane);
+  const LaneSlot ls = cz_lane_slot_packed(T, lane);
   const double2* tab0 = reinterpret_cast<const double2*>(T.obs_table) + lane;
   const size_t var_stride = (size_t)64 * tab2;
   const bool self = ls.kind == 2 && (int)ls.idx == ls.agent;
@@ -186,12 +203,31 @@ __device__ __forceinline__ void cz_obs_phase_fast(const CzDev& T, const SmemTabs
     if (ls.off >= 0) cz_slot_state<true>(T, st, ls, ws->obj, ws->ag, sb, var, le, xy, fb);
     const uint32_t me = my_me[le];
     double* set = stage + (OBS == OBS_TMA ? buf * set_stride : 0);
+    // every value of this lane's slot is computed before the synchronisation below (whose memory
+    // clobber stops the compiler from hoisting the table loads itself); only stores follow it
+    double X, Y;
+    uint32_t hi[5];
+    {
+      const int x = xy & 7u, y = (xy >> 3) & 7u;
+      X = sxl[x - (self ? 0 : (int)(me & 7u))];          // (x - ax) / W, or x / W for the observer itself
+      Y = syl[y - (self ? 0 : (int)((me >> 3) & 7u))];
+      if (!(xy & 64u)) { X = 0.0; Y = 0.0; }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) hi[k] = (fb >> k & 1u) ? 0x3FF00000u : 0u;  // 1.0 = 0x3FF00000'00000000
+    }
     if (OBS == OBS_TMA) {
       // the bulk stores that last read this staging set must have drained
       if (lane == 0) cz_bulk_wait_read<CZ_STAGE_SETS - 1>();
       __syncwarp();
     }
-    if (ls.off >= 0) cz_slot_store(ls, xy, fb, me & 7u, (me >> 3) & 7u, self, sxl, syl, set + ls.agent * row_stride);
+    if (ls.off >= 0) {
+      double* out = set + ls.agent * row_stride + ls.off;
+      out[0] = X;
+      out[1] = Y;
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        if (k < (int)ls.flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, hi[k]);
+    }
     if (OBS == OBS_TMA) {
       cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
       __syncwarp();
@@ -256,7 +292,8 @@ __host__ __device__ inline size_t cz_block_smem_head() { return (sizeof(BlockSme
 
 template <int MODE, int OBS, int NA>
 __global__ void __launch_bounds__(CZ_THREADS, CZ_MIN_BLOCKS)
-cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, const uint8_t* __restrict__ actions,
+cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* state_out,  // may alias (in-place step)
+              const uint8_t* __restrict__ actions,
               const int32_t* __restrict__ layout_ids, const uint8_t* __restrict__ recipe_ids,
               const uint8_t* __restrict__ mask, double* __restrict__ obs, double* __restrict__ reward,
               uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint32_t* __restrict__ errflags,
@@ -265,7 +302,8 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
   // NA > 0: specialised kernel for NA agents (tables in shared memory, packed observation lanes)
   constexpr bool FAST = NA != 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // lane 0's broadcast tells the compiler the warp index is warp-uniform (uniform datapath, plain UBLKCP operands)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int D = T.D, A = FAST ? NA : T.A;
   BlockSmem* bs = reinterpret_cast<BlockSmem*>(smem_raw);
   WarpSmem wsv;
@@ -287,7 +325,8 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
   for (int i = threadIdx.x; i < (int)(sizeof(BlockSmem) / 16); i += CZ_THREADS)
     reinterpret_cast<uint4*>(bs)[i] = __ldg(reinterpret_cast<const uint4*>(T.blob) + i);
   // never-occupied slots stay zero: the staging rows are cleared once and only live slots are rewritten
-  for (int i = lane; i < CZ_STAGE_SETS * A * row_stride; i += 32) stage[i] = 0.0;
+  if (OBS != OBS_NONE)
+    for (int i = lane; i < CZ_STAGE_SETS * A * row_stride; i += 32) stage[i] = 0.0;
   const SmemTabs* st = &bs->tabs;
   const double* sxl = bs->xlut + (T.W - 1);
   const double* syl = bs->ylut + (T.H - 1);
@@ -296,7 +335,8 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
   const int n_tiles = (n_envs + 31) >> 5;
   const int warps_total = gridDim.x * CZ_WARPS_PER_BLOCK;
   const size_t N = (size_t)n_envs;
-  uint32_t* misc = state + (size_t)(D + A) * N;
+  const uint32_t* misc = state + (size_t)(D + A) * N;
+  uint32_t* misc_out = state_out + (size_t)(D + A) * N;  // == misc unless the step is pipelined (ping-pong state)
 
   for (int tile = blockIdx.x * CZ_WARPS_PER_BLOCK + warp; tile < n_tiles; tile += warps_total) {
     const int env = tile * 32 + lane;
@@ -370,14 +410,14 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
 
       // ---- phase 3: shared columns -> state
       if (MODE != MODE_OBSERVE && (MODE == MODE_STEP || do_reset)) {
-        for (int s = 0; s < D; ++s) state[(size_t)s * N + env] = e.o[s * OSTRIDE];
-        for (int i = 0; i < A; ++i) state[(size_t)(D + i) * N + env] = e.ag[i * OSTRIDE];
-        misc[(size_t)CZ_ROW_SBITS * N + env] = e.sbits;
-        misc[(size_t)CZ_ROW_TINFO * N + env] = e.tinfo;
-        misc[(size_t)CZ_ROW_MARKS * N + env] = e.marks;
-        misc[(size_t)CZ_ROW_VARIANT * N + env] = e.variant;
-        misc[(size_t)CZ_ROW_RECIPES * N + env] = e.rids;
-        misc[(size_t)CZ_ROW_EPISODE * N + env] = e.episode;
+        for (int s = 0; s < D; ++s) state_out[(size_t)s * N + env] = e.o[s * OSTRIDE];
+        for (int i = 0; i < A; ++i) state_out[(size_t)(D + i) * N + env] = e.ag[i * OSTRIDE];
+        misc_out[(size_t)CZ_ROW_SBITS * N + env] = e.sbits;
+        misc_out[(size_t)CZ_ROW_TINFO * N + env] = e.tinfo;
+        misc_out[(size_t)CZ_ROW_MARKS * N + env] = e.marks;
+        misc_out[(size_t)CZ_ROW_VARIANT * N + env] = e.variant;
+        misc_out[(size_t)CZ_ROW_RECIPES * N + env] = e.rids;
+        misc_out[(size_t)CZ_ROW_EPISODE * N + env] = e.episode;
         if (errflags && e.err) errflags[env] |= e.err;
       }
     }
@@ -386,6 +426,7 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
     ws->wobs[lane] = write_obs ? 1u : 0u;
     __syncwarp();
 
+    if (OBS == OBS_NONE) continue;  // pipelined step: observations come from the observe kernel on the other stream
     // ---- phase 4: observation rows of the tile, one environment (A rows) at a time, whole warp
     // Its invariants are derived here, from an opaque copy of the lane id, so that they are not
     // hoisted above the dynamics (where they would be spilled: registers are capped for 28 warps/SM).
@@ -486,6 +527,87 @@ cz_env_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, con
 }
 
 // =========================================================================================
+// Environment-per-warp observation writer (specialised configurations): obs = f(state), ONE WARP PER
+// ENVIRONMENT (its NA rows), eight environments per block, tens of thousands of short blocks.
+// Used by the pipelined step: short blocks retire continuously, so the high-priority dynamics
+// kernel of the next step finds free SM slots and overlaps with this kernel's stores instead of
+// queueing behind a single wave of long-running blocks.  A lane owns one (observer, slot) pair and
+// reads its slot's state word straight from L2 (the dynamics kernel has just written it); the warp
+// zero-fills and fills its private staging rows, then streams the computed range and the table
+// segments out with 128-bit stores.  No TMA, no proxy fence, no block-level barrier.
+// =========================================================================================
+#define ENVS_WARPS 8
+#ifndef CZ_ENVS_MIN_BLOCKS
+#define CZ_ENVS_MIN_BLOCKS 8
+#endif
+
+template <int NA>
+__global__ void __launch_bounds__(32 * ENVS_WARPS, CZ_ENVS_MIN_BLOCKS)
+cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, double* __restrict__ obs, int n_envs) {
+  extern __shared__ __align__(16) unsigned char smem_rows[];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int env = blockIdx.x * ENVS_WARPS + warp;
+  if (env >= n_envs) return;
+  const int D = T.D, tab2 = T.tab_len >> 1, L2 = T.L >> 1;
+  const size_t N = (size_t)n_envs;
+  const int stage2 = (T.stage_len + 1) >> 1;  // double2 per staging row
+  double2* stage = reinterpret_cast<double2*>(smem_rows) + (size_t)warp * NA * stage2;
+
+  // this lane's (observer, slot) pair and the state words it needs
+  const LaneSlot ls = cz_lane_slot_packed(T, lane);
+  const bool is_agent = ls.kind == 2;
+  uint32_t rec = 0;
+  if (ls.off >= 0) rec = __ldg(state + (size_t)(is_agent ? D + ls.idx : ls.idx) * N + env);
+  const uint32_t me = __ldg(state + (size_t)(D + ls.agent) * N + env);           // this pair's observer
+  const uint32_t var = __ldg(state + (size_t)(D + NA + CZ_ROW_VARIANT) * N + env);
+  const double2* tab = reinterpret_cast<const double2*>(T.obs_table) + (size_t)var * 64 * tab2 + lane;
+  double2* g2 = reinterpret_cast<double2*>(obs + (size_t)env * NA * T.L);
+  // never-occupied slots are zeros: clear the staging rows, then fill the live slots
+  for (int k = lane; k < NA * stage2; k += 32) stage[k] = make_double2(0.0, 0.0);
+  __syncwarp();
+  if (ls.off >= 0) {
+    const bool present = is_agent || (rec & O_PRESENT);
+    const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+    const uint32_t fb4 = is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2);
+    const uint32_t one = 1u << (ls.flen - 1);
+    const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
+    const bool self = is_agent && (int)ls.idx == ls.agent;
+    const int x = rec & 7u, y = (rec >> 3) & 7u;
+    // (x - ax) / W from the host-divided table; the observer's own entry is x / W (cooking_env.py:364-368)
+    double X = __ldg(T.xlut + (x - (self ? 0 : (int)(me & 7u)) + T.W - 1));
+    double Y = __ldg(T.ylut + (y - (self ? 0 : (int)((me >> 3) & 7u)) + T.H - 1));
+    if (!present) { X = 0.0; Y = 0.0; }
+    double* out = reinterpret_cast<double*>(stage + ls.agent * stage2) + ls.off;
+    out[0] = X;
+    out[1] = Y;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (k < (int)ls.flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, (fb >> k & 1u) ? 0x3FF00000u : 0u);
+  }
+  __syncwarp();
+  {
+    const int n2 = T.ranges[0][1] >> 1, o2 = T.ranges[0][0] >> 1, s2 = (T.ranges[0][0] - T.stage_lo) >> 1;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+      for (int k = lane; k < n2; k += 32) g2[a * L2 + o2 + k] = stage[a * stage2 + s2 + k];
+  }
+  {  // table segments: all rows' loads first, then the stores
+    double2 v0[NA], v1[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const uint32_t cell = __shfl_sync(0xffffffffu, me, a * T.n_comp) & 63u;  // lane a*n_comp observes for agent a
+      if (ls.t0 >= 0) v0[a] = __ldg(tab + cell * tab2);
+      if (ls.t1 >= 0) v1[a] = __ldg(tab + cell * tab2 + 32);
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      if (ls.t0 >= 0) g2[a * L2 + ls.t0] = v0[a];
+      if (ls.t1 >= 0) g2[a * L2 + ls.t1] = v1[a];
+    }
+  }
+}
+
+// =========================================================================================
 // Host side: tables object and the C ABI
 // =========================================================================================
 static thread_local char g_err[512] = "";
@@ -512,6 +634,12 @@ struct cz_tables {
   // scratch for cz_step_host
   uint8_t* d_actions; double* d_obs; double* d_reward; uint8_t* d_term; uint8_t* d_trunc;
   int scratch_envs;
+  // pipelined step: dynamics on a high-priority stream, observations on a second one, ping-pong state
+  cudaStream_t pipe_dyn, pipe_obs;
+  cudaEvent_t ev_user, ev_dyn, ev_obs[2];
+  int pipe_ready, pipe_cur, pipe_obs_pending[2];
+  int pipe_dyn_blocks;   // resident dynamics blocks per SM in the pipelined step (0 = no cap)
+  size_t smem_optin;
 };
 
 template <typename Tp>
@@ -571,6 +699,11 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   memset(t, 0, sizeof(*t));
   t->device = device;
   t->num_sms = prop.multiProcessorCount;
+  t->smem_optin = prop.sharedMemPerBlockOptin;
+  {
+    const char* pb = getenv("CZ_PIPE_DYN_BLOCKS");
+    t->pipe_dyn_blocks = pb ? atoi(pb) : 0;
+  }
   const char* p = getenv("CZ_OBS_PATH");
   t->obs_path = (p && !strcmp(p, "stg")) ? OBS_STG : OBS_TMA;
   if (d->obs_len & 1) t->obs_path = OBS_STG;  // bulk copies need 16-byte rows
@@ -589,7 +722,6 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     T.stage_len = T.ranges[T.n_ranges - 1][0] + T.ranges[T.n_ranges - 1][1] - T.stage_lo;
   }
   if ((T.L & 1) && T.n_segs > 0) { delete t; return cz_fail(CZ_EINVAL, "%s", "table segments need an even obs_len"); }
-
   T.V = d->num_variants; T.P = d->num_layouts; T.B = d->num_book; T.max_steps = d->max_steps;
   T.end_all = d->end_all; T.grace = d->grace_period; T.n_switches = d->num_switches; T.n_blocks = d->num_blocks;
   T.rows = T.D + T.A + CZ_NUM_MISC_ROWS;
@@ -617,6 +749,21 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   UP(spawn_x, d->spawn_x, (size_t)T.A * 8);
   UP(spawn_y, d->spawn_y, (size_t)T.A * 8);
   UP(spawn_n, d->spawn_n, (size_t)T.A * 2);
+  if (rc == CZ_OK) {  // per-lane maps of the packed (observer, slot) layout
+    int4 lm[32];
+    const int n0 = T.n_segs > 0 ? T.segs[0][1] >> 1 : 0, n1 = T.n_segs > 1 ? T.segs[1][1] >> 1 : 0;
+    for (int l = 0; l < 32; ++l) {
+      const bool live = T.n_comp > 0 && l < T.A * T.n_comp;
+      int tt[2];
+      for (int k = 0; k < 2; ++k) {
+        const int e = l + 32 * k;
+        tt[k] = e < n0 ? (T.segs[0][0] >> 1) + e : (e < n0 + n1 ? (T.segs[1][0] >> 1) + e - n0 : -1);
+      }
+      // the computed-slot descriptor itself travels in the map: one load instead of a dependent pair
+      lm[l] = make_int4(live ? (int)d->comp_slots[l % T.n_comp] : -1, live ? l / T.n_comp : 0, tt[0], tt[1]);
+    }
+    rc = upload(t, lm, 32, &T.lane_map);
+  }
 #undef UP
   if (rc == CZ_OK) {  // read-only shared-memory image of a block: LUTs + the small tables
     static BlockSmem img;
@@ -653,13 +800,15 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     const char* g = getenv("CZ_GENERIC");
     if (g && g[0] == '1') t->simple = 0;
   }
-#define SET_SMEM(K) CZ_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+#define SET_SMEM(K) CZ_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin))
 #define SET_MODE(M)                                                                                    \
   SET_SMEM((cz_env_kernel<M, OBS_TMA, 0>)); SET_SMEM((cz_env_kernel<M, OBS_STG, 0>));                   \
   SET_SMEM((cz_env_kernel<M, OBS_TMA, 1>)); SET_SMEM((cz_env_kernel<M, OBS_TMA, 2>));                   \
   SET_SMEM((cz_env_kernel<M, OBS_TMA, 3>)); SET_SMEM((cz_env_kernel<M, OBS_TMA, 4>));                   \
   SET_SMEM((cz_env_kernel<M, OBS_STG, 1>)); SET_SMEM((cz_env_kernel<M, OBS_STG, 2>));                   \
-  SET_SMEM((cz_env_kernel<M, OBS_STG, 3>)); SET_SMEM((cz_env_kernel<M, OBS_STG, 4>))
+  SET_SMEM((cz_env_kernel<M, OBS_STG, 3>)); SET_SMEM((cz_env_kernel<M, OBS_STG, 4>));                   \
+  SET_SMEM((cz_env_kernel<M, OBS_NONE, 1>)); SET_SMEM((cz_env_kernel<M, OBS_NONE, 2>));                 \
+  SET_SMEM((cz_env_kernel<M, OBS_NONE, 3>)); SET_SMEM((cz_env_kernel<M, OBS_NONE, 4>))
   SET_MODE(MODE_STEP); SET_MODE(MODE_RESET); SET_MODE(MODE_OBSERVE);
 #undef SET_MODE
 #undef SET_SMEM
@@ -676,6 +825,10 @@ extern "C" int cz_tables_destroy(cz_tables* t) {
   if (t->d_reward) cudaFree(t->d_reward);
   if (t->d_term) cudaFree(t->d_term);
   if (t->d_trunc) cudaFree(t->d_trunc);
+  if (t->pipe_ready) {
+    cudaStreamDestroy(t->pipe_dyn); cudaStreamDestroy(t->pipe_obs);
+    cudaEventDestroy(t->ev_user); cudaEventDestroy(t->ev_dyn); cudaEventDestroy(t->ev_obs[0]); cudaEventDestroy(t->ev_obs[1]);
+  }
   delete t;
   return CZ_OK;
 }
@@ -690,20 +843,34 @@ static int cz_grid(const cz_tables* t, int n_envs) {
 }
 
 template <int MODE>
-static int cz_launch(const cz_tables* t, uint32_t* state, const uint8_t* actions, const int32_t* layout_ids,
+static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_out, bool dyn_only, const uint8_t* actions,
+                     const int32_t* layout_ids,
                      const uint8_t* recipe_ids, const uint8_t* mask, double* obs, double* reward, uint8_t* term,
                      uint8_t* trunc, uint32_t* err, int n_envs, uint32_t flags, uint64_t seed, int64_t env_offset,
                      void* stream) {
-  if (!t || !state || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (!t || !state || !state_out || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (n_envs <= 0) return CZ_OK;
   if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
   size_t smem = cz_smem_bytes(t->dev);
+  if (dyn_only && t->pipe_dyn_blocks > 0) {
+    // pipelined step: pad the dynamics kernel's shared memory so that only `pipe_dyn_blocks` of its
+    // blocks fit on an SM and the observation kernel of the previous step keeps the rest of the SM
+    size_t want = (size_t)(227 * 1024) / t->pipe_dyn_blocks - 1024;
+    if (want > smem && want <= t->smem_optin) smem = want;
+  }
   int grid = cz_grid(t, n_envs);
   cudaStream_t s = (cudaStream_t)stream;
 #define CZ_GO(O, NA)                                                                                                  \
-  cz_env_kernel<MODE, O, NA><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, actions, layout_ids, recipe_ids, mask, obs, \
+  cz_env_kernel<MODE, O, NA><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, state_out, actions, layout_ids, recipe_ids, mask, obs, \
                                                            reward, term, trunc, err, n_envs, flags, seed, env_offset)
-  if (t->simple && t->obs_path == OBS_TMA) {
+  if (dyn_only && t->simple) {
+    switch (t->dev.A) {
+      case 1: CZ_GO(OBS_NONE, 1); break;
+      case 2: CZ_GO(OBS_NONE, 2); break;
+      case 3: CZ_GO(OBS_NONE, 3); break;
+      default: CZ_GO(OBS_NONE, 4); break;
+    }
+  } else if (t->simple && t->obs_path == OBS_TMA) {
     switch (t->dev.A) {
       case 1: CZ_GO(OBS_TMA, 1); break;
       case 2: CZ_GO(OBS_TMA, 2); break;
@@ -731,7 +898,7 @@ static int cz_launch(const cz_tables* t, uint32_t* state, const uint8_t* actions
 extern "C" int cz_reset(const cz_tables* t, uint32_t* state, const int32_t* layout_ids, const uint8_t* recipe_ids,
                         const uint8_t* mask, double* obs, int n_envs, void* stream) {
   if (!layout_ids) return cz_fail(CZ_EINVAL, "%s", "layout_ids is required");
-  return cz_launch<MODE_RESET>(t, state, nullptr, layout_ids, recipe_ids, mask, obs, nullptr, nullptr, nullptr, nullptr,
+  return cz_launch<MODE_RESET>(t, state, state, false, nullptr, layout_ids, recipe_ids, mask, obs, nullptr, nullptr, nullptr, nullptr,
                                n_envs, 0, 0, 0, stream);
 }
 
@@ -739,13 +906,91 @@ extern "C" int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actio
                        uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, uint32_t flags,
                        uint64_t seed, int64_t env_offset, void* stream) {
   if (!actions || !reward || !terminated || !truncated) return cz_fail(CZ_EINVAL, "%s", "null argument");
-  return cz_launch<MODE_STEP>(t, state, actions, nullptr, nullptr, nullptr, obs, reward, terminated, truncated,
+  return cz_launch<MODE_STEP>(t, state, state, false, actions, nullptr, nullptr, nullptr, obs, reward, terminated, truncated,
                               error_flags, n_envs, flags, seed, env_offset, stream);
 }
 
 extern "C" int cz_observe(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, void* stream) {
-  return cz_launch<MODE_OBSERVE>(t, const_cast<uint32_t*>(state), nullptr, nullptr, nullptr, nullptr, obs, nullptr,
+  return cz_launch<MODE_OBSERVE>(t, state, const_cast<uint32_t*>(state), false, nullptr, nullptr, nullptr, nullptr, obs, nullptr,
                                  nullptr, nullptr, nullptr, n_envs, 0, 0, 0, stream);
+}
+
+static int cz_pipe_init(cz_tables* t) {
+  if (t->pipe_ready) return CZ_OK;
+  int lo = 0, hi = 0;
+  CZ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CZ_CUDA(cudaStreamCreateWithPriority(&t->pipe_dyn, cudaStreamNonBlocking, hi));  // highest priority: slips in between observe blocks
+  CZ_CUDA(cudaStreamCreateWithPriority(&t->pipe_obs, cudaStreamNonBlocking, lo));
+  CZ_CUDA(cudaEventCreateWithFlags(&t->ev_user, cudaEventDisableTiming));
+  CZ_CUDA(cudaEventCreateWithFlags(&t->ev_dyn, cudaEventDisableTiming));
+  CZ_CUDA(cudaEventCreateWithFlags(&t->ev_obs[0], cudaEventDisableTiming));
+  CZ_CUDA(cudaEventCreateWithFlags(&t->ev_obs[1], cudaEventDisableTiming));
+  t->pipe_ready = 1;
+  return CZ_OK;
+}
+
+extern "C" int cz_pipeline_reset(cz_tables* t, int current_half) {
+  if (!t || (current_half != 0 && current_half != 1)) return cz_fail(CZ_EINVAL, "%s", "bad argument");
+  int rc = cz_pipe_init(t);
+  if (rc != CZ_OK) return rc;
+  CZ_CUDA(cudaStreamSynchronize(t->pipe_dyn));
+  CZ_CUDA(cudaStreamSynchronize(t->pipe_obs));
+  t->pipe_cur = current_half;
+  t->pipe_obs_pending[0] = t->pipe_obs_pending[1] = 0;
+  return CZ_OK;
+}
+
+extern "C" int cz_pipeline_current(const cz_tables* t) { return t ? t->pipe_cur : CZ_EINVAL; }
+
+extern "C" int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* actions, double* obs, double* reward,
+                                 uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, uint32_t flags,
+                                 uint64_t seed, int64_t env_offset, void* stream) {
+  if (!t || !state2 || !actions || !obs || !reward || !terminated || !truncated) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (!t->simple) return cz_fail(CZ_EINVAL, "%s", "the pipelined step needs the specialised kernels (see DESIGN.md)");
+  int rc = cz_pipe_init(t);
+  if (rc != CZ_OK) return rc;
+  const size_t half = (size_t)t->dev.rows * n_envs;
+  const int cur = t->pipe_cur, nxt = cur ^ 1;
+  uint32_t* in = state2 + (size_t)cur * half;
+  uint32_t* out = state2 + (size_t)nxt * half;
+  cudaStream_t user = (cudaStream_t)stream;
+  // the caller's stream has produced the actions and consumed the previous rewards / flags
+  CZ_CUDA(cudaEventRecord(t->ev_user, user));
+  CZ_CUDA(cudaStreamWaitEvent(t->pipe_dyn, t->ev_user, 0));
+  // the observe kernel that read the half we are about to overwrite must be done
+  if (t->pipe_obs_pending[nxt]) CZ_CUDA(cudaStreamWaitEvent(t->pipe_dyn, t->ev_obs[nxt], 0));
+  rc = cz_launch<MODE_STEP>(t, in, out, true, actions, nullptr, nullptr, nullptr, obs, reward, terminated, truncated,
+                            error_flags, n_envs, flags, seed, env_offset, t->pipe_dyn);
+  if (rc != CZ_OK) return rc;
+  CZ_CUDA(cudaEventRecord(t->ev_dyn, t->pipe_dyn));
+  CZ_CUDA(cudaStreamWaitEvent(t->pipe_obs, t->ev_dyn, 0));
+  CZ_CUDA(cudaStreamWaitEvent(t->pipe_obs, t->ev_user, 0));
+  {
+    const int blocks = (n_envs + ENVS_WARPS - 1) / ENVS_WARPS;
+    const size_t smem = (size_t)ENVS_WARPS * t->dev.A * ((t->dev.stage_len + 1) / 2) * 16;
+    switch (t->dev.A) {
+      case 1: cz_obs_envs_kernel<1><<<blocks, 32 * ENVS_WARPS, smem, t->pipe_obs>>>(t->dev, out, obs, n_envs); break;
+      case 2: cz_obs_envs_kernel<2><<<blocks, 32 * ENVS_WARPS, smem, t->pipe_obs>>>(t->dev, out, obs, n_envs); break;
+      case 3: cz_obs_envs_kernel<3><<<blocks, 32 * ENVS_WARPS, smem, t->pipe_obs>>>(t->dev, out, obs, n_envs); break;
+      default: cz_obs_envs_kernel<4><<<blocks, 32 * ENVS_WARPS, smem, t->pipe_obs>>>(t->dev, out, obs, n_envs); break;
+    }
+    g_launches.fetch_add(1);
+    CZ_CUDA(cudaGetLastError());
+  }
+  CZ_CUDA(cudaEventRecord(t->ev_obs[nxt], t->pipe_obs));
+  t->pipe_obs_pending[nxt] = 1;
+  t->pipe_cur = nxt;
+  return CZ_OK;
+}
+
+extern "C" int cz_pipeline_wait(cz_tables* t, void* stream) {
+  if (!t) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (!t->pipe_ready) return CZ_OK;
+  cudaStream_t user = (cudaStream_t)stream;
+  CZ_CUDA(cudaEventRecord(t->ev_dyn, t->pipe_dyn));
+  CZ_CUDA(cudaStreamWaitEvent(user, t->ev_dyn, 0));
+  if (t->pipe_obs_pending[t->pipe_cur]) CZ_CUDA(cudaStreamWaitEvent(user, t->ev_obs[t->pipe_cur], 0));
+  return CZ_OK;
 }
 
 extern "C" int cz_step_host(cz_tables* t, uint32_t* state_dev, const uint8_t* actions_host, double* obs_host,

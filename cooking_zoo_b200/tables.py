@@ -359,3 +359,4 @@ def _compile_obs_plan(t, obs_slots):
     t.obs_ranges, t.num_obs_ranges = rng_arr, len(ranges)
     t.comp_slots = np.array([o | (n - 2) << 12 | kind << 15 | idx << 17 for o, n, kind, idx in comp] or [0], np.uint32)
     t.num_comp_slots = len(comp)
+

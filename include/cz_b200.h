@@ -181,6 +181,20 @@ uint64_t cz_layout_draw(uint64_t seed, uint64_t global_env, uint64_t episode);
  * list[floor(u * len)].  Parity harnesses patch the reference's call sites to read this stream. */
 double cz_spawn_uniform(uint64_t seed, uint64_t global_env, uint64_t episode, uint64_t t, uint64_t c);
 
+/* Pipelined throughput mode (specialised kernels only).  `state2` is TWO state matrices back to back
+ * ([2][rows][n]); step k+1's dynamics (cooking_world.world_step + compute_rewards) run on an internal
+ * high-priority stream reading one half and writing the other, while the observation writer
+ * (get_feature_vector) of step k is still streaming out on a second internal stream.  Every step does
+ * the full work of cz_step; only the ordering guarantee changes: outputs are ordered with the
+ * caller's stream after cz_pipeline_wait().  cz_pipeline_reset(t, h) declares that half h holds the
+ * current state (after cz_reset wrote it) and drains the internal streams. */
+int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* actions, double* obs, double* reward,
+                      uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs,
+                      uint32_t flags, uint64_t seed, int64_t env_offset, void* stream);
+int cz_pipeline_wait(cz_tables* t, void* stream);
+int cz_pipeline_reset(cz_tables* t, int current_half);
+int cz_pipeline_current(const cz_tables* t);
+
 /* Number of kernels launched by this library since load (the bench's gpu_launches claim). */
 uint64_t cz_launch_count(void);
 

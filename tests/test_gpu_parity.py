@@ -144,3 +144,24 @@ def test_auto_reset_and_shard_independence():
                 lid = whole.lib.cz_layout_draw(11, k, episode) % P
                 orc = OracleEnv(whole.tables.layouts[lid], cfg["recipes"], 7, end_condition_all_dishes=True)
                 assert_obs_equal(np.stack([orc.observe(i) for i in range(2)]), o[k].cpu().numpy(), f"autoreset env {k}")
+
+
+def test_pipelined_step_is_bit_identical_to_the_in_place_step():
+    """throughput mode (cz_step_pipelined: two streams, ping-pong state) does the same work as cz_step"""
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=30,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    n = 5000
+    a = _make(n, cfg, auto_reset=True, seed=3, layout_pool_size=64)
+    b = _make(n, cfg, auto_reset=True, seed=3, layout_pool_size=64, pipelined=True)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(1)
+    for t in range(70):
+        act = torch.from_numpy(rng.integers(0, 5, size=(n, 2)).astype(np.uint8)).cuda()
+        oa, ra, ta, ua, _ = a.step(act)
+        ob, rb, tb, ub, _ = b.step(act)
+        if t % 7 == 0 or t > 60:
+            b.wait()
+            torch.cuda.synchronize()
+            assert torch.equal(oa.view(torch.int64), ob.view(torch.int64)), t
+            assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(ta, tb) and torch.equal(ua, ub)
+            assert torch.equal(a.state, b.state)
