@@ -193,7 +193,7 @@ def run_gpu_arm(args):
 
     def timed_run(pipelined, sample_clocks):
         """W warm-up + K timed steps of one mode; returns (env, ms_total max over ranks, launches, clocks)."""
-        env = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+        env = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
                                 device=str(dev), recipe_pool=BOOK, layout_pool_size=400, layout_seed=0,
                                 auto_reset=True, seed=2026, env_offset=rank * N, pipelined=pipelined)
         env.reset(recipe_ids=recipe_ids)
@@ -281,7 +281,7 @@ def run_gpu_arm(args):
     cfg3 = None
     if rank == 0 and world == 1 and not args.no_cfg3:
         n3 = 4096
-        env3 = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+        env3 = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
                                  device=str(dev), layout_pool_size=400, layout_seed=0, auto_reset=True, seed=7)
         env3.reset()
         act3 = torch.randint(0, 5, (ring, n3, A), generator=g, dtype=torch.uint8).to(dev)

@@ -24,7 +24,7 @@ class TableDesc(C.Structure):
                  ("num_obs_segs", C.c_int32), ("num_obs_ranges", C.c_int32), ("obs_table_len", C.c_int32),
                  ("obs_segs", (C.c_int32 * 3) * 2), ("obs_ranges", (C.c_int32 * 2) * 3),
                  ("obs_len", C.c_int32), ("num_variants", C.c_int32), ("num_layouts", C.c_int32),
-                 ("num_book", C.c_int32), ("max_steps", C.c_int32), ("end_all", C.c_int32),
+                 ("num_book", C.c_int32), ("max_steps", C.c_int32), ("end_all", C.c_int32), ("action_scheme", C.c_int32),
                  ("grace_period", C.c_int32), ("num_switches", C.c_int32), ("num_blocks", C.c_int32),
                  ("reward_node", C.c_double), ("reward_recipe", C.c_double), ("reward_penalty", C.c_double),
                  ("reward_time", C.c_double), ("respawn_rate", C.c_double), ("despawn_rate", C.c_double)]
@@ -101,6 +101,7 @@ def make_desc(t):
             d.obs_ranges[k][j] = int(t.obs_ranges[k, j])
     d.num_variants, d.num_layouts, d.num_book = t.num_variants, t.num_layouts, len(t.recipe_names)
     d.max_steps, d.end_all, d.grace_period = t.max_steps, t.end_all, t.grace_period
+    d.action_scheme = t.action_scheme
     d.num_switches, d.num_blocks = t.num_switches, t.num_blocks
     d.reward_node, d.reward_recipe, d.reward_penalty = t.reward_node, t.reward_recipe, t.reward_penalty
     d.reward_time, d.respawn_rate, d.despawn_rate = t.reward_time, t.respawn_rate, t.despawn_rate

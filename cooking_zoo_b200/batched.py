@@ -37,7 +37,7 @@ class _LazyInfo:
 
 class BatchedCookingEnv:
     def __init__(self, num_envs, level, meta_file, num_agents, max_steps, recipes, agent_visualization=None,
-                 obs_spaces=None, end_condition_all_dishes=False, action_scheme="scheme3", render=False,
+                 obs_spaces=None, end_condition_all_dishes=False, action_scheme="scheme1", render=False,
                  reward_scheme=None, agent_respawn_rate=0.0, grace_period=20, agent_despawn_rate=0.0, *,
                  device="cuda:0", recipe_pool=None, layout_pool_size=256, layout_seed=0, layouts=None,
                  auto_reset=False, seed=0, env_offset=0, pipelined=False):
@@ -45,9 +45,9 @@ class BatchedCookingEnv:
         if any(o != "feature_vector" for o in obs_spaces):
             raise NotImplementedError("the batched entry point builds feature_vector observations only "
                                       "(symbolic/full are host object graphs in the reference)")
-        if action_scheme != "scheme3":
-            raise NotImplementedError("only action_scheme='scheme3' is compiled (scheme1 is next; scheme2 "
-                                      "raises AttributeError in the reference itself)")
+        if action_scheme not in ("scheme1", "scheme3"):
+            raise NotImplementedError("action_scheme must be 'scheme1' or 'scheme3' (scheme2 raises AttributeError "
+                                      "in the reference itself, action_scheme2.py:15)")
         if render:
             raise NotImplementedError("rendering is out of scope")
         self.lib = _native.load_library()       # raises when the CUDA library is missing
@@ -58,7 +58,8 @@ class BatchedCookingEnv:
         self.possible_agents = ["player_" + str(r) for r in range(num_agents)]   # cooking_env.py:76
         self.tables = compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_scheme,
                                      end_condition_all_dishes, grace_period, agent_respawn_rate,
-                                     agent_despawn_rate, recipe_pool, layout_pool_size, layout_seed, layouts)
+                                     agent_despawn_rate, recipe_pool, layout_pool_size, layout_seed, layouts,
+                                     action_scheme)
         t = self.tables
         self.obs_len, self.max_steps = t.obs_len, t.max_steps
         self.auto_reset, self.seed, self.env_offset = bool(auto_reset), int(seed), int(env_offset)

@@ -11,6 +11,7 @@
 // ---- device copy of the compiled tables (passed to kernels by value) ------------------
 struct CzDev {
   int W, H, A, R, D, S, T, L, V, P, B, max_steps, end_all, grace, n_switches, n_blocks, rows;
+  int scheme;  // 1 or 3: ActionScheme1 / ActionScheme3 (cooking_world/actions.py:2-17, 39-50)
   int n_comp, n_segs, n_ranges, tab_len;
   int segs[2][3];    // table segments of a row: {row offset, length, table offset} (doubles, even)
   int ranges[3][2];  // computed ranges of a row: {row offset, length}
@@ -200,8 +201,11 @@ __device__ __forceinline__ uint32_t cz_plate_count_clear_free(const CzDev& T, En
 
 // resolve_interaction -> resolve_execute_action | resolve_primary_interaction -> attempt_merge
 // (action_scheme3.py:37-43, cooking_world.py:114-136, 156-170, 243-261).
+// mode: 0 = scheme3 (execute iff an action object holds something unfinished, else primary),
+//       5 / 6 / 7 = scheme1's INTERACT_PRIMARY / INTERACT_PICK_UP_SPECIAL / EXECUTE_ACTION (action_scheme1.py:33-40).
+// Returns the plate whose content lost an item (its free flags are refreshed at the end of the step) or 0xFF.
 template <bool FAST>
-__device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, uint32_t cell) {
+__device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int i, uint32_t cell, uint32_t mode) {
   const uint32_t agent_rec = e.ag[i * OSTRIDE];
   const SmemTabs* st = e.st;
   const uint32_t g = TAB_GRID(e.variant, cell);
@@ -226,11 +230,25 @@ __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, u
   }
   const bool blocked = cz_agent_on(T, e, cell);
 
-  if ((kind == ST_CUTBOARD || kind == ST_BLENDER) && any_not_done) {
+  if (mode == 6u) {
+    // ---- resolve_interaction_pick_up_special (cooking_world.py:138-154): take the last item off the one plate
+    if (blocked || A_HAS(agent_rec) || n_dyn == 0 || n_plates != 1) return 0xFFu;
+    int top = -1, ts = -1;
+    for (int k = 0; k < T.D; ++k) {
+      uint32_t r = e.o[k * OSTRIDE];
+      if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == (uint32_t)plate && (int)O_POS(r) > top) { top = O_POS(r); ts = k; }
+    }
+    if (ts < 0) return 0xFFu;  // content.pop(-1) on an empty plate: IndexError, swallowed
+    e.o[ts * OSTRIDE] = O_WITH_XY(O_WITH_CONT(e.o[ts * OSTRIDE], CK_HELD, i, 0), A_XY(agent_rec));
+    e.ag[i * OSTRIDE] = (agent_rec & ~(0x3Fu << 9)) | (1u << 9) | ((uint32_t)ts << 10);
+    return (uint32_t)plate;
+  }
+  if (mode == 7u || (mode == 0u && (kind == ST_CUTBOARD || kind == ST_BLENDER) && any_not_done)) {
     // ---- resolve_execute_action (cooking_world.py:156-170)
-    if (blocked) return;
+    if (blocked) return 0xFFu;
+    if (kind != ST_CUTBOARD && kind != ST_BLENDER) return 0xFFu;  // not an ActionObject
     if (kind == ST_CUTBOARD) {  // Cutboard.action (world_objects.py:250-269)
-      if (!(e.sbits & SB_CUT_READY(sp))) return;
+      if (!(e.sbits & SB_CUT_READY(sp))) return 0xFFu;
       for (int p = 0; p < n_content; ++p) {
         int s = -1;
         for (int k = 0; k < T.D; ++k) {
@@ -241,7 +259,7 @@ __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, u
         uint32_t r = e.o[s * OSTRIDE];
         uint32_t tid = TAB_STYPE(s);
         uint32_t tf = TAB_TF(s);
-        if (!(tf & TF_CHOP)) return;
+        if (!(tf & TF_CHOP)) return 0xFFu;
         if (r & O_CHOP) continue;  // ChopFood.chop / Bread.chop: already chopped -> not executed
         e.o[s * OSTRIDE] = r | O_CHOP;
         e.sbits &= ~SB_CUT_READY(sp);
@@ -256,20 +274,20 @@ __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, u
             e.o[slot * OSTRIDE] = O_WITH_CONT(cell | O_PRESENT | O_CHOP | O_FREE, CK_STATIC, 0, n_content);
           }
         }
-        return;
+        return 0xFFu;
       }
       e.err |= CZ_ERR_CUTBOARD_NONE;
     } else {  // Blender.action (world_objects.py:356-360)
       if (e.sbits & SB_BL_READY(sp)) e.sbits ^= SB_BL_TOGGLE(sp);
     }
-    return;
+    return 0xFFu;
   }
 
   // ---- resolve_primary_interaction (cooking_world.py:114-136)
-  if (blocked) return;
+  if (blocked) return 0xFFu;
   const uint32_t axy = A_XY(agent_rec);
   if (!A_HAS(agent_rec)) {
-    if (n_dyn == 0) return;
+    if (n_dyn == 0) return 0xFFu;
     bool rel = true;  // StaticObject.releases() with side effects
     if (kind == ST_DELIVER) rel = false;  // world_objects.py:117-118
     else if (kind == ST_CUTBOARD) {  // :275-278
@@ -278,15 +296,15 @@ __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, u
       if (e.sbits & SB_BL_TOGGLE(sp)) rel = false;
       else if (n_content - 1 == 0) e.sbits &= ~SB_BL_READY(sp);
     }
-    if (!rel) return;
+    if (!rel) return 0xFFu;
     int gs = first_free >= 0 ? first_free : last;
     uint32_t r = e.o[gs * OSTRIDE];
-    if (O_CK(r) != CK_STATIC) return;  // `object_to_grab in static_object.content`
+    if (O_CK(r) != CK_STATIC) return 0xFFu;  // `object_to_grab in static_object.content`
     cz_remove_from_static(T, e, cell, O_POS(r));
     e.o[gs * OSTRIDE] = O_WITH_CONT(r, CK_HELD, i, 0);
     cz_move_obj<FAST>(T, e, gs, axy);  // Agent.grab (world_objects.py:786-788)
     e.ag[i * OSTRIDE] = (agent_rec & ~(0x3Fu << 9)) | (1u << 9) | ((uint32_t)gs << 10);
-    return;
+    return 0xFFu;
   }
 
   // ---- attempt_merge (cooking_world.py:243-261)
@@ -330,6 +348,7 @@ __device__ __forceinline__ void cz_interact(const CzDev& T, EnvRegs& e, int i, u
       e.ag[i * OSTRIDE] = dropped;
     }
   }
+  return 0xFFu;
 }
 
 // progress_world's free-flag refresh for one static container (cooking_world.py:82-88):
@@ -343,6 +362,20 @@ __device__ __forceinline__ void cz_refresh_static_free(const CzDev& T, EnvRegs& 
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
     if ((r & O_PRESENT) && O_CK(r) == CK_STATIC && O_XY(r) == cell)
+      e.o[k * OSTRIDE] = ((int)O_POS(r) == top) ? (r | O_FREE) : (r & ~O_FREE);
+  }
+}
+
+// The same for a plate that lost its top item (scheme1's pick-up-special).
+__device__ __forceinline__ void cz_refresh_plate_free(const CzDev& T, EnvRegs& e, uint32_t p) {
+  int top = -1;
+  for (int k = 0; k < T.D; ++k) {
+    uint32_t r = e.o[k * OSTRIDE];
+    if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == p && (int)O_POS(r) > top) top = O_POS(r);
+  }
+  for (int k = 0; k < T.D; ++k) {
+    uint32_t r = e.o[k * OSTRIDE];
+    if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == p)
       e.o[k * OSTRIDE] = ((int)O_POS(r) == top) ? (r | O_FREE) : (r & ~O_FREE);
   }
 }
@@ -401,6 +434,7 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
                                             double* __restrict__ reward, uint8_t* __restrict__ term_out,
                                             uint8_t* __restrict__ trunc_out, uint64_t seed, uint64_t genv) {
   const int A = NA ? NA : T.A;  // compile-time agent count in the specialised kernels
+  const bool scheme1 = T.scheme == 1;
   const SmemTabs* st = e.st;
   const uint32_t t = TI_T(e.tinfo) + 1;  // :244
   uint32_t active = 0;
@@ -414,19 +448,19 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
   for (int i = 0; i < A; ++i) {
     if (!(active >> i & 1u)) continue;
     uint32_t ai = (act_packed >> (8 * i)) & 255u;
-    if (ai > 4u) ai = 0;  // outside Discrete(5): behaves as a no-op
+    if (ai > (scheme1 ? 7u : 4u)) ai = 0;  // outside the action space: behaves as a no-op
     uint32_t rec = e.ag[i * OSTRIDE];
     int x = rec & 7u, y = (rec >> 3) & 7u;
     uint32_t faced = A_XY(rec);
-    if (ai) {
+    if (ai >= 1u && ai <= 4u) {
       rec = (rec & ~(7u << 6)) | (ai << 6);  // change_orientation even if cancelled later (:8-10)
       e.ag[i * OSTRIDE] = rec;
       int tx = x + (ai == 2) - (ai == 1), ty = y + (ai == 3) - (ai == 4);  // cooking_world.py:172-184
       if (tx < 0 || ty < 0 || tx > T.W - 1 || ty > T.H - 1) ai = 0;  // check_inbounds :192-204
       else faced = (uint32_t)(tx | ty << 3);
     }
-    // check_collisions, first loop (:206-216)
-    uint32_t tgt = ai ? faced : A_XY(rec);
+    // check_collisions, first loop (:206-216); scheme1's interact actions target the agent's own cell
+    uint32_t tgt = (ai >= 1u && ai <= 4u) ? faced : A_XY(rec);
     bool w = cz_walkable<FAST>(T, e, tgt);
     uint32_t endc = (w ? tgt : A_XY(rec)) | (w ? 0x40u : 0u);
     apack |= ai << (8 * i);
@@ -444,11 +478,24 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
     }
   }
   // sequential resolution in agent order (action_scheme3.py:15-34)
-  uint32_t pressed = 0, dirty = 0xFFFFFFFFu;
+  uint32_t pressed = 0, dirty = 0xFFFFFFFFu, dirty_plate = 0xFFFFFFFFu;
   for (int i = 0; i < A; ++i) {
     if (!(active >> i & 1u)) continue;
     uint32_t rec = e.ag[i * OSTRIDE];
     uint32_t ai = (cancel >> i & 1u) ? 0u : ((apack >> (8 * i)) & 255u);
+    if (scheme1) {
+      if (ai == 0u) continue;  // scheme1: only walk actions walk (action_scheme1.py:16-19), a no-op does nothing
+      if (ai >= 5u) {          // interact with the cell the agent faces (cooking_world.py:115,139,157)
+        const uint32_t o = A_ORI(rec);
+        const int fx = (int)(rec & 7u) + (o == 2) - (o == 1), fy = (int)((rec >> 3) & 7u) + (o == 3) - (o == 4);
+        if (fx < 0 || fy < 0 || fx > T.W - 1 || fy > T.H - 1) { e.err |= CZ_ERR_OFFGRID; continue; }
+        const uint32_t cell = (uint32_t)(fx | fy << 3);
+        const uint32_t p = cz_interact<FAST>(T, e, i, cell, ai);
+        dirty = (dirty & ~(0xFFu << (8 * i))) | (cell << (8 * i));
+        dirty_plate = (dirty_plate & ~(0xFFu << (8 * i))) | (p << (8 * i));
+        continue;
+      }
+    }
     uint32_t tgt = ai ? ((fpack >> (8 * i)) & 63u) : A_XY(rec);
     if (cz_walkable<FAST>(T, e, tgt)) {  // resolve_walking_action (:26-34)
       rec = (rec & ~63u) | tgt;
@@ -459,8 +506,8 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
         e.sbits ^= SB_SW_ACTIVE(g >> 4);
         pressed |= 1u << (g >> 4);
       }
-    } else if (ai) {
-      cz_interact<FAST>(T, e, i, tgt);
+    } else if (ai && !scheme1) {
+      cz_interact<FAST>(T, e, i, tgt, 0u);
       dirty = (dirty & ~(0xFFu << (8 * i))) | (tgt << (8 * i));
     }
   }
@@ -490,6 +537,12 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
     for (int i = 0; i < A; ++i) {
       uint32_t c = (dirty >> (8 * i)) & 255u;
       if (c != 0xFFu) cz_refresh_static_free(T, e, c);
+    }
+  }
+  if (dirty_plate != 0xFFFFFFFFu) {
+    for (int i = 0; i < A; ++i) {
+      uint32_t p = (dirty_plate >> (8 * i)) & 255u;
+      if (p != 0xFFu) cz_refresh_plate_free(T, e, p);
     }
   }
   // ---- resolve_linked_interactions (cooking_world.py:90-92; Switch :165-169, Block :215-216)

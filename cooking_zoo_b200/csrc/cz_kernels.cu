@@ -723,6 +723,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   }
   if ((T.L & 1) && T.n_segs > 0) { delete t; return cz_fail(CZ_EINVAL, "%s", "table segments need an even obs_len"); }
   T.V = d->num_variants; T.P = d->num_layouts; T.B = d->num_book; T.max_steps = d->max_steps;
+  T.scheme = d->action_scheme == 1 ? 1 : 3;
   T.end_all = d->end_all; T.grace = d->grace_period; T.n_switches = d->num_switches; T.n_blocks = d->num_blocks;
   T.rows = T.D + T.A + CZ_NUM_MISC_ROWS;
   T.r_node = d->reward_node; T.r_recipe = d->reward_recipe; T.r_penalty = d->reward_penalty; T.r_time = d->reward_time;

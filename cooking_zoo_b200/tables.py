@@ -42,11 +42,16 @@ class CompiledTables:
 def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_scheme=None,
                    end_condition_all_dishes=False, grace_period=20, agent_respawn_rate=0.0,
                    agent_despawn_rate=0.0, recipe_pool=None, layout_pool_size=256, layout_seed=0,
-                   layouts=None):
+                   layouts=None, action_scheme="scheme3"):
     """`recipes`: the per-agent recipe names of the reference constructor (default per-env
     assignment).  `recipe_pool`: every recipe name environments may be assigned (defaults to
     `recipes`).  `layouts`: explicit list of layout dicts (overrides sampling)."""
     t = CompiledTables()
+    if action_scheme not in ("scheme1", "scheme3"):
+        # scheme2 raises AttributeError on its first step in the reference (action_scheme2.py:15)
+        raise NotImplementedError("action_scheme must be 'scheme1' or 'scheme3'")
+    t.action_scheme = 1 if action_scheme == "scheme1" else 3
+    t.num_actions = 8 if action_scheme == "scheme1" else 5       # len(ACTIONS), cooking_env.py:131
     level_object = load_level_object(level)
     meta = load_meta(meta_file)
     meta_count = dict(meta)

@@ -66,7 +66,7 @@ class ParallelCookingEnv:
         self.goal_vectors = {a: np.eye(len(book))[i] for i, a in enumerate(self.possible_agents)}
         L = self._b.obs_len
         self.observation_spaces = {a: _box(-1, 1, (L,)) for a in self.possible_agents}
-        self.action_spaces = {a: _discrete(5) for a in self.possible_agents}   # len(ActionScheme3.ACTIONS)
+        self.action_spaces = {a: _discrete(self._b.tables.num_actions) for a in self.possible_agents}  # cooking_env.py:131
 
     def observation_space(self, agent):
         return self.observation_spaces[agent]

@@ -48,6 +48,7 @@ extern "C" {
 #define CZ_ERR_SPAWN_LOC 8u       /* generate_location timed out (parsing.py:154-167)               */
 #define CZ_ERR_TRUNC_DESPAWN 16u  /* IndexError at cooking_env.py:348 (truncation with despawned agent) */
 #define CZ_ERR_OBS_OVERFLOW 32u   /* more objects of a type than meta slots (cooking_env.py:371)    */
+#define CZ_ERR_OFFGRID 64u        /* scheme1 interaction with a cell off the grid: get_objects_at(...)[0] IndexError */
 
 /* ---- packed per-environment state --------------------------------------------------
  * `state` is a u32 matrix [cz_state_rows()][n_envs] (structure of arrays: row-major, the
@@ -106,6 +107,7 @@ typedef struct cz_table_desc {
   int32_t num_book;           /* B: compiled recipes                                        */
   int32_t max_steps;
   int32_t end_all;            /* end_condition_all_dishes                                   */
+  int32_t action_scheme;      /* 1 or 3 (ActionScheme1 / ActionScheme3, cooking_world/actions.py)  */
   int32_t grace_period;
   int32_t num_switches, num_blocks;
   double reward_node, reward_recipe, reward_penalty; /* reward_scheme terms                  */
@@ -154,7 +156,7 @@ int cz_reset(const cz_tables* t, uint32_t* state, const int32_t* layout_ids, con
 /* CookingEnvironment.accumulated_step + observe (environment/cooking_env.py:243-288):
  * world_step (cooking_world/cooking_world.py:104-112, action_scheme3.py:4-43), compute_rewards /
  * compute_truncated (:290-350), get_feature_vector (:352-373) for n_envs environments.
- * actions u8 [n][A]; obs f64 [n][A][L]; reward f64 [n][A]; terminated/truncated u8 [n][A];
+ * actions u8 [n][A] (0..4 under scheme3, 0..7 under scheme1); obs f64 [n][A][L]; reward f64 [n][A]; terminated/truncated u8 [n][A];
  * error_flags u32 [n] (OR-accumulated, may be NULL).  With CZ_STEP_AUTO_RESET the layout of
  * episode k of global environment g = env_offset + e is pool[cz_layout_draw(seed, g, k) % P]. */
 int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actions, double* obs, double* reward,

@@ -225,7 +225,7 @@ class OracleEnv:
 
     def __init__(self, layout, recipes, max_steps, reward_scheme=None,
                  end_condition_all_dishes=False, agent_respawn_rate=0.0, grace_period=20,
-                 agent_despawn_rate=0.0, spawn_stream=None):
+                 agent_despawn_rate=0.0, spawn_stream=None, action_scheme="scheme3"):
         self.layout = layout
         self.recipe_names = list(recipes)
         self.max_steps = max_steps
@@ -235,6 +235,9 @@ class OracleEnv:
         self.despawn_rate = agent_despawn_rate
         self.grace_period = grace_period
         self.spawn_stream = spawn_stream   # SpawnStream: stands in for np.random.random / random.sample
+        if action_scheme not in ("scheme1", "scheme3"):
+            raise ValueError("scheme2 raises AttributeError in the reference itself (action_scheme2.py:15)")
+        self.scheme = action_scheme
         self.error = 0                  # bit flags: "the reference would have raised here"
         self.events = {}                # branch-coverage counters for the test-suite
         self.reset()
@@ -320,7 +323,10 @@ class OracleEnv:
     def _world_step(self, actions):
         idx = [i for i in range(len(self.agents)) if self.active[i]]   # cooking_world.py:295
         self.status_changed = [False] * len(self.agents)
-        self._agent_actions(idx, [actions[i] for i in idx])
+        if self.scheme == "scheme1":
+            self._agent_actions_scheme1(idx, [actions[i] for i in idx])
+        else:
+            self._agent_actions(idx, [actions[i] for i in idx])
         self._progress_world()
         self._linked()
         self._agent_spawn()
@@ -372,6 +378,75 @@ class OracleEnv:
                 moved = True
             if not moved and a != 0:                             # `orig_location is agent.location` :22
                 self._interact(ag, cell)
+
+    def _checked_actions(self, ags, acts):
+        """check_inbounds + check_collisions (cooking_world.py:192-221), shared by the schemes."""
+        acts = list(acts)
+        for k, (ag, a) in enumerate(zip(ags, acts)):
+            if a == 0 or a == 5:
+                continue
+            tx, ty = self._target(ag, a)
+            if tx > self.W - 1 or tx < 0 or ty > self.H - 1 or ty < 0:
+                acts[k] = 0
+        ends, walk = [], []
+        for ag, a in zip(ags, acts):
+            tgt = self._target(ag, a)
+            w = self._walkable(tgt)
+            ends.append(tgt if w else (ag.x, ag.y))
+            walk.append(w)
+        final = []
+        for k, a in enumerate(acts):
+            others = ends[:k] + ends[k + 1:]
+            final.append(0 if (ends[k] in others and walk[k]) else a)
+            if final[-1] != a:
+                self._ev("collision_cancel")
+        return final
+
+    def _agent_actions_scheme1(self, idx, acts):
+        """action_scheme1.perform_agent_actions (action_scheme1.py:4-40): eight actions; walking never
+        interacts, 5 = primary interaction, 6 = pick up from a plate, 7 = execute, all on the faced cell."""
+        ags = [self.agents[i] for i in idx]
+        for ag, a in zip(ags, acts):
+            if a in _DELTA:
+                ag.orientation = a                               # :7-8
+        final = self._checked_actions(ags, acts)
+        for ag, a in zip(ags, final):
+            if a in _DELTA:                                      # resolve_walking_action :22-30
+                tgt = self._target(ag, a)
+                if self._walkable(tgt):
+                    ag.x, ag.y = tgt
+                    if ag.holding is not None:
+                        self._move_obj(ag.holding, tgt[0], tgt[1])
+                    st = self.static_at[tgt]
+                    if st.type == "Switch":
+                        st.switch_active = not st.switch_active
+                        st.pressed = True
+            elif a in (5, 6, 7):                                 # resolve_interaction :33-40
+                cell = self._target(ag, ag.orientation)
+                if cell not in self.static_at:
+                    self.error |= 64                             # get_objects_at(...)[0] -> IndexError off the grid
+                    continue
+                st = self.static_at[cell]
+                if a == 5:
+                    self._primary(ag, cell, st, self._scan(*cell))
+                elif a == 6:
+                    self._pickup_special(ag, cell)
+                else:
+                    self._execute(ag, cell, st)
+
+    def _pickup_special(self, ag, cell):
+        """resolve_interaction_pick_up_special (cooking_world.py:138-154): take the last item off the
+        one plate at the faced cell."""
+        if self._agent_on(cell):
+            return
+        dyn = self._scan(*cell)
+        if ag.holding is None and dyn:
+            plates = [d for d in dyn if d.tr.get("plate", False)]
+            if len(plates) == 1 and plates[0].content:
+                obj = plates[0].content.pop(-1)
+                ag.holding = obj
+                self._move_obj(obj, ag.x, ag.y)
+                self._ev("pickup_special")
 
     def _interact(self, ag, cell):
         """resolve_interaction (action_scheme3.py:37-43)."""

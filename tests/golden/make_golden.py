@@ -45,7 +45,7 @@ def record(cfg, seeds, T, policy, teleports=None):
         spawn = cfg.get("spawn")      # {"respawn", "despawn", "grace", "seed"}: trace n is environment n of the stream
         env = RefEnv(seed, _path(cfg["level"]), _path(cfg["meta_file"]), cfg["num_agents"], cfg["max_steps"],
                      cfg["recipes"], end_condition_all_dishes=cfg["end_all"],
-                     reward_scheme=cfg.get("reward_scheme"),
+                     reward_scheme=cfg.get("reward_scheme"), action_scheme=cfg.get("action_scheme", "scheme3"),
                      **({} if not spawn else dict(agent_respawn_rate=spawn["respawn"], agent_despawn_rate=spawn["despawn"],
                                                  grace_period=spawn["grace"],
                                                  spawn_stream=SpawnStream(spawn["seed"], n_trace, 1))))
@@ -155,6 +155,13 @@ class Heuristic:
         return np.where(rng.random(A) < self.eps, rng.integers(0, 5, size=A), act)
 
 
+def scheme1_mix(rng, t, A, prev):
+    """scheme1's eight actions, interaction-heavy, sticky"""
+    new = rng.choice([0, 1, 2, 3, 4, 5, 5, 5, 6, 7, 7], size=A)
+    keep = rng.random(A) < 0.3
+    return np.where(keep & (t > 0), prev, new)
+
+
 def scripted(seq):
     def pol(rng, t, A, prev):
         return np.array(seq[t] if t < len(seq) else [0] * A)
@@ -212,6 +219,15 @@ def main():
     save("tiny4_agents4", cfgt, record(cfgt, range(720, 726), 150, uniform), 150)
     cfgt3 = dict(cfgt, num_agents=3, recipes=["TomatoSalad", "no_recipe", "no_recipe"])
     save("tiny4_agents3", cfgt3, record(cfgt3, range(730, 734), 150, sticky), 150)
+    # scheme1 (the constructor default, cooking_env.py:27): explicit primary / pick-up-special / execute actions
+    cfgs1 = dict(cfg2, action_scheme="scheme1", max_steps=300)
+    save("scheme1_cfg2", cfgs1, record(cfgs1, range(900, 910), 300, scheme1_mix), 300)
+    cfgs1b = dict(cfg1, action_scheme="scheme1", max_steps=300)
+    save("scheme1_cfg1", cfgs1b, record(cfgs1b, range(910, 914), 300, scheme1_mix), 300)
+    cfgs1c = dict(cfgs, action_scheme="scheme1")
+    save("scheme1_switch", cfgs1c, record(cfgs1c, range(920, 924), 300, scheme1_mix), 300)
+    cfgs1d = dict(cfg4a, action_scheme="scheme1")
+    save("scheme1_open4", cfgs1d, record(cfgs1d, range(930, 934), 250, scheme1_mix), 250)
     # agent despawn / respawn (BASELINE config 5): randomness from the shared stream
     cfgsp = dict(cfg2, max_steps=10000, spawn={"respawn": 0.3, "despawn": 0.1, "grace": 2, "seed": 4242})
     save("spawn_cfg2", cfgsp, record(cfgsp, range(800, 808), 300, sticky), 300)

@@ -15,7 +15,7 @@ BOOK = ["TomatoSalad", "TomatoLettuceSalad", "CarrotBanana", "MashedCarrotBanana
 
 def _env(n=N, **kw):
     from cooking_zoo_b200 import BatchedCookingEnv
-    return BatchedCookingEnv(n, "coop_test", "example", 2, 400, BOOK[1:3], end_condition_all_dishes=True,
+    return BatchedCookingEnv(n, "coop_test", "example", 2, 400, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
                              recipe_pool=BOOK, layout_pool_size=400, layout_seed=0, **kw)
 
 

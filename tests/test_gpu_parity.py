@@ -17,7 +17,7 @@ def _make(n, cfg, **kw):
                   seed=sp["seed"])
     return BatchedCookingEnv(n, cfg["level"], cfg["meta_file"], cfg["num_agents"], cfg["max_steps"],
                              cfg["recipes"], end_condition_all_dishes=cfg["end_all"],
-                             reward_scheme=cfg["reward_scheme"], **kw)
+                             reward_scheme=cfg["reward_scheme"], action_scheme=cfg.get("action_scheme", "scheme3"), **kw)
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])

@@ -32,7 +32,7 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     from cooking_zoo_b200 import BatchedCookingEnv
     with pytest.raises(_native.NativeError):
-        BatchedCookingEnv(4, "coop_test", "example", 2, 400, ["TomatoLettuceSalad", "CarrotBanana"])
+        BatchedCookingEnv(4, "coop_test", "example", 2, 400, ["TomatoLettuceSalad", "CarrotBanana"], action_scheme="scheme3")
 
 
 def test_sampler_reproduces_golden_layouts():

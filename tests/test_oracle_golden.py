@@ -16,7 +16,7 @@ def test_oracle_replays_golden(path):
         kw = {} if not sp else dict(agent_respawn_rate=sp["respawn"], agent_despawn_rate=sp["despawn"],
                                     grace_period=sp["grace"], spawn_stream=SpawnStream(sp["seed"], n, 1))
         env = OracleEnv(layout, cfg["recipes"], cfg["max_steps"], reward_scheme=cfg["reward_scheme"],
-                        end_condition_all_dishes=cfg["end_all"], **kw)
+                        end_condition_all_dishes=cfg["end_all"], action_scheme=cfg.get("action_scheme", "scheme3"), **kw)
         ctx = f"{path} trace {n} reset"
         assert_state_equal({k: g[k][n, 0] for k in ("agents", "objs", "statics", "marks")}, env.export_state(), ctx)
         assert_obs_equal(g["obs"][n, 0], np.stack([env.observe(i) for i in range(A)]), ctx)
