@@ -228,6 +228,12 @@ def main():
     save("scheme1_switch", cfgs1c, record(cfgs1c, range(920, 924), 300, scheme1_mix), 300)
     cfgs1d = dict(cfg4a, action_scheme="scheme1")
     save("scheme1_open4", cfgs1d, record(cfgs1d, range(930, 934), 250, scheme1_mix), 250)
+    # coexistence_test: OPTIONAL objects (parsing.py:28-33,87-92) -> per-layout object sets and static variants
+    cfgco = dict(base, level="coexistence_test", num_agents=2, recipes=["TomatoLettuceSalad", "CarrotBanana"],
+                 end_all=True, max_steps=250)
+    save("coexistence_sticky", cfgco, record(cfgco, range(940, 952), 250, sticky), 250)
+    cfgco1 = dict(cfgco, action_scheme="scheme1")
+    save("coexistence_scheme1", cfgco1, record(cfgco1, range(960, 966), 250, scheme1_mix), 250)
     # agent despawn / respawn (BASELINE config 5): randomness from the shared stream
     cfgsp = dict(cfg2, max_steps=10000, spawn={"respawn": 0.3, "despawn": 0.1, "grace": 2, "seed": 4242})
     save("spawn_cfg2", cfgsp, record(cfgsp, range(800, 808), 300, sticky), 300)
