@@ -318,8 +318,26 @@ def run_gpu_arm(args):
         a1.record()
         torch.cuda.synchronize(dev)
         graphed = n3 * ring * reps / (a0.elapsed_time(a1) / 1e3)
+        # pipelined throughput mode at this size
+        env3p = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+                                  action_scheme="scheme3", device=str(dev), layout_pool_size=400, layout_seed=0,
+                                  auto_reset=True, seed=7, pipelined=True)
+        env3p.reset()
+        for s in range(20):
+            env3p.step(act3[s % ring])
+        env3p.wait()
+        torch.cuda.synchronize(dev)
+        a0.record()
+        for s in range(k3):
+            env3p.step(act3[s % ring])
+        env3p.wait()
+        a1.record()
+        torch.cuda.synchronize(dev)
+        piped = n3 * k3 / (a0.elapsed_time(a1) / 1e3)
+        env3p.close()
         cfg3 = {"workload": "cfg3: 4096 two-agent coop_test envs, 1 GPU, random actions, feature_vector obs",
                 "per_launch_env_steps_per_s": per_launch, "cuda_graph_env_steps_per_s": graphed,
+                "pipelined_env_steps_per_s": piped,
                 "note": "20 MB per step: launch/latency bound, not HBM bound"}
         env3.close()
 
