@@ -21,10 +21,12 @@
 
 #include "cz_device.cuh"
 
+#ifndef CZ_WARPS_PER_BLOCK
 #define CZ_WARPS_PER_BLOCK 4
+#endif
 #define CZ_THREADS (32 * CZ_WARPS_PER_BLOCK)
 #ifndef CZ_MIN_BLOCKS
-#define CZ_MIN_BLOCKS 7  // 28 warps/SM: registers capped at 72, shared memory at 32 KB per block
+#define CZ_MIN_BLOCKS (28 / CZ_WARPS_PER_BLOCK)  // 28 warps/SM: registers capped at 72, shared memory at 32 KB per block
 #endif
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
