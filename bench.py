@@ -142,6 +142,31 @@ def cpu_port_throughput(steps_per_worker, warm, procs=None):
     return total / max(times), procs, wall
 
 
+def cpu_port_c_throughput(n_envs=4096, steps=60, warm=5):
+    """The compiled restatement (oracle/cz_oracle.c) on all host threads: an honest compiled-CPU data point
+    beside the Python-port baseline (the reference itself is Python)."""
+    import random
+    from oracle.cz_oracle_c import CBatch
+    from cooking_zoo_b200.layout import sample_layout
+    from cooking_zoo_b200.levels import load_level_object, load_meta
+    rng = np.random.default_rng(5)
+    lay_rng = random.Random(5)
+    level, meta = load_level_object(LEVEL), load_meta(META)
+    pool = [sample_layout(level, meta, NUM_AGENTS, lay_rng) for _ in range(64)]
+    threads = os.cpu_count() or 1
+    batch = CBatch([pool[i % 64] for i in range(n_envs)],
+                   [[BOOK[int(rng.integers(8))], BOOK[int(rng.integers(8))]] for _ in range(n_envs)], 10 ** 6,
+                   threads=threads, end_condition_all_dishes=True)
+    acts = rng.integers(0, 5, size=(steps + warm, n_envs, NUM_AGENTS)).astype(np.uint8)
+    for s in range(warm):
+        batch.step(acts[s])
+    t0 = time.perf_counter()
+    for s in range(warm, warm + steps):
+        batch.step(acts[s])
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, threads
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -360,6 +385,13 @@ def run_gpu_arm(args):
             cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
                    "sample": f"{procs} processes x {args.cpu_steps} env-steps of oracle/cz_oracle.py (Python restatement "
                              f"of the Python reference), same level/recipes/action distribution, {wall:.1f} s wall"}
+            try:
+                vc, thr = cpu_port_c_throughput()
+                cpu["compiled_port"] = {"value": vc, "unit": UNIT, "threads": thr,
+                                        "sample": "4096 envs x 60 steps of oracle/cz_oracle.c (gcc -O2), step + both "
+                                                  "observations, all host threads; informational: the reference is Python"}
+            except Exception as ex:     # no compiler on the box: the Python port stands alone
+                cpu["compiled_port"] = {"unavailable": str(ex)[:120]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",

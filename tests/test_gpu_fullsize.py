@@ -135,3 +135,28 @@ def test_fullsize_determinism_and_halves():
         o2, r2, *_ = hi.step(acts[t, h:].contiguous())
     assert torch.equal(torch.cat([o1, o2]).view(torch.int64), runs[0][0].view(torch.int64))
     assert torch.equal(torch.cat([r1, r2]).view(torch.int64), runs[0][1].view(torch.int64))
+
+
+def test_fullsize_exhaustive_lockstep_against_the_compiled_oracle():
+    """every one of the 131072 environments, every step: observations (f64), rewards (f64) and flags of the CUDA
+    path against oracle/cz_oracle.c (itself pinned to the reference's golden traces by tests/test_c_oracle.py)"""
+    from oracle.cz_oracle_c import CBatch
+    env = _env()
+    rid = _recipe_ids(N, 21)
+    lids = env.default_layout_ids()
+    obs = env.reset(layout_ids=lids, recipe_ids=rid).cpu().numpy()
+    ridn = rid.numpy()
+    cpu = CBatch([env.tables.layouts[l] for l in lids], [[BOOK[int(r)] for r in row] for row in ridn], 400,
+                 end_condition_all_dishes=True)
+    assert np.array_equal(bits(cpu.observe()), bits(obs))
+    acts = _actions(40, N, 22)
+    for t in range(40):
+        o, r, te, tu, _ = env.step(acts[t])
+        co, cr, cte, ctu = cpu.step(acts[t].cpu().numpy())
+        assert np.array_equal(bits(cr), bits(r.cpu().numpy())), t
+        assert np.array_equal(cte, te.cpu().numpy()) and np.array_equal(ctu, tu.cpu().numpy()), t
+        got = o.cpu().numpy()
+        if not np.array_equal(bits(co), bits(got)):
+            bad = np.argwhere(bits(co) != bits(got))
+            raise AssertionError(f"step {t}: obs differ at {bad[:5].tolist()}")
+    assert int(env.error_flags.abs().sum()) == 0
