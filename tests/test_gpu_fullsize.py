@@ -160,3 +160,45 @@ def test_fullsize_exhaustive_lockstep_against_the_compiled_oracle():
             bad = np.argwhere(bits(co) != bits(got))
             raise AssertionError(f"step {t}: obs differ at {bad[:5].tolist()}")
     assert int(env.error_flags.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("name,level,meta,A,recipes,scheme,spawn", [
+    ("scheme1_spawn_open4", "tests/golden/levels/open4.json", "tests/golden/levels/meta4.json", 4,
+     ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"], "scheme1", (0.2, 0.15, 3)),
+    ("scheme3_spawn_coop", "coop_test", "example", 2, ["TomatoLettuceSalad", "CarrotBanana"], "scheme3", (0.3, 0.1, 2)),
+    ("scheme1_switch", "switch_test", "example", 2, ["TomatoLettuceSalad", "CarrotBanana"], "scheme1", None),
+    ("scheme3_tiny4", "tests/golden/levels/tiny4.json", "tests/golden/levels/meta4.json", 3,
+     ["TomatoSalad", "no_recipe", "no_recipe"], "scheme3", None),
+])
+def test_exhaustive_lockstep_other_paths(name, level, meta, A, recipes, scheme, spawn):
+    """16384 environments x 80 steps, every environment compared every step: scheme1, despawn/respawn from the
+    shared stream, 3/4 agents (generic and NA-specialised kernels), Switch/Block — CUDA vs oracle/cz_oracle.c"""
+    import os
+    from cooking_zoo_b200 import BatchedCookingEnv
+    from oracle.cz_oracle import SpawnStream
+    from oracle.cz_oracle_c import CBatch
+    from tests.replay import ROOT
+    n = 16384
+    lv = os.path.join(ROOT, level) if level.endswith(".json") else level
+    mt = os.path.join(ROOT, meta) if meta.endswith(".json") else meta
+    kw = {} if not spawn else dict(agent_respawn_rate=spawn[0], agent_despawn_rate=spawn[1], grace_period=spawn[2])
+    env = BatchedCookingEnv(n, lv, mt, A, 10 ** 5, recipes, end_condition_all_dishes=True, action_scheme=scheme,
+                            layout_pool_size=64, layout_seed=9, seed=31, **kw)
+    lids = env.default_layout_ids()
+    obs = env.reset(layout_ids=lids).cpu().numpy()
+    cpu = CBatch([env.tables.layouts[l] for l in lids], [recipes] * n, 10 ** 5, end_condition_all_dishes=True,
+                 action_scheme=scheme, **kw)
+    if spawn:
+        for k, e in enumerate(cpu.envs):
+            cpu.lib.czo_set_stream(e.h, 31, k, 1)
+    assert np.array_equal(bits(cpu.observe()), bits(obs))
+    g = torch.Generator(device="cpu").manual_seed(77)
+    hi = 8 if scheme == "scheme1" else 5
+    for t in range(80):
+        act = torch.randint(0, hi, (n, A), generator=g, dtype=torch.uint8)
+        o, r, te, tu, _ = env.step(act.cuda())
+        co, cr, cte, ctu = cpu.step(act.numpy())
+        assert np.array_equal(bits(cr), bits(r.cpu().numpy())), (name, t)
+        assert np.array_equal(cte, te.cpu().numpy()) and np.array_equal(ctu, tu.cpu().numpy()), (name, t)
+        assert np.array_equal(bits(co), bits(o.cpu().numpy())), (name, t)
+    assert int(env.error_flags.abs().sum()) == 0
