@@ -55,6 +55,8 @@ def record(cfg, seeds, T, policy, teleports=None):
         rng = np.random.default_rng(1000 + seed)
         tr = {"layout": env.layout(), "actions": np.zeros((T, A), np.int8),
               "teleport": -np.ones((T, A, 2), np.int8)}
+        if hasattr(policy, "raw"):
+            tr["policy"] = np.zeros((T, A), np.int8)
         st = env.export_state()
         keys = ("agents", "objs", "statics", "marks")
         hist = {k: [st[k]] for k in keys}
@@ -70,6 +72,8 @@ def record(cfg, seeds, T, policy, teleports=None):
             act = policy(rng, t, A, prev)
             prev = act
             tr["actions"][t] = act
+            if "policy" in tr:
+                tr["policy"][t] = policy.raw
             try:
                 r, te, tu, re_ = env.step(act)
             except IndexError:
@@ -114,6 +118,9 @@ def save(name, cfg, traces, T):
         "teleport": np.stack([tr["teleport"] for tr in traces]),
         "length": np.array([tr["length"] for tr in traces], np.int32),
     }
+    if "policy" in traces[0]:
+        # raw CookingAgent.step outputs on the state BEFORE step t (-1: the reference agent raised)
+        arrays["policy"] = np.stack([tr["policy"] for tr in traces])
     for k in ("agents", "objs", "statics", "marks", "obs"):
         arrays[k] = pad(k, T + 1)
     for k in ("reward", "term", "trunc", "rel"):
@@ -140,18 +147,27 @@ class Heuristic:
 
     def __init__(self, eps):
         self.eps = eps
+        self.raw = None     # the cooks' own decisions of the last call, before the epsilon mix
 
     def bind(self, env, cfg):
         from cooking_zoo.cooking_agents.cooking_agent import CookingAgent
         self.env = env
-        self.cooks = [CookingAgent(cfg["recipes"][i], f"agent-{i + 1}") for i in range(cfg["num_agents"])]
+        names = cfg.get("policy_recipes", cfg["recipes"])     # the cooks' own recipes (default: the environment's)
+        self.cooks = [CookingAgent(names[i], f"agent-{i + 1}") for i in range(cfg["num_agents"])]
 
     def __call__(self, rng, t, A, prev):
         from collections import defaultdict
         sym = defaultdict(list)
         sym.update(self.env.env.world.world_objects)
         sym["Agent"] = self.env.env.world.agents
-        act = np.array([int(c.step(sym)) for c in self.cooks])
+        raw = []
+        for c in self.cooks:
+            try:
+                raw.append(int(c.step(sym)))
+            except (IndexError, AttributeError, TypeError):
+                raw.append(-1)           # the scripted cook itself raises on this world (oracle/cz_policy.py)
+        self.raw = np.array(raw)
+        act = np.maximum(self.raw, 0)
         return np.where(rng.random(A) < self.eps, rng.integers(0, 5, size=A), act)
 
 
@@ -168,7 +184,41 @@ def scripted(seq):
     return pol
 
 
+def main_policy():
+    """SURVEY §8 f3 / BASELINE config 5: traces that also hold the scripted cook's raw decisions"""
+    base = {"level": "coop_test", "meta_file": "example", "max_steps": 400, "reward_scheme": None}
+    book = ["TomatoSalad", "TomatoLettuceSalad", "CarrotBanana", "MashedCarrotBanana",
+            "CucumberOnion", "AppleWatermelon", "TomatoLettuceOnionSalad", "no_recipe"]
+    cfg = dict(base, num_agents=2, recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, max_steps=300)
+    save("policy_cfg2", cfg, record(cfg, range(1100, 1108), 300, Heuristic(0.1)), 300)
+    for k in range(0, 8, 2):
+        c = dict(cfg, recipes=book[k:k + 2])
+        save(f"policy_book_{k}", c, record(c, range(1110 + k, 1113 + k), 300, Heuristic(0.15)), 300)
+    # the cooks follow other recipes than the environment scores
+    c = dict(cfg, recipes=["TomatoSalad", "no_recipe"], policy_recipes=["CarrotBanana", "TomatoLettuceSalad"])
+    save("policy_other", c, record(c, range(1130, 1134), 300, Heuristic(0.1)), 300)
+    # config 5: 1..4 agents in the open kitchen, despawn / respawn on, heuristic streams
+    for a in (1, 2, 3, 4):
+        c = dict(base, level="tests/golden/levels/open4.json", meta_file="tests/golden/levels/meta4.json",
+                 num_agents=a, recipes=["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "AppleWatermelon"][:a],
+                 end_all=True, max_steps=10000,
+                 spawn={"respawn": 0.2, "despawn": 0.05 if a > 1 else 0.0, "grace": 3, "seed": 500 + a})
+        save(f"policy_cfg5_a{a}", c, record(c, range(1140 + 4 * a, 1144 + 4 * a), 200, Heuristic(0.1)), 200)
+    # scheme1 environment, same cook (it only ever walks)
+    c = dict(cfg, action_scheme="scheme1")
+    save("policy_scheme1", c, record(c, range(1170, 1174), 300, Heuristic(0.1)), 300)
+    # OPTIONAL objects: worlds that lack an ingredient make the cook raise
+    c = dict(base, level="coexistence_test", num_agents=2, recipes=["TomatoLettuceSalad", "CarrotBanana"],
+             end_all=True, max_steps=250)
+    save("policy_coexistence", c, record(c, range(1180, 1190), 250, Heuristic(0.1)), 250)
+    c = dict(base, level="switch_test", num_agents=2, recipes=["TomatoLettuceSalad", "CarrotBanana"],
+             end_all=True, max_steps=300)
+    save("policy_switch", c, record(c, range(1190, 1194), 300, Heuristic(0.1)), 300)
+
+
 def main():
+    if sys.argv[1:] == ["policy"]:
+        return main_policy()
     base = {"level": "coop_test", "meta_file": "example", "max_steps": 400, "reward_scheme": None}
     # BASELINE config 1: single agent, TomatoLettuceSalad
     cfg1 = dict(base, num_agents=1, recipes=["TomatoLettuceSalad"], end_all=False)
@@ -239,6 +289,7 @@ def main():
     save("spawn_cfg2", cfgsp, record(cfgsp, range(800, 808), 300, sticky), 300)
     cfgsp4 = dict(cfg4a, max_steps=10000, spawn={"respawn": 0.2, "despawn": 0.15, "grace": 3, "seed": 77})
     save("spawn_open4", cfgsp4, record(cfgsp4, range(810, 816), 200, uniform), 200)
+    main_policy()
 
 
 if __name__ == "__main__":
