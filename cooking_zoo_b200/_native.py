@@ -34,6 +34,11 @@ class TableDesc(C.Structure):
                                      "spawn_x", "spawn_y", "spawn_n")])
 
 
+class PolicyDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("num_variants", C.c_int32), ("lists", _P), ("list_len", _P),
+                ("reach", _P), ("first_step", _P)]
+
+
 # every symbol include/cz_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "cz_abi_version": (C.c_int, []),
@@ -51,6 +56,9 @@ SIGNATURES = {
     "cz_pipeline_wait": (C.c_int, [_P, _P]),
     "cz_pipeline_reset": (C.c_int, [_P, C.c_int]),
     "cz_pipeline_current": (C.c_int, [_P]),
+    "cz_policy_create": (C.c_int, [_P, C.POINTER(PolicyDesc), C.POINTER(_P)]),
+    "cz_policy_destroy": (C.c_int, [_P]),
+    "cz_policy_act": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     "cz_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint64, C.c_int64, _P]),
 }
 
@@ -115,6 +123,18 @@ def make_desc(t):
                         ("default_recipes", np.uint8), ("spawn_x", np.uint8), ("spawn_y", np.uint8),
                         ("spawn_n", np.uint8)):
         arr = np.ascontiguousarray(getattr(t, name), dtype=dtype)
+        keep.append(arr)
+        setattr(d, name, arr.ctypes.data)
+    return d, keep
+
+
+def make_policy_desc(t, p):
+    """cz_policy_desc over the arrays of policy.compile_policy_tables (kept alive by the caller)."""
+    d = PolicyDesc()
+    d.abi_version, d.num_variants = ABI_VERSION, t.num_variants
+    keep = []
+    for name, dtype in (("lists", np.uint8), ("list_len", np.uint8), ("reach", np.uint64), ("first_step", np.uint8)):
+        arr = np.ascontiguousarray(p[name], dtype=dtype)
         keep.append(arr)
         setattr(d, name, arr.ctypes.data)
     return d, keep

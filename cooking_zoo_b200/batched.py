@@ -86,6 +86,9 @@ class BatchedCookingEnv:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def close(self):
+        if getattr(self, "_policy", None):
+            self.lib.cz_policy_destroy(self._policy)
+            self._policy = None
         if getattr(self, "_handle", None):
             self.lib.cz_tables_destroy(self._handle)
             self._handle = None
@@ -160,6 +163,43 @@ class BatchedCookingEnv:
         if self.pipelined:
             with torch.cuda.device(self.device):
                 _native.check(self.lib.cz_pipeline_wait(self._handle, self._stream()))
+
+    def heuristic_actions(self, cook_recipes=None):
+        """One decision of the reference's scripted cook (CookingAgent.step, cooking_agents/cooking_agent.py:9-17)
+        per agent of every environment, computed on the device from the current state.
+
+        cook_recipes: None (cook i follows recipe i of its environment), a list of A recipe names, or a
+        uint8 tensor [N, A] of indices into tables.recipe_names.  Returns (actions u8 [N, A], crashed u8 [N]):
+        bit i of crashed[e] is set where the reference cook would raise (its action is 0)."""
+        from .policy import compile_policy_tables
+        N, A = self.num_envs, self.num_agents
+        if getattr(self, "_policy", None) is None:
+            desc, self._policy_keep = _native.make_policy_desc(self.tables, compile_policy_tables(self.tables))
+            handle = C.c_void_p()
+            _native.check(self.lib.cz_policy_create(self._handle, C.byref(desc), C.byref(handle)))
+            self._policy = handle
+            self.cook_actions = torch.zeros((N, A), dtype=torch.uint8, device=self.device)
+            self.cook_crashed = torch.zeros((N,), dtype=torch.uint8, device=self.device)
+        rid = None
+        if cook_recipes is not None:
+            if not isinstance(cook_recipes, torch.Tensor):
+                names = list(cook_recipes)
+                if len(names) != A or any(n not in self.tables.recipe_names for n in names):
+                    raise ValueError("cook_recipes must name one recipe of tables.recipe_names per agent "
+                                     "(pass the names in recipe_pool)")
+                cook_recipes = torch.tensor([self.tables.recipe_names.index(n) for n in names],
+                                            dtype=torch.uint8).expand(N, A)
+            rid = cook_recipes.to(device=self.device, dtype=torch.uint8).contiguous()
+            if rid.shape != (N, A):
+                raise ValueError("cook_recipes must have shape [num_envs, num_agents]")
+        if self.pipelined:
+            self.wait()
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.cz_policy_act(self._policy, self.state.data_ptr(),
+                                                 rid.data_ptr() if rid is not None else None,
+                                                 self.cook_actions.data_ptr(), self.cook_crashed.data_ptr(), N,
+                                                 self._stream()))
+        return self.cook_actions, self.cook_crashed
 
     def observe(self):
         with torch.cuda.device(self.device):

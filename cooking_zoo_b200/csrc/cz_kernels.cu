@@ -1026,3 +1026,5 @@ extern "C" int cz_step_host(cz_tables* t, uint32_t* state_dev, const uint8_t* ac
   CZ_CUDA(cudaStreamSynchronize(s));
   return CZ_OK;
 }
+
+#include "cz_policy.cuh"

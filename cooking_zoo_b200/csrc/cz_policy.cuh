@@ -1,0 +1,333 @@
+// cz_policy.cuh — the reference's scripted cook as a device policy.
+//
+// CookingAgent.step (cooking_agents/cooking_agent.py:9-122) + BaseAgent helpers
+// (cooking_agents/base_agent.py:49-199) are a pure function of the world: the agent's private
+// recipe graph is re-evaluated from scratch every call (recipe.py:77-87) and its `reachable`
+// cache only memoises a property of the Floor tiles.  So the policy needs no state of its own:
+// one lane reads the environment's state column (the same shared-memory columns the step kernel
+// uses), evaluates every cook of that environment and writes actions u8 [n][A].
+//
+// Floor tiles never move, which turns both graph searches into host-built tables per static
+// variant (cooking_zoo_b200/policy.py): reach[v][a] = cells b with reachable(a, b)
+// (base_agent.py:94-126) and first_step[v][a][b] = walk_to_location's answer (base_agent.py:62-92,
+// with its left/right/down/up expansion order and first-discoverer paths).
+// Included at the end of cz_kernels.cu (one translation unit, shares cz_tables / error helpers).
+#pragma once
+
+struct CzPolicyDev {
+  const uint8_t* lists;       // [V][8][64] cells of each static kind in world_objects order
+  const uint8_t* list_len;    // [V][8]
+  const uint64_t* reach;      // [V][64]
+  const uint8_t* first_step;  // [V][64][64]
+};
+
+struct PolList {
+  const uint8_t* cells;  // static kind: cell list; nullptr for a dynamic type
+  int base, n;
+};
+
+__device__ __forceinline__ PolList pol_list(const CzDev& T, const CzPolicyDev& P, uint32_t variant, uint32_t node) {
+  PolList l;
+  l.cells = nullptr;
+  l.base = 0;
+  l.n = 0;
+  if (node & 256u) {
+    const uint32_t kind = node & 7u;
+    l.cells = P.lists + ((size_t)variant * 8 + kind) * 64;
+    l.n = __ldg(P.list_len + variant * 8 + kind);
+  } else if ((node & 255u) != 255u) {
+    l.base = __ldg(T.type_base + (node & 255u));
+    l.n = __ldg(T.type_count + (node & 255u));
+  }
+  return l;
+}
+
+// k-th entry of observation[type name]: false for an empty slot (OPTIONAL object absent, unused Bread twin)
+__device__ __forceinline__ bool pol_item(const PolList& l, const uint32_t* o, int k, uint32_t& loc, uint32_t& rec) {
+  if (l.cells) {
+    loc = __ldg(l.cells + k);
+    rec = O_PRESENT;
+    return true;
+  }
+  rec = o[(l.base + k) * OSTRIDE];
+  loc = O_XY(rec);
+  return (rec & O_PRESENT) != 0;
+}
+
+// check_node_conditions (base_agent.py:192-198): unmet conditions of a node on one object (0 or 1)
+__device__ __forceinline__ uint32_t pol_unmet(uint32_t cond, uint32_t rec) {
+  return cond == 1u ? !(rec & O_CHOP) : (cond == 2u ? !(rec & O_MASH) : 0u);
+}
+
+// BaseAgent.distance squared (monotone in the reference's sqrt; all values are small integers)
+__device__ __forceinline__ int pol_d2(uint32_t a, uint32_t b) {
+  int dx = (int)(a & 7u) - (int)(b & 7u), dy = (int)(a >> 3) - (int)(b >> 3);
+  return dx * dx + dy * dy;
+}
+
+// BaseAgent.closest (base_agent.py:128-138) over the cells of a static list that pass `keep`:
+// first strictly nearest cell reachable from `origin`; -1 if none (the reference then raises).
+__device__ __forceinline__ int pol_closest(const CzPolicyDev& P, uint32_t variant, uint32_t kind, uint32_t origin,
+                                           uint64_t keep) {
+  const uint8_t* cells = P.lists + ((size_t)variant * 8 + kind) * 64;
+  const int n = __ldg(P.list_len + variant * 8 + kind);
+  const uint64_t ok = keep & __ldg(P.reach + variant * 64 + origin);
+  int best = -1, best_d = 1 << 20;
+  for (int k = 0; k < n; ++k) {
+    const uint32_t c = __ldg(cells + k);
+    if (!(ok >> c & 1ull)) continue;
+    const int d = pol_d2(origin, c);
+    if (d < best_d) {
+      best_d = d;
+      best = (int)c;
+    }
+  }
+  return best;
+}
+
+#define POL_WALK(from, to) ((uint32_t)__ldg(P.first_step + ((size_t)variant * 64 + (from)) * 64 + (to)))
+
+// generic_sequence (base_agent.py:148-190): get food `slot` processed by an appliance of `kind`
+__device__ __forceinline__ uint32_t pol_appliance(const CzDev& T, const CzPolicyDev& P, const uint32_t* o, uint32_t variant,
+                                                  uint32_t agent_rec, uint32_t kind, uint32_t slot, bool& crash) {
+  const uint32_t me = A_XY(agent_rec);
+  const uint32_t rec = o[slot * OSTRIDE];
+  const uint32_t at = O_XY(rec);
+  const uint64_t near = __ldg(P.reach + variant * 64 + me);
+  const uint8_t* apps = P.lists + ((size_t)variant * 8 + kind) * 64;
+  const int n_apps = __ldg(P.list_len + variant * 8 + kind);
+  uint64_t app_cells = 0;
+  for (int k = 0; k < n_apps; ++k) app_cells |= 1ull << __ldg(apps + k);
+  app_cells &= near;
+  // `obj in appliance.content` for a reachable appliance: walk into it (the bump chops / blends)
+  if (O_CK(rec) == CK_STATIC && (app_cells >> at & 1ull)) return POL_WALK(me, at);
+  uint64_t filled = 0;  // static objects with content
+  for (int k = 0; k < T.D; ++k) {
+    const uint32_t r = o[k * OSTRIDE];
+    if ((r & O_PRESENT) && O_CK(r) == CK_STATIC) filled |= 1ull << O_XY(r);
+  }
+  const uint64_t empty_apps = app_cells & ~filled;
+  int target;
+  if (A_HAS(agent_rec) && A_HOLD(agent_rec) == slot) {
+    if (empty_apps) target = pol_closest(P, variant, kind, at, empty_apps);
+    else target = pol_closest(P, variant, ST_COUNTER, at, near);
+  } else if (empty_apps) {
+    if (A_HAS(agent_rec)) target = pol_closest(P, variant, ST_COUNTER, me, near & ~filled);  // put the other thing down
+    else return POL_WALK(me, at);
+  } else {
+    target = pol_closest(P, variant, kind, me, app_cells);
+  }
+  if (target < 0) {
+    crash = true;  // walk_to_location(None): tuple(None) raises (base_agent.py:63)
+    return 0;
+  }
+  return POL_WALK(me, (uint32_t)target);
+}
+
+// CookingAgent.step for cook `i` following book recipe `rid`
+__device__ __forceinline__ uint32_t pol_cook(const CzDev& T, const CzPolicyDev& P, const uint32_t* o, uint32_t variant,
+                                             uint32_t agent_rec, uint32_t rid, bool& crash) {
+  const uint32_t me = A_XY(agent_rec);
+  // own recipe graph, re-evaluated from the world (cooking_agent.py:12, recipe.py:77-87)
+  uint64_t m[CZ_MAX_NODES];
+  const int n = __ldg(T.recipe_len + rid);
+  int pick = -1;  // find_node (base_agent.py:49-53): first unmarked node from the back of node_list
+#pragma unroll
+  for (int k = CZ_MAX_NODES - 1; k >= 0; --k) {
+    m[k] = 0;
+    if (k < n) {
+      const uint32_t node = __ldg(T.recipe_nodes + rid * CZ_MAX_NODES + k);
+      const bool is_static = node & 256u, known = (node & 255u) != 255u;
+      uint64_t mask = cz_node_mask(o, node, is_static ? __ldg(T.static_masks + variant * 8 + (node & 7u)) : 0ull,
+                                   (!is_static && known) ? (int)__ldg(T.type_base + (node & 255u)) : 0,
+                                   (!is_static && known) ? (int)__ldg(T.type_count + (node & 255u)) : 0);
+      const uint32_t kids = node >> 16;
+#pragma unroll
+      for (int j = k + 1; j < CZ_MAX_NODES; ++j)
+        if (kids & (1u << j)) mask &= m[j];
+      m[k] = mask;
+      if (!mask && pick < 0) pick = k;
+    }
+  }
+  if (pick < 0) return 0;
+  const uint32_t node = __ldg(T.recipe_nodes + rid * CZ_MAX_NODES + pick);
+  const uint32_t cond = (node >> 9) & 3u, kids = node >> 16;
+  const PolList objs = pol_list(T, P, variant, node);
+  const uint64_t near = __ldg(P.reach + variant * 64 + me);
+
+  // ---- compute_condition_action (cooking_agent.py:42-55): the object closest to fulfilling the node
+  {
+    int best = -1, best_key = 1 << 20;
+    uint32_t best_rec = 0;
+    for (int k = 0; k < objs.n; ++k) {
+      uint32_t loc, rec;
+      if (!pol_item(objs, o, k, loc, rec)) continue;
+      const int key = (int)(pol_unmet(cond, rec) << 10) + pol_d2(me, loc);  // sorted by (unmet, distance), first wins
+      if (key < best_key) {
+        best_key = key;
+        best = k;
+        best_rec = rec;
+      }
+    }
+    if (best < 0) {
+      crash = true;  // sorted([])[0] (cooking_agent.py:49)
+      return 0;
+    }
+    if (pol_unmet(cond, best_rec)) {
+      // handle_condition_sequence (base_agent.py:133-146): CHOPPED -> Cutboard, MASHED -> Blender
+      const uint32_t act = pol_appliance(T, P, o, variant, agent_rec, cond == 1u ? ST_CUTBOARD : ST_BLENDER,
+                                         (uint32_t)(objs.base + best), crash);
+      if (crash) return 0;
+      if (act) return act;
+    }
+  }
+
+  // ---- compute_contains_action (cooking_agent.py:26-40)
+  // get_location_with_most_objects (:99-122)
+  int main_cell = -1, main_count = -1;
+  for (int k = 0; k < objs.n; ++k) {
+    uint32_t mloc, mrec;
+    if (!pol_item(objs, o, k, mloc, mrec) || !(near >> mloc & 1ull)) continue;
+    int count = 0;
+    for (int j = pick + 1; j < n; ++j) {
+      if (!(kids >> j & 1u)) continue;
+      const uint32_t kid = __ldg(T.recipe_nodes + rid * CZ_MAX_NODES + j);
+      const PolList kl = pol_list(T, P, variant, kid);
+      for (int q = 0; q < kl.n; ++q) {
+        uint32_t loc, rec;
+        if (!pol_item(kl, o, q, loc, rec) || !(near >> loc & 1ull)) continue;
+        if (loc == mloc && !pol_unmet((kid >> 9) & 3u, rec)) ++count;
+      }
+    }
+    if (count > main_count || (count == main_count && pol_d2(me, mloc) < pol_d2(me, (uint32_t)main_cell))) {
+      main_count = count;
+      main_cell = (int)mloc;
+    }
+  }
+  // get_best_contains_obj (:57-76): nearest object of any child type that is not already there
+  int target = -1, target_d = 1 << 20;
+  for (int j = pick + 1; j < n; ++j) {
+    if (!(kids >> j & 1u)) continue;
+    const uint32_t kid = __ldg(T.recipe_nodes + rid * CZ_MAX_NODES + j);
+    const PolList kl = pol_list(T, P, variant, kid);
+    for (int q = 0; q < kl.n; ++q) {
+      uint32_t loc, rec;
+      if (!pol_item(kl, o, q, loc, rec) || !(near >> loc & 1ull)) continue;
+      if (main_cell < 0) {
+        crash = true;  // None.location (:66)
+        return 0;
+      }
+      if ((int)loc == main_cell) continue;
+      const int d = pol_d2(me, loc);
+      if (d < target_d) {
+        target_d = d;
+        target = (int)loc;
+      }
+    }
+  }
+  if (target < 0) return 0;
+  return ((uint32_t)target == me) ? POL_WALK(me, (uint32_t)main_cell) : POL_WALK(me, (uint32_t)target);
+}
+
+#define CZ_POLICY_THREADS 128
+
+// One lane per environment; cook_recipes u8 [n][A] (book indices) or NULL = recipe i of the environment.
+__global__ void __launch_bounds__(CZ_POLICY_THREADS)
+cz_policy_kernel(const __grid_constant__ CzDev T, const __grid_constant__ CzPolicyDev P, const uint32_t* __restrict__ state,
+                 const uint8_t* __restrict__ cook_recipes, uint8_t* __restrict__ actions, uint8_t* __restrict__ crashed,
+                 int n_envs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = T.D, A = T.A;
+  uint32_t* col = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * (D + A) * OSTRIDE + lane;
+  uint32_t* ag = col + D * OSTRIDE;
+  const size_t N = (size_t)n_envs;
+  const int env = blockIdx.x * CZ_POLICY_THREADS + threadIdx.x;
+  if (env >= n_envs) return;
+  for (int s = 0; s < D + A; ++s) cz_cp_async4(col + s * OSTRIDE, state + (size_t)s * N + env);
+  const uint32_t* misc = state + (size_t)(D + A) * N;
+  const uint32_t variant = misc[(size_t)CZ_ROW_VARIANT * N + env];
+  const uint32_t rids = misc[(size_t)CZ_ROW_RECIPES * N + env];
+  cz_cp_async_wait_all();
+  uint32_t bad = 0;
+  for (int i = 0; i < A; ++i) {
+    // an environment scores at most CZ_MAX_RECIPES recipes; cook i follows recipe i unless told otherwise
+    const uint32_t rid = cook_recipes ? cook_recipes[(size_t)env * A + i] : ((rids >> (8 * i)) & 255u);
+    bool crash = false;
+    uint32_t act = 0;
+    if (rid < (uint32_t)T.B) act = pol_cook(T, P, col, variant, ag[i * OSTRIDE], rid, crash);
+    else crash = true;
+    if (crash) bad |= 1u << i;
+    actions[(size_t)env * A + i] = (uint8_t)(crash ? 0u : act);
+  }
+  if (crashed) crashed[env] = (uint8_t)bad;
+}
+
+// ---- host side ---------------------------------------------------------------------------
+struct cz_policy {
+  const cz_tables* tables;
+  CzPolicyDev dev;
+  void* allocs[4];
+  int n_allocs;
+};
+
+template <typename Tp>
+static int pol_upload(cz_policy* p, const Tp* host, size_t count, const Tp** out) {
+  void* d = nullptr;
+  CZ_CUDA(cudaMalloc(&d, count * sizeof(Tp)));
+  p->allocs[p->n_allocs++] = d;
+  CZ_CUDA(cudaMemcpy(d, host, count * sizeof(Tp), cudaMemcpyHostToDevice));
+  *out = (const Tp*)d;
+  return CZ_OK;
+}
+
+extern "C" int cz_policy_destroy(cz_policy* p) {
+  if (!p) return CZ_OK;
+  cudaSetDevice(p->tables->device);
+  for (int i = 0; i < p->n_allocs; ++i) cudaFree(p->allocs[i]);
+  delete p;
+  return CZ_OK;
+}
+
+extern "C" int cz_policy_create(const cz_tables* t, const cz_policy_desc* d, cz_policy** out) {
+  if (!t || !d || !out) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  *out = nullptr;
+  if (d->abi_version != CZ_ABI_VERSION) return cz_fail(CZ_EINVAL, "%s", "cz_policy_desc.abi_version mismatch");
+  if (d->num_variants != t->dev.V) return cz_fail(CZ_EINVAL, "%s", "cz_policy_desc.num_variants differs from the tables");
+  if (!d->lists || !d->list_len || !d->reach || !d->first_step) return cz_fail(CZ_EINVAL, "%s", "null policy table");
+  const size_t V = (size_t)d->num_variants;
+  for (size_t i = 0; i < V * 8; ++i)
+    if (d->list_len[i] > CZ_MAX_CELLS) return cz_fail(CZ_ELIMIT, "%s", "static list longer than the grid");
+  for (size_t i = 0; i < V * 64 * 64; ++i)
+    if (d->first_step[i] > 4) return cz_fail(CZ_EINVAL, "%s", "first_step holds a non-movement action");
+  CZ_CUDA(cudaSetDevice(t->device));
+  cz_policy* p = new (std::nothrow) cz_policy();
+  if (!p) return cz_fail(CZ_EINVAL, "%s", "out of host memory");
+  p->tables = t;
+  p->n_allocs = 0;
+  int rc = pol_upload(p, d->lists, V * 8 * 64, &p->dev.lists);
+  if (rc == CZ_OK) rc = pol_upload(p, d->list_len, V * 8, &p->dev.list_len);
+  if (rc == CZ_OK) rc = pol_upload(p, d->reach, V * 64, &p->dev.reach);
+  if (rc == CZ_OK) rc = pol_upload(p, d->first_step, V * 64 * 64, &p->dev.first_step);
+  if (rc != CZ_OK) {
+    cz_policy_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return CZ_OK;
+}
+
+extern "C" int cz_policy_act(const cz_policy* p, const uint32_t* state, const uint8_t* cook_recipes, uint8_t* actions,
+                             uint8_t* crashed, int n_envs, void* stream) {
+  if (!p || !state || !actions) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (n_envs < 0) return cz_fail(CZ_EINVAL, "%s", "negative n_envs");
+  if (n_envs == 0) return CZ_OK;
+  const CzDev& T = p->tables->dev;
+  const size_t smem = (size_t)(CZ_POLICY_THREADS / 32) * (T.D + T.A) * OSTRIDE * 4;
+  const int blocks = (n_envs + CZ_POLICY_THREADS - 1) / CZ_POLICY_THREADS;
+  cz_policy_kernel<<<blocks, CZ_POLICY_THREADS, smem, (cudaStream_t)stream>>>(T, p->dev, state, cook_recipes, actions, crashed,
+                                                                              n_envs);
+  g_launches.fetch_add(1);
+  CZ_CUDA(cudaGetLastError());
+  return CZ_OK;
+}

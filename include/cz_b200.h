@@ -197,6 +197,34 @@ int cz_pipeline_wait(cz_tables* t, void* stream);
 int cz_pipeline_reset(cz_tables* t, int current_half);
 int cz_pipeline_current(const cz_tables* t);
 
+/* ---- Scripted cook as a device policy -----------------------------------
+ * Replaces CookingAgent.step (cooking_agents/cooking_agent.py:9-122) + BaseAgent.walk_to_location /
+ * reachable / closest / generic_sequence (cooking_agents/base_agent.py:49-199), which the reference
+ * evaluates per agent on a deep-copied symbolic observation.  The decision is a pure function of the
+ * world, so the policy keeps no state; its two graph searches over the Floor tiles are host-built
+ * tables per static variant (cooking_zoo_b200/policy.py). */
+typedef struct cz_policy_desc {
+  int abi_version;
+  int num_variants;           /* must equal cz_table_desc.num_variants                          */
+  const uint8_t* lists;       /* [V][8 static kinds][64] cells of each static kind (Floor, Counter,
+                                 Cutboard, ...) in world_objects list order                      */
+  const uint8_t* list_len;    /* [V][8]                                                          */
+  const uint64_t* reach;      /* [V][64] bit b of reach[a]: BaseAgent.reachable(a, b)            */
+  const uint8_t* first_step;  /* [V][64 from][64 to] action 0..4 of BaseAgent.walk_to_location   */
+} cz_policy_desc;
+
+typedef struct cz_policy cz_policy;
+int cz_policy_create(const cz_tables* t, const cz_policy_desc* desc, cz_policy** out);
+int cz_policy_destroy(cz_policy* p);
+
+/* One CookingAgent.step per agent of every environment, on the CURRENT state.
+ * cook_recipes u8 [n][A]: recipe-book index each cook follows, or NULL (cook i follows recipe i of
+ * its environment).  actions u8 [n][A] (0..4: the cook only ever walks).  crashed u8 [n] (may be
+ * NULL): bit i set where the reference cook would raise (no object of the wanted type, nothing
+ * reachable; oracle/cz_policy.py lists the sites) — that agent's action is 0. */
+int cz_policy_act(const cz_policy* p, const uint32_t* state, const uint8_t* cook_recipes, uint8_t* actions,
+                  uint8_t* crashed, int n_envs, void* stream);
+
 /* Number of kernels launched by this library since load (the bench's gpu_launches claim). */
 uint64_t cz_launch_count(void);
 

@@ -1,0 +1,149 @@
+"""GPU: the device policy (cz_policy_act) against the recorded decisions of the reference's
+CookingAgent (tests/golden/policy_*.npz) and against the policy oracle on live batches."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.cz_oracle import OracleEnv, SpawnStream
+from oracle import cz_policy
+from tests.replay import GOLDEN_DIR, ROOT, load_golden
+from tests.test_gpu_parity import _make
+
+pytestmark = pytest.mark.gpu
+BOOK = ["TomatoSalad", "TomatoLettuceSalad", "CarrotBanana", "MashedCarrotBanana",
+        "CucumberOnion", "AppleWatermelon", "TomatoLettuceOnionSalad", "no_recipe"]
+
+
+def policy_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "policy_*.npz")))
+
+
+def _decode(actions, crashed, A):
+    """device (actions, crashed bits) -> the recorder's convention: -1 where the cook raised"""
+    a = actions.cpu().numpy().astype(np.int64)
+    c = crashed.cpu().numpy()
+    for i in range(A):
+        bad = (c >> i) & 1 == 1
+        assert (a[bad, i] == 0).all()
+        a[bad, i] = -1
+    return a
+
+
+@pytest.mark.parametrize("path", policy_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_device_policy_replays_recorded_cook(path):
+    g = load_golden(path)
+    cfg = g["config"]
+    n, A = len(g["layouts"]), cfg["num_agents"]
+    names = cfg.get("policy_recipes", cfg["recipes"])[:A]
+    env = _make(n, cfg, layouts=g["layouts"], recipe_pool=list(dict.fromkeys(list(cfg["recipes"]) + list(names))))
+    env.reset(layout_ids=np.arange(n))
+    explicit = names != cfg["recipes"][:A]
+    for t in range(g["actions"].shape[1]):
+        live = [k for k in range(n) if t < g["length"][k]]
+        if not live:
+            break
+        got = _decode(*env.heuristic_actions(names if (explicit or t % 2) else None), A)
+        for k in live:
+            assert got[k].tolist() == g["policy"][k, t].tolist(), f"{path} trace {k} step {t}"
+        env.step(torch.from_numpy(g["actions"][:, t].astype(np.uint8)))
+
+
+def _live_lockstep(cfg, n_envs, check, steps, seed, pool, eps=0.15, per_env_cooks=False, **kw):
+    A = cfg["num_agents"]
+    env = _make(n_envs, cfg, layout_pool_size=48, layout_seed=seed, recipe_pool=pool, **kw)
+    rng = np.random.default_rng(seed)
+    lids = rng.integers(0, env.tables.num_layouts, size=n_envs).astype(np.int32)
+    R = len(cfg["recipes"])
+    rids = rng.integers(0, len(pool), size=(n_envs, R)).astype(np.uint8)
+    cooks = rng.integers(0, len(pool), size=(n_envs, A)).astype(np.uint8) if per_env_cooks else rids[:, :A]
+    env.reset(layout_ids=lids, recipe_ids=rids)
+    names = env.tables.recipe_names
+    picks = np.linspace(0, n_envs - 1, check).astype(int)
+    sp = cfg.get("spawn")
+    oracles = {}
+    for k in picks:
+        okw = {} if not sp else dict(agent_respawn_rate=sp["respawn"], agent_despawn_rate=sp["despawn"],
+                                     grace_period=sp["grace"], spawn_stream=SpawnStream(sp["seed"], int(k), 1))
+        oracles[int(k)] = OracleEnv(env.tables.layouts[lids[k]], [names[r] for r in rids[k]], cfg["max_steps"],
+                                    end_condition_all_dishes=cfg["end_all"],
+                                    action_scheme=cfg.get("action_scheme", "scheme3"), **okw)
+    cook_t = torch.from_numpy(cooks).cuda() if per_env_cooks else None
+    seen = set()
+    alive = set(oracles)
+    for t in range(steps):
+        got = _decode(*env.heuristic_actions(cook_t), A)
+        for k in sorted(alive):
+            want = cz_policy.heuristic_actions(oracles[k], [names[r] for r in cooks[k]])
+            assert got[k].tolist() == want, f"env {k} step {t}: oracle {want}, device {got[k].tolist()}"
+            seen.update(want)
+        act = np.where(rng.random((n_envs, A)) < eps, rng.integers(0, 5, size=(n_envs, A)), np.maximum(got, 0)).astype(np.uint8)
+        _, _, term, trunc, _ = env.step(torch.from_numpy(act))
+        term, trunc = term.cpu().numpy(), trunc.cpu().numpy()
+        for k in sorted(alive):
+            _, te, tu, _ = oracles[k].step(act[k])
+            assert [int(v) for v in te] == list(term[k]), f"env {k} step {t}"
+            if any(te) or oracles[k].t >= cfg["max_steps"]:
+                alive.discard(k)
+        if not alive:
+            break
+    return seen
+
+
+def test_device_policy_vs_oracle_coop_book():
+    """2048 coop_test envs, per-env recipe pairs from the whole book, cooks follow their env's recipes"""
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=250,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    seen = _live_lockstep(cfg, 2048, 96, 250, 21, BOOK)
+    assert {0, 1, 2, 3, 4} <= seen
+
+
+def test_device_policy_vs_oracle_per_env_cooks_open4_spawn():
+    """BASELINE config 5 shape: 4 agents, despawn / respawn, every cook with its own recipe (tensor argument)"""
+    cfg = dict(level=os.path.join(ROOT, "tests/golden/levels/open4.json"),
+               meta_file=os.path.join(ROOT, "tests/golden/levels/meta4.json"), num_agents=4, max_steps=200,
+               recipes=["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"], end_all=True,
+               reward_scheme=None, spawn={"respawn": 0.2, "despawn": 0.05, "grace": 3, "seed": 91})
+    seen = _live_lockstep(cfg, 1024, 64, 200, 33, BOOK, per_env_cooks=True)
+    assert {-1, 0, 1, 2, 3, 4} <= seen
+
+
+def test_device_policy_vs_oracle_switch_and_optional_levels():
+    for level, seed in (("switch_test", 41), ("coexistence_test", 43)):
+        cfg = dict(level=level, meta_file="example", num_agents=2, max_steps=150,
+                   recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+        _live_lockstep(cfg, 512, 48, 150, seed, BOOK[:3] + ["no_recipe"], per_env_cooks=True)
+
+
+def test_device_cooks_finish_their_dishes_at_scale():
+    """closed loop, no host in between: 16384 single-cook kitchens driven only by the device policy deliver
+    TomatoLettuceSalad (terminated) well inside the step budget"""
+    cfg = dict(level="coop_test", meta_file="example", num_agents=1, max_steps=400,
+               recipes=["TomatoLettuceSalad"], end_all=False, reward_scheme=None)
+    env = _make(16384, cfg, layout_pool_size=64)
+    env.reset()
+    done = torch.zeros(16384, dtype=torch.bool, device="cuda")
+    for t in range(200):
+        act, crashed = env.heuristic_actions()
+        assert int(crashed.sum()) == 0
+        _, _, term, _, _ = env.step(act)
+        done |= term[:, 0].bool()
+    assert float(done.float().mean()) > 0.95
+
+
+def test_policy_argument_errors():
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=50,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    env = _make(8, cfg)
+    env.reset()
+    with pytest.raises(ValueError):
+        env.heuristic_actions(["TomatoLettuceSalad"])                    # one name per agent
+    with pytest.raises(ValueError):
+        env.heuristic_actions(["TomatoLettuceSalad", "AppleWatermelon"])   # not in the compiled recipe pool
+    with pytest.raises(ValueError):
+        env.heuristic_actions(torch.zeros((8, 3), dtype=torch.uint8))
+    # a book index outside the pool: the cook cannot exist -> reported as crashed, action 0
+    act, crashed = env.heuristic_actions(torch.full((8, 2), 200, dtype=torch.uint8))
+    assert crashed.tolist() == [3] * 8 and int(act.sum()) == 0

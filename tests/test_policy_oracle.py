@@ -46,3 +46,42 @@ def test_policy_goldens_cover_crashes_and_all_moves():
     for path in policy_files():
         seen.update(np.unique(load_golden(path)["policy"]).tolist())
     assert seen == {-1, 0, 1, 2, 3, 4}
+
+
+@pytest.mark.parametrize("level,meta,agents", [("coop_test", "example", 2), ("switch_test", "example", 2),
+                                               ("coexistence_test", "example", 2),
+                                               ("tests/golden/levels/open4.json", "tests/golden/levels/meta4.json", 4),
+                                               ("tests/golden/levels/tiny4.json", "tests/golden/levels/meta4.json", 4)])
+def test_policy_tables_match_the_queue_level_searches(level, meta, agents):
+    """reach / first_step / lists of cooking_zoo_b200/policy.py == oracle.cz_policy.reachable / walk on every cell pair"""
+    from cooking_zoo_b200.tables import compile_tables, ROW_VARIANT
+    from cooking_zoo_b200.policy import compile_policy_tables
+    from tests.replay import ROOT
+    path = lambda p: os.path.join(ROOT, p) if p.endswith(".json") else p
+    t = compile_tables(path(level), path(meta), agents, 100, ["TomatoSalad"] * agents, layout_pool_size=24, layout_seed=5)
+    p = compile_policy_tables(t)
+    col = t.num_dyn_slots + t.num_agents + ROW_VARIANT
+    done = set()
+    for li, lay in enumerate(t.layouts):
+        v = int(t.pool[li, col])
+        if v in done:
+            continue
+        done.add(v)
+        env = OracleEnv(lay, ["TomatoSalad"] * agents, 100)
+        floor = cz_policy._floor(env)
+        for name, objs in env.by_type.items():
+            from cooking_zoo_b200.entities import entity
+            et = entity(name)
+            if et.kind == "static":
+                n = int(p["list_len"][v, et.static_code])
+                assert p["lists"][v, et.static_code, :n].tolist() == [o.y * 8 + o.x for o in objs]
+        cells = [(x, y) for y in range(t.height) for x in range(t.width)]
+        for a in cells:
+            ia = a[1] * 8 + a[0]
+            for b in cells:
+                ib = b[1] * 8 + b[0]
+                r = cz_policy.reachable(env, a, b, floor)
+                assert bool(int(p["reach"][v, ia]) >> ib & 1) == r, (v, a, b)
+                assert int(p["first_step"][v, ia, ib]) == cz_policy.walk(env, a, b, floor), (v, a, b)
+                assert r == cz_policy.reachable(env, b, a, floor)          # the cook's cache assumes symmetry
+    assert len(done) == t.num_variants
