@@ -147,3 +147,59 @@ def test_policy_argument_errors():
     # a book index outside the pool: the cook cannot exist -> reported as crashed, action 0
     act, crashed = env.heuristic_actions(torch.full((8, 2), 200, dtype=torch.uint8))
     assert crashed.tolist() == [3] * 8 and int(act.sum()) == 0
+
+
+def test_cfg5_mixed_agent_counts_heuristic_streams_spawning_per_env_recipes():
+    """BASELINE config 5 end to end on the device: 1-4 agents per environment, actions from the device cook
+    (epsilon-mixed), despawn / respawn from the shared stream, a recipe assignment per environment; sampled
+    environments in lockstep with the step oracle and the policy oracle."""
+    from cooking_zoo_b200 import MixedAgentCookingEnv
+    level = os.path.join(ROOT, "tests/golden/levels/open4.json")
+    meta = os.path.join(ROOT, "tests/golden/levels/meta4.json")
+    rng = np.random.default_rng(77)
+    N, steps, seed = 1500, 120, 1234
+    counts = rng.integers(1, 5, size=N)
+    recipes = ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"]
+    env = MixedAgentCookingEnv(counts, level, meta, 10000, recipes, end_condition_all_dishes=True,
+                               action_scheme="scheme3", recipe_pool=BOOK, layout_pool_size=40, layout_seed=3,
+                               agent_respawn_rate=0.2, agent_despawn_rate=0.05, grace_period=3, seed=seed)
+    assert sorted(env.groups) == [1, 2, 3, 4]
+    lids = rng.integers(0, 40, size=N).astype(np.int32)
+    rids = rng.integers(0, len(BOOK), size=(N, 4)).astype(np.uint8)
+    obs = env.reset(layout_ids=lids, recipe_ids=rids)
+    picks = rng.choice(N, size=60, replace=False)
+    pos = {a: {int(g): j for j, g in enumerate(env.index[a].cpu().numpy())} for a in env.groups}
+    oracles = {}
+    for k in picks:
+        a = int(counts[k])
+        names = env.groups[a].tables.recipe_names
+        oracles[int(k)] = OracleEnv(env.groups[a].tables.layouts[lids[k]], [names[r] for r in rids[k, :a]], 10000,
+                                    end_condition_all_dishes=True, agent_respawn_rate=0.2, agent_despawn_rate=0.05,
+                                    grace_period=3, spawn_stream=SpawnStream(seed, int(env.stream_ids[k]), 1))
+    alive = set(oracles)
+    for t in range(steps):
+        act, crashed = env.heuristic_actions()
+        act = act.cpu().numpy().astype(np.int64)
+        crashed = crashed.cpu().numpy()
+        for k in sorted(alive):
+            a = int(counts[k])
+            names = env.groups[a].tables.recipe_names
+            want = cz_policy.heuristic_actions(oracles[k], [names[r] for r in rids[k, :a]])
+            got = [(-1 if crashed[k] >> i & 1 else int(act[k, i])) for i in range(a)]
+            assert got == want, f"env {k} ({a} agents) step {t}"
+            assert (act[k, a:] == 0).all()
+        mix = np.where(rng.random((N, 4)) < 0.1, rng.integers(0, 5, size=(N, 4)), act).astype(np.uint8)
+        obs, rew, term, trunc = env.step(torch.from_numpy(mix))
+        rew, term, trunc = rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+        obs = {a: o.cpu().numpy() for a, o in obs.items()}
+        for k in sorted(alive):
+            a = int(counts[k])
+            r, te, tu, _ = oracles[k].step(mix[k, :a])
+            ctx = f"env {k} ({a} agents) step {t}"
+            assert np.array_equal(np.asarray(r, np.float64).view(np.uint64), rew[k, :a].view(np.uint64)), ctx
+            assert [int(v) for v in te] == list(term[k, :a]) and [int(v) for v in tu] == list(trunc[k, :a]), ctx
+            want = np.stack([oracles[k].observe(i) for i in range(a)])
+            assert np.array_equal(want.view(np.uint64), obs[a][pos[a][k]].view(np.uint64)), ctx
+            if any(te):
+                alive.discard(k)
+    assert len(alive) > 20
