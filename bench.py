@@ -366,6 +366,38 @@ def run_gpu_arm(args):
                 "note": "20 MB per step: launch/latency bound, not HBM bound"}
         env3.close()
 
+    # ---- closed loop with the device policy: CookingAgent decisions + step, no host in between
+    cook = None
+    if rank == 0 and world == 1 and not args.no_cfg3:
+        env.wait()
+        torch.cuda.synchronize(dev)
+        envc = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+                                 action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size=400,
+                                 layout_seed=0, auto_reset=True, seed=2026)
+        envc.reset(recipe_ids=recipe_ids)
+        for _ in range(5):
+            envc.step(envc.heuristic_actions()[0])
+        torch.cuda.synchronize(dev)
+        kc = 200
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(kc):
+            envc.step(envc.heuristic_actions()[0])
+        c1.record()
+        torch.cuda.synchronize(dev)
+        loop_ms = c0.elapsed_time(c1) / kc
+        c0.record()
+        for _ in range(kc):
+            envc.heuristic_actions()
+        c1.record()
+        torch.cuda.synchronize(dev)
+        pol_ms = c0.elapsed_time(c1) / kc
+        cook = {"workload": f"{N} two-agent envs, every action from cz_policy_act (the scripted cook), in-place step",
+                "closed_loop_env_steps_per_s": N / (loop_ms / 1e3), "policy_ms_per_launch": pol_ms,
+                "policy_decisions_per_s": N * A / (pol_ms / 1e3),
+                "recipes_done_now": float(envc.info()["recipe_done"].sum())}
+        envc.close()
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -405,7 +437,7 @@ def run_gpu_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step)",
                         "host_link_gbs": (h2d + d2h) * e2e_value / N / 1e9 / world},
-                "gpu_launches": int(launches), "clocks": clocks, "cfg3": cfg3,
+                "gpu_launches": int(launches), "clocks": clocks, "cfg3": cfg3, "device_policy": cook,
                 "mode": args.mode,
                 "sync_step": {"value": sync_value, "ms_per_step": ms_sync / args.steps,
                               "frac": N * bytes_per_env_step / (ms_sync / args.steps / 1e3) / 1e9 / peak,
