@@ -204,8 +204,10 @@ __device__ __forceinline__ uint32_t cz_plate_count_clear_free(const CzDev& T, En
 // mode: 0 = scheme3 (execute iff an action object holds something unfinished, else primary),
 //       5 / 6 / 7 = scheme1's INTERACT_PRIMARY / INTERACT_PICK_UP_SPECIAL / EXECUTE_ACTION (action_scheme1.py:33-40).
 // Returns the plate whose content lost an item (its free flags are refreshed at the end of the step) or 0xFF.
+// `stale` is set when the static container at `cell` keeps items whose free flags must be refreshed in
+// progress_world (it lost one of several items, or a chopped Bread spawned its twin on top).
 template <bool FAST>
-__device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int i, uint32_t cell, uint32_t mode) {
+__device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int i, uint32_t cell, uint32_t mode, bool& stale) {
   const uint32_t agent_rec = e.ag[i * OSTRIDE];
   const SmemTabs* st = e.st;
   const uint32_t g = TAB_GRID(e.variant, cell);
@@ -272,6 +274,7 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
             e.err |= CZ_ERR_OBS_OVERFLOW;  // the reference's obs vector would grow (cooking_env.py:371)
           } else {
             e.o[slot * OSTRIDE] = O_WITH_CONT(cell | O_PRESENT | O_CHOP | O_FREE, CK_STATIC, 0, n_content);
+            stale = true;
           }
         }
         return 0xFFu;
@@ -300,7 +303,10 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
     int gs = first_free >= 0 ? first_free : last;
     uint32_t r = e.o[gs * OSTRIDE];
     if (O_CK(r) != CK_STATIC) return 0xFFu;  // `object_to_grab in static_object.content`
-    cz_remove_from_static(T, e, cell, O_POS(r));
+    if (n_content > 1) {  // a lone item leaves nothing behind to shift or to refresh
+      cz_remove_from_static(T, e, cell, O_POS(r));
+      stale = true;
+    }
     e.o[gs * OSTRIDE] = O_WITH_CONT(r, CK_HELD, i, 0);
     cz_move_obj<FAST>(T, e, gs, axy);  // Agent.grab (world_objects.py:786-788)
     e.ag[i * OSTRIDE] = (agent_rec & ~(0x3Fu << 9)) | (1u << 9) | ((uint32_t)gs << 10);
@@ -329,8 +335,14 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
       uint32_t n = cz_plate_count_clear_free(T, e, h, false);
       if (n < 64) {
         cz_plate_count_clear_free(T, e, h, true);
-        if (O_CK(pr) == CK_STATIC) cz_remove_from_static(T, e, cell, O_POS(pr));
-        else e.err |= CZ_ERR_REMOVE;
+        if (O_CK(pr) == CK_STATIC) {
+          if (n_content > 1) {
+            cz_remove_from_static(T, e, cell, O_POS(pr));
+            stale = true;
+          }
+        } else {
+          e.err |= CZ_ERR_REMOVE;
+        }
         e.o[last * OSTRIDE] = O_WITH_XY(O_WITH_CONT(pr, CK_PLATE, h, n) | O_FREE, axy);
       }
     }
@@ -490,8 +502,9 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
         const int fx = (int)(rec & 7u) + (o == 2) - (o == 1), fy = (int)((rec >> 3) & 7u) + (o == 3) - (o == 4);
         if (fx < 0 || fy < 0 || fx > T.W - 1 || fy > T.H - 1) { e.err |= CZ_ERR_OFFGRID; continue; }
         const uint32_t cell = (uint32_t)(fx | fy << 3);
-        const uint32_t p = cz_interact<FAST>(T, e, i, cell, ai);
-        dirty = (dirty & ~(0xFFu << (8 * i))) | (cell << (8 * i));
+        bool stale = false;
+        const uint32_t p = cz_interact<FAST>(T, e, i, cell, ai, stale);
+        if (stale) dirty = (dirty & ~(0xFFu << (8 * i))) | (cell << (8 * i));
         dirty_plate = (dirty_plate & ~(0xFFu << (8 * i))) | (p << (8 * i));
         continue;
       }
@@ -507,8 +520,9 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
         pressed |= 1u << (g >> 4);
       }
     } else if (ai && !scheme1) {
-      cz_interact<FAST>(T, e, i, tgt, 0u);
-      dirty = (dirty & ~(0xFFu << (8 * i))) | (tgt << (8 * i));
+      bool stale = false;
+      cz_interact<FAST>(T, e, i, tgt, 0u, stale);
+      if (stale) dirty = (dirty & ~(0xFFu << (8 * i))) | (tgt << (8 * i));
     }
   }
 
