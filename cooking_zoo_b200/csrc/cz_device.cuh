@@ -34,6 +34,7 @@ struct CzDev {
   const uint32_t* comp_slots;
   const double* obs_table;
   const uint32_t* recipe_nodes;
+  const uint32_t* recipe_spans;  // [B][8] per node: first slot | slots << 8 | required record bits << 16 (cz_tables_create)
   const uint8_t* recipe_len;
   const uint32_t* pool;
   const uint8_t* default_recipes;
@@ -52,6 +53,7 @@ struct CzDev {
 struct SmemTabs {
   uint64_t static_masks[CZ_SV][8];
   uint32_t recipe_nodes[CZ_SB][CZ_MAX_NODES];
+  uint32_t recipe_spans[CZ_SB][CZ_MAX_NODES];
   uint8_t grid[CZ_SV][64];
   uint8_t scan_order[CZ_SV][CZ_MAX_DYN];
   uint8_t special_cells[CZ_SV][4 * CZ_MAX_SPECIAL];
@@ -79,8 +81,14 @@ enum { FV_NONE = 0, FV_ONE, FV_CHOP, FV_CHOPBLEND, FV_AGENT, FV_SWITCH, FV_BLOCK
 #define O_CK(r) (((r) >> 10) & 3u)
 #define O_CID(r) (((r) >> 12) & 31u)
 #define O_POS(r) (((r) >> 17) & 63u)
+#define O_PCOUNT(r) (((r) >> 23) & 127u) /* Plate records: items on the plate (kept by the merge / pick-up-special paths) */
+#define O_PCOUNT_ONE (1u << 23)
 #define O_WITH_XY(r, xy) (((r) & ~63u) | (xy))
-#define O_WITH_CONT(r, k, id, pos) (((r) & 0x3FFu) | ((uint32_t)(k) << 10) | ((uint32_t)(id) << 12) | ((uint32_t)(pos) << 17))
+#define O_WITH_CONT(r, k, id, pos) (((r) & 0xFF8003FFu) | ((uint32_t)(k) << 10) | ((uint32_t)(id) << 12) | ((uint32_t)(pos) << 17))
+// one masked compare instead of three field tests (hot inner loops of the dynamics)
+#define O_AT(r, cell) (((r) & 0x7Fu) == ((cell) | O_PRESENT))                             /* present, at cell */
+#define O_IN_STATIC_AT(r, cell) (((r) & 0xC7Fu) == ((cell) | O_PRESENT | (1u << 10)))      /* ... as content of the static object */
+#define O_ON_PLATE(r, p) (((r) & 0x1FC40u) == (O_PRESENT | (2u << 10) | ((uint32_t)(p) << 12))) /* present, content of plate p */
 #define CK_HELD 0u
 #define CK_STATIC 1u
 #define CK_PLATE 2u
@@ -110,6 +118,7 @@ enum { FV_NONE = 0, FV_ONE, FV_CHOP, FV_CHOPBLEND, FV_AGENT, FV_SWITCH, FV_BLOCK
 #define TAB_SCELL(v, i) (FAST ? (uint32_t)st->static_cells[v][i] : (uint32_t)__ldg(T.static_cells + (v) * T.S + (i)))
 #define TAB_SMASK(v, k) (FAST ? st->static_masks[v][k] : __ldg(T.static_masks + (v) * 8 + (k)))
 #define TAB_RNODE(b, k) (FAST ? st->recipe_nodes[b][k] : __ldg(T.recipe_nodes + (b) * CZ_MAX_NODES + (k)))
+#define TAB_RSPAN(b, k) (FAST ? st->recipe_spans[b][k] : __ldg(T.recipe_spans + (b) * CZ_MAX_NODES + (k)))
 #define TAB_RLEN(b) (FAST ? (uint32_t)st->recipe_len[b] : (uint32_t)__ldg(T.recipe_len + (b)))
 #define TAB_TF(s) (FAST ? (uint32_t)st->slot_tf[s] : (uint32_t)__ldg(T.type_flags + __ldg(T.slot_type + (s))))
 #define TAB_STYPE(s) (FAST ? (uint32_t)st->slot_type[s] : (uint32_t)__ldg(T.slot_type + (s)))
@@ -167,12 +176,13 @@ __device__ __forceinline__ bool cz_agent_on(const CzDev& T, const EnvRegs& e, ui
 // (abstract_classes.py:21-22, world_objects.py:393-396).
 template <bool FAST>
 __device__ __forceinline__ void cz_move_obj(const CzDev& T, EnvRegs& e, uint32_t s, uint32_t xy) {
-  e.o[s * OSTRIDE] = O_WITH_XY(e.o[s * OSTRIDE], xy);
+  const uint32_t rec = e.o[s * OSTRIDE];
+  e.o[s * OSTRIDE] = O_WITH_XY(rec, xy);
   const SmemTabs* st = e.st;
-  if (TAB_TF(s) & TF_PLATE) {
+  if ((TAB_TF(s) & TF_PLATE) && O_PCOUNT(rec)) {  // an empty plate (the common case) has nothing to carry along
     for (int k = 0; k < T.D; ++k) {
       uint32_t r = e.o[k * OSTRIDE];
-      if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == s) e.o[k * OSTRIDE] = O_WITH_XY(r, xy);
+      if (O_ON_PLATE(r, s)) e.o[k * OSTRIDE] = O_WITH_XY(r, xy);
     }
   }
 }
@@ -181,22 +191,17 @@ __device__ __forceinline__ void cz_move_obj(const CzDev& T, EnvRegs& e, uint32_t
 __device__ __forceinline__ void cz_remove_from_static(const CzDev& T, EnvRegs& e, uint32_t cell, uint32_t pos) {
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
-    if ((r & O_PRESENT) && O_CK(r) == CK_STATIC && O_XY(r) == cell && O_POS(r) > pos) e.o[k * OSTRIDE] = r - (1u << 17);
+    if (O_IN_STATIC_AT(r, cell) && O_POS(r) > pos) e.o[k * OSTRIDE] = r - (1u << 17);
   }
 }
 
 // add_content's `for c in content: c.free = False; content[-1].free = True` for a plate
-// (world_objects.py:398-406): clear the flag of everything already on plate `p`, count it.
-__device__ __forceinline__ uint32_t cz_plate_count_clear_free(const CzDev& T, EnvRegs& e, uint32_t p, bool clear) {
-  uint32_t n = 0;
+// (world_objects.py:398-406): clear the flag of everything already on plate `p`.
+__device__ __forceinline__ void cz_plate_clear_free(const CzDev& T, EnvRegs& e, uint32_t p) {
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
-    if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == p) {
-      ++n;
-      if (clear) e.o[k * OSTRIDE] = r & ~O_FREE;
-    }
+    if (O_ON_PLATE(r, p)) e.o[k * OSTRIDE] = r & ~O_FREE;
   }
-  return n;
 }
 
 // resolve_interaction -> resolve_execute_action | resolve_primary_interaction -> attempt_merge
@@ -218,7 +223,7 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
   for (int k = 0; k < T.D; ++k) {
     int s = TAB_SCAN(e.variant, k);
     uint32_t r = e.o[s * OSTRIDE];
-    if (!(r & O_PRESENT) || O_XY(r) != cell) continue;
+    if (!O_AT(r, cell)) continue;
     ++n_dyn;
     last = s;
     if (first_free < 0 && (r & O_FREE)) first_free = s;
@@ -238,9 +243,10 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
     int top = -1, ts = -1;
     for (int k = 0; k < T.D; ++k) {
       uint32_t r = e.o[k * OSTRIDE];
-      if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == (uint32_t)plate && (int)O_POS(r) > top) { top = O_POS(r); ts = k; }
+      if (O_ON_PLATE(r, plate) && (int)O_POS(r) > top) { top = O_POS(r); ts = k; }
     }
     if (ts < 0) return 0xFFu;  // content.pop(-1) on an empty plate: IndexError, swallowed
+    e.o[plate * OSTRIDE] -= O_PCOUNT_ONE;
     e.o[ts * OSTRIDE] = O_WITH_XY(O_WITH_CONT(e.o[ts * OSTRIDE], CK_HELD, i, 0), A_XY(agent_rec));
     e.ag[i * OSTRIDE] = (agent_rec & ~(0x3Fu << 9)) | (1u << 9) | ((uint32_t)ts << 10);
     return (uint32_t)plate;
@@ -255,7 +261,7 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
         int s = -1;
         for (int k = 0; k < T.D; ++k) {
           uint32_t r = e.o[k * OSTRIDE];
-          if ((r & O_PRESENT) && O_CK(r) == CK_STATIC && O_XY(r) == cell && O_POS(r) == (uint32_t)p) s = k;
+          if (O_IN_STATIC_AT(r, cell) && O_POS(r) == (uint32_t)p) s = k;
         }
         if (s < 0) break;
         uint32_t r = e.o[s * OSTRIDE];
@@ -321,9 +327,10 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
   if (n_plates == 1) {
     // Plate.accepts: Food and done and room (world_objects.py:408-409)
     if ((htf & (TF_CHOP | TF_BLEND)) && (hr & (O_CHOP | O_MASH))) {
-      uint32_t n = cz_plate_count_clear_free(T, e, plate, false);
+      const uint32_t n = O_PCOUNT(e.o[plate * OSTRIDE]);
       if (n < 64) {
-        cz_plate_count_clear_free(T, e, plate, true);
+        if (n) cz_plate_clear_free(T, e, plate);
+        e.o[plate * OSTRIDE] += O_PCOUNT_ONE;
         e.o[h * OSTRIDE] = O_WITH_XY(O_WITH_CONT(hr, CK_PLATE, plate, n) | O_FREE, cell);
         e.ag[i * OSTRIDE] = dropped;  // put_down (world_objects.py:790-792)
       }
@@ -332,9 +339,10 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
     uint32_t pr = e.o[last * OSTRIDE];
     uint32_t ptf = TAB_TF(last);
     if ((ptf & (TF_CHOP | TF_BLEND)) && (pr & (O_CHOP | O_MASH))) {
-      uint32_t n = cz_plate_count_clear_free(T, e, h, false);
+      const uint32_t n = O_PCOUNT(hr);
       if (n < 64) {
-        cz_plate_count_clear_free(T, e, h, true);
+        if (n) cz_plate_clear_free(T, e, h);
+        e.o[h * OSTRIDE] = hr + O_PCOUNT_ONE;
         if (O_CK(pr) == CK_STATIC) {
           if (n_content > 1) {
             cz_remove_from_static(T, e, cell, O_POS(pr));
@@ -369,11 +377,11 @@ __device__ __forceinline__ void cz_refresh_static_free(const CzDev& T, EnvRegs& 
   int top = -1;
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
-    if ((r & O_PRESENT) && O_CK(r) == CK_STATIC && O_XY(r) == cell && (int)O_POS(r) > top) top = O_POS(r);
+    if (O_IN_STATIC_AT(r, cell) && (int)O_POS(r) > top) top = O_POS(r);
   }
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
-    if ((r & O_PRESENT) && O_CK(r) == CK_STATIC && O_XY(r) == cell)
+    if (O_IN_STATIC_AT(r, cell))
       e.o[k * OSTRIDE] = ((int)O_POS(r) == top) ? (r | O_FREE) : (r & ~O_FREE);
   }
 }
@@ -383,11 +391,11 @@ __device__ __forceinline__ void cz_refresh_plate_free(const CzDev& T, EnvRegs& e
   int top = -1;
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
-    if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == p && (int)O_POS(r) > top) top = O_POS(r);
+    if (O_ON_PLATE(r, p) && (int)O_POS(r) > top) top = O_POS(r);
   }
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
-    if ((r & O_PRESENT) && O_CK(r) == CK_PLATE && O_CID(r) == p)
+    if (O_ON_PLATE(r, p))
       e.o[k * OSTRIDE] = ((int)O_POS(r) == top) ? (r | O_FREE) : (r & ~O_FREE);
   }
 }
@@ -396,14 +404,11 @@ __device__ __forceinline__ void cz_refresh_plate_free(const CzDev& T, EnvRegs& e
 // the `for obj in world.world_objects[node.name]` loop of Recipe.update_recipe_state
 // (recipe.py:83-87) with check_conditions' attribute test (:96-98).  Out of line: it is called
 // for every node of every recipe and would otherwise be replicated by the unrolled caller.
-__device__ __noinline__ uint64_t cz_node_mask(const uint32_t* o, uint32_t node, uint64_t static_mask, int base, int cnt) {
-  const uint32_t ty = node & 255u;
-  if (node & 256u) return static_mask;
-  if (ty == 255u) return 0;  // a type the meta file does not know: no such object can exist
-  const uint32_t cond = (node >> 9) & 3u;
-  const uint32_t need = O_PRESENT | (cond == 1 ? O_CHOP : (cond == 2 ? O_MASH : 0u));
+__device__ __noinline__ uint64_t cz_node_mask(const uint32_t* o, uint32_t span) {
+  const uint32_t need = span >> 16;  // O_PRESENT plus the chopped / mashed bit the node asks for
+  const int base = span & 255u, end = base + ((span >> 8) & 255u);  // no slots: a type the meta file does not know
   uint64_t mask = 0;
-  for (int s = base; s < base + cnt; ++s) {
+  for (int s = base; s < end; ++s) {
     uint32_t r = o[s * OSTRIDE];
     if ((r & need) == need) mask |= 1ull << O_XY(r);
   }
@@ -424,14 +429,13 @@ __device__ __forceinline__ uint32_t cz_recipe_marks(const CzDev& T, const EnvReg
     m[k] = 0;
     if (k < n) {
       const uint32_t node = TAB_RNODE(rid, k);
-      const bool is_static = node & 256u, known = (node & 255u) != 255u;
-      uint64_t mask = cz_node_mask(e.o, node, is_static ? TAB_SMASK(e.variant, node & 7u) : 0ull,
-                                   (!is_static && known) ? TAB_TBASE(node & 255u) : 0,
-                                   (!is_static && known) ? TAB_TCOUNT(node & 255u) : 0);
+      uint64_t mask = (node & 256u) ? TAB_SMASK(e.variant, node & 7u) : cz_node_mask(e.o, TAB_RSPAN(rid, k));
       const uint32_t kids = node >> 16;
+      if (kids) {  // leaves (most nodes) skip the child loop
 #pragma unroll
-      for (int j = k + 1; j < CZ_MAX_NODES; ++j)
-        if (kids & (1u << j)) mask &= m[j];
+        for (int j = k + 1; j < CZ_MAX_NODES; ++j)
+          if (kids & (1u << j)) mask &= m[j];
+      }
       m[k] = mask;
       if (mask) marks |= 1u << k;
     }
@@ -536,7 +540,7 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
       bool all_mashed = true;
       for (int s = 0; s < T.D; ++s) {
         uint32_t r = e.o[s * OSTRIDE];
-        if (!(r & O_PRESENT) || O_CK(r) != CK_STATIC || O_XY(r) != cell) continue;
+        if (!O_IN_STATIC_AT(r, cell)) continue;
         ++n;
         if (!(r & (O_CHOP | O_MASH))) {  // BlenderFood.blend: one call takes FRESH to MASHED (abstract_classes.py:266-273)
           r |= O_MASH;

@@ -747,6 +747,21 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   UP(obs_table, d->obs_table, (size_t)T.V * 64 * T.tab_len);
   UP(recipe_nodes, d->recipe_nodes, (size_t)T.B * CZ_MAX_NODES);
   UP(recipe_len, d->recipe_len, T.B);
+  static uint32_t spans[256 * CZ_MAX_NODES];  // per node: first slot | slots << 8 | required record bits << 16
+  for (int b = 0; b < T.B; ++b)
+    for (int k = 0; k < CZ_MAX_NODES; ++k) {
+      const uint32_t node = d->recipe_nodes[b * CZ_MAX_NODES + k], ty = node & 255u, cond = (node >> 9) & 3u;
+      uint32_t span = 0;
+      if (!(node & 256u) && ty != 255u) {
+        if ((int)ty >= T.T) {
+          cz_tables_destroy(t);
+          return cz_fail(CZ_EINVAL, "%s", "recipe node names a dynamic type outside type_base");
+        }
+        span = d->type_base[ty] | (uint32_t)d->type_count[ty] << 8;
+      }
+      spans[b * CZ_MAX_NODES + k] = span | (O_PRESENT | (cond == 1 ? O_CHOP : (cond == 2 ? O_MASH : 0u))) << 16;
+    }
+  UP(recipe_spans, spans, (size_t)T.B * CZ_MAX_NODES);
   UP(pool, d->pool, (size_t)T.P * T.rows);
   UP(default_recipes, d->default_recipes, T.R);
   UP(spawn_x, d->spawn_x, (size_t)T.A * 8);
@@ -783,7 +798,10 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
       for (int k = 0; k < T.S; ++k) w.static_cells[v][k] = d->static_cells[v * T.S + k];
     }
     for (int b = 0; b < nb; ++b) {
-      for (int k = 0; k < CZ_MAX_NODES; ++k) w.recipe_nodes[b][k] = d->recipe_nodes[b * CZ_MAX_NODES + k];
+      for (int k = 0; k < CZ_MAX_NODES; ++k) {
+        w.recipe_nodes[b][k] = d->recipe_nodes[b * CZ_MAX_NODES + k];
+        w.recipe_spans[b][k] = spans[b * CZ_MAX_NODES + k];
+      }
       w.recipe_len[b] = d->recipe_len[b];
     }
     for (int i = 0; i < T.D; ++i) { w.slot_type[i] = d->slot_type[i]; w.slot_tf[i] = d->type_flags[d->slot_type[i]]; }

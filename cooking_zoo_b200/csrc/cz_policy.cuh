@@ -137,10 +137,8 @@ __device__ __forceinline__ uint32_t pol_cook(const CzDev& T, const CzPolicyDev& 
     m[k] = 0;
     if (k < n) {
       const uint32_t node = __ldg(T.recipe_nodes + rid * CZ_MAX_NODES + k);
-      const bool is_static = node & 256u, known = (node & 255u) != 255u;
-      uint64_t mask = cz_node_mask(o, node, is_static ? __ldg(T.static_masks + variant * 8 + (node & 7u)) : 0ull,
-                                   (!is_static && known) ? (int)__ldg(T.type_base + (node & 255u)) : 0,
-                                   (!is_static && known) ? (int)__ldg(T.type_count + (node & 255u)) : 0);
+      uint64_t mask = (node & 256u) ? __ldg(T.static_masks + variant * 8 + (node & 7u))
+                                    : cz_node_mask(o, __ldg(T.recipe_spans + rid * CZ_MAX_NODES + k));
       const uint32_t kids = node >> 16;
 #pragma unroll
       for (int j = k + 1; j < CZ_MAX_NODES; ++j)

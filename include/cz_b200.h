@@ -64,7 +64,8 @@ extern "C" {
  *
  * object record : 0-2 x | 3-5 y | 6 present | 7 chopped | 8 mashed | 9 free |
  *                 10-11 container kind (0 held by agent, 1 static content, 2 plate content) |
- *                 12-16 container id (agent index / 0 / plate slot) | 17-22 position in content
+ *                 12-16 container id (agent index / 0 / plate slot) | 17-22 position in content |
+ *                 23-29 Plate records only: number of items on the plate (len(plate.content))
  * agent record  : 0-2 x | 3-5 y | 6-8 orientation | 9 holding? | 10-14 held slot |
  *                 15 active | 16-31 grace period left
  * SBITS         : 0-3 cutboard k READY | 4-7 blender k READY | 8-11 blender k toggle |
