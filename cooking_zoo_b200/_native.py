@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcz_b200.so")
+LIB_PATH = os.environ.get("CZ_B200_LIB") or os.path.join(HERE, "libcz_b200.so")   # override: A/B builds of the same ABI
 ABI_VERSION = 1
 STEP_AUTO_RESET = 1
 

@@ -25,6 +25,9 @@
 #define CZ_WARPS_PER_BLOCK 4
 #endif
 #define CZ_THREADS (32 * CZ_WARPS_PER_BLOCK)
+#ifndef CZ_DYN_MIN_BLOCKS
+#define CZ_DYN_MIN_BLOCKS CZ_MIN_BLOCKS  // the dynamics-only instantiation (OBS_NONE) of the pipelined step
+#endif
 #ifndef CZ_MIN_BLOCKS
 #define CZ_MIN_BLOCKS (28 / CZ_WARPS_PER_BLOCK)  // 28 warps/SM: registers capped at 72, shared memory at 32 KB per block
 #endif
@@ -293,7 +296,7 @@ __host__ __device__ inline size_t cz_warp_words(int D, int A) { return (size_t)(
 __host__ __device__ inline size_t cz_block_smem_head() { return (sizeof(BlockSmem) + 15) & ~(size_t)15; }
 
 template <int MODE, int OBS, int NA>
-__global__ void __launch_bounds__(CZ_THREADS, CZ_MIN_BLOCKS)
+__global__ void __launch_bounds__(CZ_THREADS, OBS == 2 ? CZ_DYN_MIN_BLOCKS : CZ_MIN_BLOCKS)
 cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* state_out,  // may alias (in-place step)
               const uint8_t* __restrict__ actions,
               const int32_t* __restrict__ layout_ids, const uint8_t* __restrict__ recipe_ids,
