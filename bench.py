@@ -216,11 +216,11 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def timed_run(pipelined, sample_clocks):
+    def timed_run(pipelined, sample_clocks, obs_dtype=torch.float64):
         """W warm-up + K timed steps of one mode; returns (env, ms_total max over ranks, launches, clocks)."""
         env = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
                                 device=str(dev), recipe_pool=BOOK, layout_pool_size=400, layout_seed=0,
-                                auto_reset=True, seed=2026, env_offset=rank * N, pipelined=pipelined)
+                                auto_reset=True, seed=2026, env_offset=rank * N, pipelined=pipelined, obs_dtype=obs_dtype)
         env.reset(recipe_ids=recipe_ids)
         for s in range(args.warmup):
             env.step(actions[s % ring])
@@ -398,6 +398,37 @@ def run_gpu_arm(args):
                 "recipes_done_now": float(envc.info()["recipe_done"].sum())}
         envc.close()
 
+    # ---- float32 observation mode (reported separately; rows = the f64 rows rounded element-wise)
+    f32 = None
+    if world == 1 and not args.no_cfg3:
+        env.wait()
+        torch.cuda.synchronize(dev)
+        envf, ms_f, _, _ = timed_run(True, False, torch.float32)
+        envf.close()
+        envf, ms_fs, _, _ = timed_run(False, False, torch.float32)
+        h_obs32 = torch.empty((N, A, L), dtype=torch.float32).pin_memory()
+
+        def host_step32():
+            _native.check(lib.cz_step_host(envf._handle, envf.state.data_ptr(), h_act.data_ptr(), h_obs32.data_ptr(),
+                                           h_rew.data_ptr(), h_term.data_ptr(), h_trunc.data_ptr(), N,
+                                           _native.STEP_AUTO_RESET | _native.STEP_OBS_F32, 2026, rank * N, stream))
+        for _ in range(3):
+            host_step32()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(e2e_steps):
+            host_step32()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        b32 = A * L * 4 + A * 8 + 2 * A + A + 2 * envf.tables.rows * 4
+        f32 = {"dtype": "f32 observations (f64 rewards)", "bytes_per_env_step": b32,
+               "pipelined_env_steps_per_s": N * args.steps / (ms_f / 1e3),
+               "pipelined_gbs": N * b32 / (ms_f / args.steps / 1e3) / 1e9,
+               "in_place_env_steps_per_s": N * args.steps / (ms_fs / 1e3),
+               "e2e_env_steps_per_s": N * e2e_steps / (e0.elapsed_time(e1) / 1e3),
+               "d2h_bytes_per_step": N * A * L * 4 + N * A * 8 + 2 * N * A}
+        envf.close()
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -437,7 +468,7 @@ def run_gpu_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step)",
                         "host_link_gbs": (h2d + d2h) * e2e_value / N / 1e9 / world},
-                "gpu_launches": int(launches), "clocks": clocks, "cfg3": cfg3, "device_policy": cook,
+                "gpu_launches": int(launches), "clocks": clocks, "cfg3": cfg3, "device_policy": cook, "f32_obs": f32,
                 "mode": args.mode,
                 "sync_step": {"value": sync_value, "ms_per_step": ms_sync / args.steps,
                               "frac": N * bytes_per_env_step / (ms_sync / args.steps / 1e3) / 1e9 / peak,

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CZ_B200_LIB") or os.path.join(HERE, "libcz_b200.so")   # override: A/B builds of the same ABI
 ABI_VERSION = 1
 STEP_AUTO_RESET = 1
+STEP_OBS_F32 = 2
 
 _P = C.c_void_p
 
@@ -52,6 +53,7 @@ SIGNATURES = {
     "cz_reset": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "cz_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint64, C.c_int64, _P]),
     "cz_observe": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "cz_observe_f32": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "cz_step_pipelined": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint64, C.c_int64, _P]),
     "cz_pipeline_wait": (C.c_int, [_P, _P]),
     "cz_pipeline_reset": (C.c_int, [_P, C.c_int]),

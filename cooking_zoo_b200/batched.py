@@ -40,7 +40,7 @@ class BatchedCookingEnv:
                  obs_spaces=None, end_condition_all_dishes=False, action_scheme="scheme1", render=False,
                  reward_scheme=None, agent_respawn_rate=0.0, grace_period=20, agent_despawn_rate=0.0, *,
                  device="cuda:0", recipe_pool=None, layout_pool_size=256, layout_seed=0, layouts=None,
-                 auto_reset=False, seed=0, env_offset=0, pipelined=False):
+                 auto_reset=False, seed=0, env_offset=0, pipelined=False, obs_dtype=torch.float64):
         obs_spaces = obs_spaces or ["feature_vector"] * num_agents
         if any(o != "feature_vector" for o in obs_spaces):
             raise NotImplementedError("the batched entry point builds feature_vector observations only "
@@ -73,7 +73,14 @@ class BatchedCookingEnv:
         self.pipelined = bool(pipelined)
         self._state2 = torch.zeros((2 if self.pipelined else 1, t.rows, N), dtype=torch.int32, device=dev)
         self.state = self._state2[0]
-        self.obs = torch.zeros((N, A, L), dtype=torch.float64, device=dev)
+        # float32 observations: the float64 rows rounded element-wise (reference obs.astype(np.float32)), written
+        # directly by their own kernel — half the bytes of the default
+        if obs_dtype not in (torch.float64, torch.float32):
+            raise ValueError("obs_dtype must be torch.float64 (the reference's dtype) or torch.float32")
+        self.obs_dtype = obs_dtype
+        self._flags = (_native.STEP_AUTO_RESET if self.auto_reset else 0) | \
+                      (_native.STEP_OBS_F32 if obs_dtype == torch.float32 else 0)
+        self.obs = torch.zeros((N, A, L), dtype=obs_dtype, device=dev)
         self.reward = torch.zeros((N, A), dtype=torch.float64, device=dev)
         self.terminated = torch.zeros((N, A), dtype=torch.uint8, device=dev)
         self.truncated = torch.zeros((N, A), dtype=torch.uint8, device=dev)
@@ -121,10 +128,14 @@ class BatchedCookingEnv:
         if mask is not None:
             mk = torch.as_tensor(mask).to(torch.uint8).to(self.device).contiguous()
         with torch.cuda.device(self.device):
+            f32 = self.obs_dtype == torch.float32
             _native.check(self.lib.cz_reset(self._handle, self.state.data_ptr(), lid.data_ptr(),
                                             rid.data_ptr() if rid is not None else None,
                                             mk.data_ptr() if mk is not None else None,
-                                            self.obs.data_ptr(), N, self._stream()))
+                                            None if f32 else self.obs.data_ptr(), N, self._stream()))
+            if f32:
+                _native.check(self.lib.cz_observe_f32(self._handle, self.state.data_ptr(), self.obs.data_ptr(), N,
+                                                      self._stream()))
             if self.pipelined:
                 torch.cuda.current_stream(self.device).synchronize()
                 _native.check(self.lib.cz_pipeline_reset(self._handle, 0))
@@ -145,8 +156,7 @@ class BatchedCookingEnv:
             _native.check(self.lib.cz_step(self._handle, self.state.data_ptr(), a.data_ptr(), self.obs.data_ptr(),
                                            self.reward.data_ptr(), self.terminated.data_ptr(),
                                            self.truncated.data_ptr(), self.error_flags.data_ptr(), self.num_envs,
-                                           _native.STEP_AUTO_RESET if self.auto_reset else 0,
-                                           self.seed, self.env_offset, self._stream()))
+                                           self._flags, self.seed, self.env_offset, self._stream()))
         return self.obs, self.reward, self.terminated, self.truncated, self._info
 
     def _step_pipelined(self, a):
@@ -154,7 +164,7 @@ class BatchedCookingEnv:
             _native.check(self.lib.cz_step_pipelined(
                 self._handle, self._state2.data_ptr(), a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
                 self.terminated.data_ptr(), self.truncated.data_ptr(), self.error_flags.data_ptr(), self.num_envs,
-                _native.STEP_AUTO_RESET if self.auto_reset else 0, self.seed, self.env_offset, self._stream()))
+                self._flags, self.seed, self.env_offset, self._stream()))
         self.state = self._state2[self.lib.cz_pipeline_current(self._handle)]
         return self.obs, self.reward, self.terminated, self.truncated, self._info
 
@@ -203,7 +213,8 @@ class BatchedCookingEnv:
 
     def observe(self):
         with torch.cuda.device(self.device):
-            _native.check(self.lib.cz_observe(self._handle, self.state.data_ptr(), self.obs.data_ptr(),
+            fn = self.lib.cz_observe_f32 if self.obs_dtype == torch.float32 else self.lib.cz_observe
+            _native.check(fn(self._handle, self.state.data_ptr(), self.obs.data_ptr(),
                                               self.num_envs, self._stream()))
         return self.obs
 

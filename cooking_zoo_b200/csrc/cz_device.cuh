@@ -41,6 +41,9 @@ struct CzDev {
   const uint8_t* spawn_x;
   const uint8_t* spawn_y;
   const uint8_t* spawn_n;
+  const float* xlut32;       // the same tables rounded to float32 once on the host (float32 observation rows)
+  const float* ylut32;
+  const float* obs_table32;
   const void* blob;  // BlockSmem image (LUTs + SmemTabs), built by cz_tables_create
 };
 

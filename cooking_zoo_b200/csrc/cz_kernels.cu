@@ -666,6 +666,8 @@ static size_t cz_smem_bytes(const CzDev& T) {
          (size_t)CZ_WARPS_PER_BLOCK * CZ_STAGE_SETS * T.A * row_bytes;
 }
 
+#include "cz_obs32.cuh"
+
 extern "C" int cz_abi_version(void) { return CZ_ABI_VERSION; }
 extern "C" const char* cz_last_error(void) { return g_err; }
 extern "C" uint64_t cz_launch_count(void) { return g_launches.load(); }
@@ -748,6 +750,19 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   UP(type_count, d->type_count, T.T);
   UP(comp_slots, d->comp_slots, T.n_comp);
   UP(obs_table, d->obs_table, (size_t)T.V * 64 * T.tab_len);
+  {  // float32 copies for cz_observe_f32 / CZ_STEP_OBS_F32: element-wise rounding of the f64 tables
+    float xl[16], yl[16];
+    for (int i = 0; i < 2 * T.W - 1; ++i) xl[i] = (float)d->xlut[i];
+    for (int i = 0; i < 2 * T.H - 1; ++i) yl[i] = (float)d->ylut[i];
+    UP(xlut32, xl, 2 * T.W - 1);
+    UP(ylut32, yl, 2 * T.H - 1);
+    const size_t n_tab = (size_t)T.V * 64 * T.tab_len;
+    float* t32 = new (std::nothrow) float[n_tab ? n_tab : 1];
+    if (!t32) { cz_tables_destroy(t); return cz_fail(CZ_EINVAL, "%s", "out of host memory"); }
+    for (size_t i = 0; i < n_tab; ++i) t32[i] = (float)d->obs_table[i];
+    UP(obs_table32, t32, n_tab);
+    delete[] t32;
+  }
   UP(recipe_nodes, d->recipe_nodes, (size_t)T.B * CZ_MAX_NODES);
   UP(recipe_len, d->recipe_len, T.B);
   static uint32_t spans[256 * CZ_MAX_NODES];  // per node: first slot | slots << 8 | required record bits << 16
@@ -831,9 +846,11 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   SET_SMEM((cz_env_kernel<M, OBS_TMA, 3>)); SET_SMEM((cz_env_kernel<M, OBS_TMA, 4>));                   \
   SET_SMEM((cz_env_kernel<M, OBS_STG, 1>)); SET_SMEM((cz_env_kernel<M, OBS_STG, 2>));                   \
   SET_SMEM((cz_env_kernel<M, OBS_STG, 3>)); SET_SMEM((cz_env_kernel<M, OBS_STG, 4>));                   \
+  SET_SMEM((cz_env_kernel<M, OBS_NONE, 0>));                                                           \
   SET_SMEM((cz_env_kernel<M, OBS_NONE, 1>)); SET_SMEM((cz_env_kernel<M, OBS_NONE, 2>));                 \
   SET_SMEM((cz_env_kernel<M, OBS_NONE, 3>)); SET_SMEM((cz_env_kernel<M, OBS_NONE, 4>))
   SET_MODE(MODE_STEP); SET_MODE(MODE_RESET); SET_MODE(MODE_OBSERVE);
+  SET_SMEM(cz_obs32_kernel);
 #undef SET_MODE
 #undef SET_SMEM
   *out = t;
@@ -872,8 +889,10 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
                      const uint8_t* recipe_ids, const uint8_t* mask, double* obs, double* reward, uint8_t* term,
                      uint8_t* trunc, uint32_t* err, int n_envs, uint32_t flags, uint64_t seed, int64_t env_offset,
                      void* stream) {
-  if (!t || !state || !state_out || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (!t || !state || !state_out) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (MODE == MODE_OBSERVE && !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (n_envs <= 0) return CZ_OK;
+  if (!obs) dyn_only = true;  // no observation buffer: dynamics / reset only
   if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
   size_t smem = cz_smem_bytes(t->dev);
   if (dyn_only && t->pipe_dyn_blocks > 0) {
@@ -894,6 +913,8 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
       case 3: CZ_GO(OBS_NONE, 3); break;
       default: CZ_GO(OBS_NONE, 4); break;
     }
+  } else if (dyn_only) {
+    CZ_GO(OBS_NONE, 0);
   } else if (t->simple && t->obs_path == OBS_TMA) {
     switch (t->dev.A) {
       case 1: CZ_GO(OBS_TMA, 1); break;
@@ -930,8 +951,18 @@ extern "C" int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actio
                        uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, uint32_t flags,
                        uint64_t seed, int64_t env_offset, void* stream) {
   if (!actions || !reward || !terminated || !truncated) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if ((flags & CZ_STEP_OBS_F32) && obs) {  // dynamics, then the float32 row writer on the same stream
+    int rc = cz_launch<MODE_STEP>(t, state, state, true, actions, nullptr, nullptr, nullptr, nullptr, reward, terminated, truncated,
+                                  error_flags, n_envs, flags, seed, env_offset, stream);
+    if (rc != CZ_OK) return rc;
+    return cz_launch_obs32(t, state, reinterpret_cast<float*>(obs), n_envs, (cudaStream_t)stream);
+  }
   return cz_launch<MODE_STEP>(t, state, state, false, actions, nullptr, nullptr, nullptr, obs, reward, terminated, truncated,
                               error_flags, n_envs, flags, seed, env_offset, stream);
+}
+
+extern "C" int cz_observe_f32(const cz_tables* t, const uint32_t* state, float* obs32, int n_envs, void* stream) {
+  return cz_launch_obs32(t, state, obs32, n_envs, (cudaStream_t)stream);
 }
 
 extern "C" int cz_observe(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, void* stream) {
@@ -989,7 +1020,10 @@ extern "C" int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* 
   CZ_CUDA(cudaEventRecord(t->ev_dyn, t->pipe_dyn));
   CZ_CUDA(cudaStreamWaitEvent(t->pipe_obs, t->ev_dyn, 0));
   CZ_CUDA(cudaStreamWaitEvent(t->pipe_obs, t->ev_user, 0));
-  {
+  if (flags & CZ_STEP_OBS_F32) {
+    rc = cz_launch_obs32(t, out, reinterpret_cast<float*>(obs), n_envs, t->pipe_obs);
+    if (rc != CZ_OK) return rc;
+  } else {
     const int blocks = (n_envs + ENVS_WARPS - 1) / ENVS_WARPS;
     const size_t smem = (size_t)ENVS_WARPS * t->dev.A * ((t->dev.stage_len + 1) / 2) * 16;
     switch (t->dev.A) {
@@ -1040,7 +1074,8 @@ extern "C" int cz_step_host(cz_tables* t, uint32_t* state_dev, const uint8_t* ac
   int rc = cz_step(t, state_dev, t->d_actions, t->d_obs, t->d_reward, t->d_term, t->d_trunc, nullptr, n_envs, flags, seed,
                    env_offset, stream);
   if (rc != CZ_OK) return rc;
-  CZ_CUDA(cudaMemcpyAsync(obs_host, t->d_obs, na * T.L * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CZ_CUDA(cudaMemcpyAsync(obs_host, t->d_obs, na * T.L * ((flags & CZ_STEP_OBS_F32) ? sizeof(float) : sizeof(double)),
+                          cudaMemcpyDeviceToHost, s));
   CZ_CUDA(cudaMemcpyAsync(reward_host, t->d_reward, na * sizeof(double), cudaMemcpyDeviceToHost, s));
   CZ_CUDA(cudaMemcpyAsync(terminated_host, t->d_term, na, cudaMemcpyDeviceToHost, s));
   CZ_CUDA(cudaMemcpyAsync(truncated_host, t->d_trunc, na, cudaMemcpyDeviceToHost, s));

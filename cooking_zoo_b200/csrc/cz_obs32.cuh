@@ -1,0 +1,104 @@
+// cz_obs32.cuh — float32 observation rows (reported separately from the f64 headline).
+//
+// obs32[e][a][k] == (float) get_feature_vector(a)[k] of environment e (cooking_env.py:352-373): every
+// element of a row is either a host-divided table entry ((x - ax) / W, (y - ay) / H), 0 or 1, so the
+// float32 row is the element-wise rounding of the float64 row and the tables are rounded once on the
+// host (cz_tables_create).  One warp builds the A rows of one environment in shared memory (table
+// segments, zeroed computed ranges, then one lane per computed slot) and streams them out with the
+// widest store the environment's byte offset allows.  Works for every observation plan (no "simple"
+// restriction).  Included by cz_kernels.cu.
+#pragma once
+
+#define CZ_OBS32_MAX_WARPS 8
+
+__global__ void __launch_bounds__(32 * CZ_OBS32_MAX_WARPS)
+cz_obs32_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, float* __restrict__ obs, int n_envs,
+                int warps_per_block) {
+  extern __shared__ __align__(16) unsigned char smem_f32[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * warps_per_block + warp;
+  if (warp >= warps_per_block || env >= n_envs) return;
+  const int A = T.A, L = T.L, D = T.D;
+  const size_t N = (size_t)n_envs;
+  const int env_floats = A * L;
+  float* stage = reinterpret_cast<float*>(smem_f32) + (size_t)warp * ((env_floats + 3) & ~3);
+  const uint32_t* misc = state + (size_t)(D + A) * N;
+  const uint32_t var = __ldg(misc + (size_t)CZ_ROW_VARIANT * N + env);
+  const uint32_t sbits = __ldg(misc + (size_t)CZ_ROW_SBITS * N + env);
+
+  // table segments and zeroed computed ranges of every row
+  for (int a = 0; a < A; ++a) {
+    const uint32_t cell = __ldg(state + (size_t)(D + a) * N + env) & 63u;
+    const float* tab = T.obs_table32 + ((size_t)var * 64 + cell) * T.tab_len;
+    float* row = stage + a * L;
+    for (int g = 0; g < T.n_segs; ++g)
+      for (int k = lane; k < T.segs[g][1]; k += 32) row[T.segs[g][0] + k] = __ldg(tab + T.segs[g][2] + k);
+    for (int g = 0; g < T.n_ranges; ++g)
+      for (int k = lane; k < T.ranges[g][1]; k += 32) row[T.ranges[g][0] + k] = 0.0f;
+  }
+  __syncwarp();
+
+  // computed slots: one lane per slot, every observer
+  for (int q = lane; q < T.n_comp; q += 32) {
+    const uint32_t d = __ldg(T.comp_slots + q);
+    const int off = d & 0xFFFu;
+    const uint32_t flen = (d >> 12) & 7u, kind = (d >> 15) & 3u, idx = (d >> 17) & 255u;
+    uint32_t rec = 0, fb4 = 0;
+    bool present;
+    if (kind != 0u) {
+      const bool is_agent = kind == 2u;
+      const bool exists = !is_agent || (int)idx < A;
+      rec = exists ? __ldg(state + (size_t)(is_agent ? D + idx : idx) * N + env) : 0u;
+      present = is_agent ? exists : (rec & O_PRESENT) != 0;
+      const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+      fb4 = is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2);
+    } else {  // static slot outside the table runs (live Switch / Block, or a plain one between computed slots)
+      const uint32_t cell = __ldg(T.static_cells + var * T.S + idx);
+      present = cell != 0xFFu;
+      rec = present ? cell : 0u;
+      const uint32_t g = __ldg(T.grid + var * 64 + rec);
+      fb4 = ((g & 15u) == ST_SWITCH ? (sbits >> (12 + (g >> 4))) : (sbits >> (16 + (g >> 4)))) & 1u;
+    }
+    const uint32_t one = 1u << (flen - 1);
+    const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
+    const int x = rec & 7u, y = (rec >> 3) & 7u;
+    for (int a = 0; a < A; ++a) {
+      const uint32_t me = __ldg(state + (size_t)(D + a) * N + env);
+      const bool self = kind == 2u && (int)idx == a;  // the observer's own entry is x / W, y / H (cooking_env.py:364-368)
+      float X = __ldg(T.xlut32 + (x - (self ? 0 : (int)(me & 7u)) + T.W - 1));
+      float Y = __ldg(T.ylut32 + (y - (self ? 0 : (int)((me >> 3) & 7u)) + T.H - 1));
+      if (!present) { X = 0.0f; Y = 0.0f; }
+      float* out = stage + a * L + off;
+      out[0] = X;
+      out[1] = Y;
+      for (uint32_t k = 0; k < flen; ++k) out[2 + k] = (fb >> k & 1u) ? 1.0f : 0.0f;
+    }
+  }
+  __syncwarp();
+
+  float* g = obs + (size_t)env * env_floats;
+  if ((env_floats & 3) == 0) {  // every environment starts 16-byte aligned
+    for (int k = lane; k < env_floats >> 2; k += 32) reinterpret_cast<float4*>(g)[k] = reinterpret_cast<const float4*>(stage)[k];
+  } else if ((env_floats & 1) == 0) {
+    for (int k = lane; k < env_floats >> 1; k += 32) reinterpret_cast<float2*>(g)[k] = reinterpret_cast<const float2*>(stage)[k];
+  } else {
+    for (int k = lane; k < env_floats; k += 32) g[k] = stage[k];
+  }
+}
+
+static int cz_launch_obs32(const cz_tables* t, const uint32_t* state, float* obs, int n_envs, cudaStream_t s) {
+  if (!t || !state || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (n_envs <= 0) return CZ_OK;
+  if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
+  const size_t per_warp = (size_t)((t->dev.A * t->dev.L + 3) & ~3) * 4;
+  int warps = (int)(((size_t)96 * 1024) / per_warp);  // keep at least two blocks per SM resident
+  if (warps > CZ_OBS32_MAX_WARPS) warps = CZ_OBS32_MAX_WARPS;
+  if (warps < 1) warps = 1;
+  const size_t smem = per_warp * warps;
+  if (smem > t->smem_optin) return cz_fail(CZ_ELIMIT, "%s", "observation rows too long for the float32 writer");
+  const int blocks = (n_envs + warps - 1) / warps;
+  cz_obs32_kernel<<<blocks, 32 * warps, smem, s>>>(t->dev, state, obs, n_envs, warps);
+  g_launches.fetch_add(1);
+  CZ_CUDA(cudaGetLastError());
+  return CZ_OK;
+}

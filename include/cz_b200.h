@@ -82,6 +82,9 @@ extern "C" {
 /* cz_step flags */
 #define CZ_STEP_AUTO_RESET 1u  /* an environment whose `done` bit is set is re-initialised from
                                   the layout pool instead of stepped (reward 0, flags 0) */
+#define CZ_STEP_OBS_F32 2u     /* `obs` points to float32 [n][A][L]: each element is the float64
+                                  observation rounded to float32 (the reference's obs.astype(float32));
+                                  honoured by cz_step, cz_step_pipelined and cz_step_host */
 
 /* Host-side description of everything compiled once per (level, meta, recipes, scheme):
  * replaces load_level.load_level / parsing.parse_* (engine/load_level.py:55-71,
@@ -166,6 +169,11 @@ int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actions, double*
 
 /* get_feature_vector only (cooking_env.py:352-373): rebuild obs from the current state. */
 int cz_observe(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, void* stream);
+
+/* The same rows as float32 (element-wise rounding of the float64 rows; any observation plan).
+ * cz_reset and cz_step accept obs == NULL (state / rewards / flags only), so a float32 consumer never
+ * pays for float64 rows: cz_reset(..., NULL, ...) + cz_observe_f32, then cz_step with CZ_STEP_OBS_F32. */
+int cz_observe_f32(const cz_tables* t, const uint32_t* state, float* obs32, int n_envs, void* stream);
 
 /* The reference-facing call with HOST buffers: copies actions host->device, steps, copies
  * obs/reward/flags device->host, and synchronises the stream before returning.  Scratch

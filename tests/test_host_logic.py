@@ -16,7 +16,7 @@ from tests.replay import golden_files, load_golden, ROOT
 def test_library_exports_every_declared_symbol():
     """every function include/cz_b200.h declares is exported by libcz_b200.so and bound in _native"""
     header = open(os.path.join(ROOT, "include", "cz_b200.h")).read()
-    declared = set(re.findall(r"\b(cz_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(cz_[a-z_0-9]+)\s*\(", header))
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     lib = ctypes.CDLL(_native.LIB_PATH)
     for name in declared:
