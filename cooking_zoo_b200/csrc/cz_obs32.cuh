@@ -86,10 +86,96 @@ cz_obs32_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ st
   }
 }
 
+// Specialised writer for the packed (observer, slot) plans of the specialised step kernels (`simple` tables, NA * L a
+// even): a lane owns one (observer, slot) pair and two table float2 per row, exactly the lane map of
+// cz_obs_envs_kernel; the A rows are staged as one 16-byte aligned block and leave as float4.
+template <int NA>
+__global__ void __launch_bounds__(32 * CZ_OBS32_MAX_WARPS, 8)
+cz_obs32_fast_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, float* __restrict__ obs, int n_envs) {
+  extern __shared__ __align__(16) unsigned char smem_f32[];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int env = blockIdx.x * CZ_OBS32_MAX_WARPS + warp;
+  if (env >= n_envs) return;
+  const int D = T.D, tab2 = T.tab_len >> 1, L2 = T.L >> 1;
+  const size_t N = (size_t)n_envs;
+  float2* stage2 = reinterpret_cast<float2*>(smem_f32) + (size_t)warp * NA * L2;  // NA * L floats, 16-byte aligned
+
+  const LaneSlot ls = cz_lane_slot_packed(T, lane);  // ls.off is relative to stage_lo
+  const bool is_agent = ls.kind == 2;
+  uint32_t rec = 0;
+  if (ls.off >= 0) rec = __ldg(state + (size_t)(is_agent ? D + ls.idx : ls.idx) * N + env);
+  const uint32_t me = __ldg(state + (size_t)(D + ls.agent) * N + env);
+  const uint32_t var = __ldg(state + (size_t)(D + NA + CZ_ROW_VARIANT) * N + env);
+  const float2* tab = reinterpret_cast<const float2*>(T.obs_table32) + (size_t)var * 64 * tab2 + lane;
+  // table segments of every row: loads first
+  float2 v0[NA], v1[NA];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    const uint32_t cell = __shfl_sync(0xffffffffu, me, a * T.n_comp) & 63u;  // lane a*n_comp observes for agent a
+    if (ls.t0 >= 0) v0[a] = __ldg(tab + cell * tab2);
+    if (ls.t1 >= 0) v1[a] = __ldg(tab + cell * tab2 + 32);
+  }
+  // the computed range of every row starts as zeros (never-occupied slots stay zero)
+  {
+    const int o2 = T.ranges[0][0] >> 1, n2 = T.ranges[0][1] >> 1;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+      for (int k = lane; k < n2; k += 32) stage2[a * L2 + o2 + k] = make_float2(0.0f, 0.0f);
+  }
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    if (ls.t0 >= 0) stage2[a * L2 + ls.t0] = v0[a];
+    if (ls.t1 >= 0) stage2[a * L2 + ls.t1] = v1[a];
+  }
+  __syncwarp();
+  if (ls.off >= 0) {
+    const bool present = is_agent || (rec & O_PRESENT);
+    const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+    const uint32_t fb4 = is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2);
+    const uint32_t one = 1u << (ls.flen - 1);
+    const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
+    const bool self = is_agent && (int)ls.idx == ls.agent;
+    const int x = rec & 7u, y = (rec >> 3) & 7u;
+    float X = __ldg(T.xlut32 + (x - (self ? 0 : (int)(me & 7u)) + T.W - 1));
+    float Y = __ldg(T.ylut32 + (y - (self ? 0 : (int)((me >> 3) & 7u)) + T.H - 1));
+    if (!present) { X = 0.0f; Y = 0.0f; }
+    float* out = reinterpret_cast<float*>(stage2 + ls.agent * L2) + T.stage_lo + ls.off;
+    out[0] = X;
+    out[1] = Y;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (k < (int)ls.flen) out[2 + k] = (fb >> k & 1u) ? 1.0f : 0.0f;
+  }
+  __syncwarp();
+  if (((NA * T.L) & 3) == 0) {  // every environment (and every warp's staging block) starts 16-byte aligned
+    float4* g4 = reinterpret_cast<float4*>(obs + (size_t)env * NA * T.L);
+    const float4* s4 = reinterpret_cast<const float4*>(stage2);
+    for (int k = lane; k < (NA * T.L) >> 2; k += 32) g4[k] = s4[k];
+  } else {
+    float2* g2 = reinterpret_cast<float2*>(obs + (size_t)env * NA * T.L);
+    for (int k = lane; k < NA * L2; k += 32) g2[k] = stage2[k];
+  }
+}
+
 static int cz_launch_obs32(const cz_tables* t, const uint32_t* state, float* obs, int n_envs, cudaStream_t s) {
   if (!t || !state || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (n_envs <= 0) return CZ_OK;
   if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
+  if (t->simple) {
+    const int blocks = (n_envs + CZ_OBS32_MAX_WARPS - 1) / CZ_OBS32_MAX_WARPS;
+    const size_t smem = (size_t)CZ_OBS32_MAX_WARPS * t->dev.A * t->dev.L * 4;
+    if (smem <= 48 * 1024) {
+      switch (t->dev.A) {
+        case 1: cz_obs32_fast_kernel<1><<<blocks, 32 * CZ_OBS32_MAX_WARPS, smem, s>>>(t->dev, state, obs, n_envs); break;
+        case 2: cz_obs32_fast_kernel<2><<<blocks, 32 * CZ_OBS32_MAX_WARPS, smem, s>>>(t->dev, state, obs, n_envs); break;
+        case 3: cz_obs32_fast_kernel<3><<<blocks, 32 * CZ_OBS32_MAX_WARPS, smem, s>>>(t->dev, state, obs, n_envs); break;
+        default: cz_obs32_fast_kernel<4><<<blocks, 32 * CZ_OBS32_MAX_WARPS, smem, s>>>(t->dev, state, obs, n_envs); break;
+      }
+      g_launches.fetch_add(1);
+      CZ_CUDA(cudaGetLastError());
+      return CZ_OK;
+    }
+  }
   const size_t per_warp = (size_t)((t->dev.A * t->dev.L + 3) & ~3) * 4;
   int warps = (int)(((size_t)96 * 1024) / per_warp);  // keep at least two blocks per SM resident
   if (warps > CZ_OBS32_MAX_WARPS) warps = CZ_OBS32_MAX_WARPS;
