@@ -26,15 +26,34 @@ cz_obs32_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ st
   const uint32_t var = __ldg(misc + (size_t)CZ_ROW_VARIANT * N + env);
   const uint32_t sbits = __ldg(misc + (size_t)CZ_ROW_SBITS * N + env);
 
-  // table segments and zeroed computed ranges of every row
+  // table segments and zeroed computed ranges of every row.  The plan is read into registers once, with
+  // constant indices (a run-time index into the kernel parameters would copy the struct to local memory).
+  const bool even = (L & 1) == 0;  // table runs exist only for even L and sit on even boundaries: 8-byte moves
+  const int sh = even ? 1 : 0;
+  const int s0o = T.segs[0][0] >> sh, s0n = T.n_segs > 0 ? T.segs[0][1] >> sh : 0, s0t = T.segs[0][2] >> sh;
+  const int s1o = T.segs[1][0] >> sh, s1n = T.n_segs > 1 ? T.segs[1][1] >> sh : 0, s1t = T.segs[1][2] >> sh;
+  const int r0o = T.ranges[0][0] >> sh, r0n = T.n_ranges > 0 ? T.ranges[0][1] >> sh : 0;
+  const int r1o = T.ranges[1][0] >> sh, r1n = T.n_ranges > 1 ? T.ranges[1][1] >> sh : 0;
+  const int r2o = T.ranges[2][0] >> sh, r2n = T.n_ranges > 2 ? T.ranges[2][1] >> sh : 0;
   for (int a = 0; a < A; ++a) {
     const uint32_t cell = __ldg(state + (size_t)(D + a) * N + env) & 63u;
     const float* tab = T.obs_table32 + ((size_t)var * 64 + cell) * T.tab_len;
     float* row = stage + a * L;
-    for (int g = 0; g < T.n_segs; ++g)
-      for (int k = lane; k < T.segs[g][1]; k += 32) row[T.segs[g][0] + k] = __ldg(tab + T.segs[g][2] + k);
-    for (int g = 0; g < T.n_ranges; ++g)
-      for (int k = lane; k < T.ranges[g][1]; k += 32) row[T.ranges[g][0] + k] = 0.0f;
+    if (even) {
+      float2* row2 = reinterpret_cast<float2*>(row);
+      const float2* tab2 = reinterpret_cast<const float2*>(tab);
+      for (int k = lane; k < s0n; k += 32) row2[s0o + k] = __ldg(tab2 + s0t + k);
+      for (int k = lane; k < s1n; k += 32) row2[s1o + k] = __ldg(tab2 + s1t + k);
+      for (int k = lane; k < r0n; k += 32) row2[r0o + k] = make_float2(0.0f, 0.0f);
+      for (int k = lane; k < r1n; k += 32) row2[r1o + k] = make_float2(0.0f, 0.0f);
+      for (int k = lane; k < r2n; k += 32) row2[r2o + k] = make_float2(0.0f, 0.0f);
+    } else {
+      for (int k = lane; k < s0n; k += 32) row[s0o + k] = __ldg(tab + s0t + k);
+      for (int k = lane; k < s1n; k += 32) row[s1o + k] = __ldg(tab + s1t + k);
+      for (int k = lane; k < r0n; k += 32) row[r0o + k] = 0.0f;
+      for (int k = lane; k < r1n; k += 32) row[r1o + k] = 0.0f;
+      for (int k = lane; k < r2n; k += 32) row[r2o + k] = 0.0f;
+    }
   }
   __syncwarp();
 
@@ -71,7 +90,9 @@ cz_obs32_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ st
       float* out = stage + a * L + off;
       out[0] = X;
       out[1] = Y;
-      for (uint32_t k = 0; k < flen; ++k) out[2 + k] = (fb >> k & 1u) ? 1.0f : 0.0f;
+#pragma unroll
+      for (uint32_t k = 0; k < 5; ++k)
+        if (k < flen) out[2 + k] = (fb >> k & 1u) ? 1.0f : 0.0f;
     }
   }
   __syncwarp();
