@@ -202,9 +202,9 @@ class BatchedCookingEnv:
             rid = cook_recipes.to(device=self.device, dtype=torch.uint8).contiguous()
             if rid.shape != (N, A):
                 raise ValueError("cook_recipes must have shape [num_envs, num_agents]")
-        if self.pipelined:
-            self.wait()
         with torch.cuda.device(self.device):
+            if self.pipelined:     # the cook reads the state only: the observation rows may still be streaming out
+                _native.check(self.lib.cz_pipeline_wait_state(self._handle, self._stream()))
             _native.check(self.lib.cz_policy_act(self._policy, self.state.data_ptr(),
                                                  rid.data_ptr() if rid is not None else None,
                                                  self.cook_actions.data_ptr(), self.cook_crashed.data_ptr(), N,

@@ -1051,6 +1051,14 @@ extern "C" int cz_pipeline_wait(cz_tables* t, void* stream) {
   return CZ_OK;
 }
 
+extern "C" int cz_pipeline_wait_state(cz_tables* t, void* stream) {
+  if (!t) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (!t->pipe_ready) return CZ_OK;
+  CZ_CUDA(cudaEventRecord(t->ev_dyn, t->pipe_dyn));
+  CZ_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, t->ev_dyn, 0));
+  return CZ_OK;
+}
+
 extern "C" int cz_step_host(cz_tables* t, uint32_t* state_dev, const uint8_t* actions_host, double* obs_host,
                             double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host, int n_envs,
                             uint32_t flags, uint64_t seed, int64_t env_offset, void* stream) {

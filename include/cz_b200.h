@@ -203,6 +203,9 @@ int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* actions, do
                       uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs,
                       uint32_t flags, uint64_t seed, int64_t env_offset, void* stream);
 int cz_pipeline_wait(cz_tables* t, void* stream);
+/* Order the caller's stream after the latest dynamics only (state, rewards, flags are final; the observation
+ * rows of that step may still be streaming out): what a device policy reading the state needs. */
+int cz_pipeline_wait_state(cz_tables* t, void* stream);
 int cz_pipeline_reset(cz_tables* t, int current_half);
 int cz_pipeline_current(const cz_tables* t);
 

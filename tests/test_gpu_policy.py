@@ -203,3 +203,24 @@ def test_cfg5_mixed_agent_counts_heuristic_streams_spawning_per_env_recipes():
             if any(te):
                 alive.discard(k)
     assert len(alive) > 20
+
+
+def test_pipelined_closed_loop_equals_in_place_closed_loop():
+    """the cook only waits for the dynamics of the pipelined step (cz_pipeline_wait_state): same trajectories"""
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=60,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    n = 30000
+    a = _make(n, cfg, auto_reset=True, seed=3, layout_pool_size=64)
+    b = _make(n, cfg, auto_reset=True, seed=3, layout_pool_size=64, pipelined=True)
+    a.reset(); b.reset()
+    for t in range(90):
+        aa, _ = a.heuristic_actions()
+        ab, _ = b.heuristic_actions()
+        assert torch.equal(aa, ab), t
+        oa, ra, *_ = a.step(aa)
+        ob, rb, *_ = b.step(ab)
+        if t % 10 == 9:
+            b.wait()
+            assert torch.equal(oa.view(torch.int64), ob.view(torch.int64)) and torch.equal(ra, rb), t
+    b.wait()
+    assert torch.equal(a.state, b.state)
