@@ -84,3 +84,40 @@ def test_python_side_validation():
     a = o1.clone()
     o2, *_ = env.step(np.full((8, 2), 9, np.uint8))
     assert torch.equal(a.view(torch.int64), o2.view(torch.int64))
+
+
+def test_policy_and_f32_entry_points_reject_bad_arguments():
+    from cooking_zoo_b200.policy import compile_policy_tables
+    lib = _native.load_library()
+    t = _tables()
+    desc, keep = _native.make_desc(t)
+    h = C.c_void_p()
+    assert lib.cz_tables_create(C.byref(desc), 0, C.byref(h)) == 0
+    ptab = compile_policy_tables(t)
+    pdesc, pkeep = _native.make_policy_desc(t, ptab)
+    p = C.c_void_p()
+    assert lib.cz_policy_create(None, C.byref(pdesc), C.byref(p)) == -1
+    pdesc.num_variants += 1
+    assert lib.cz_policy_create(h, C.byref(pdesc), C.byref(p)) == -1 and b"num_variants" in lib.cz_last_error()
+    pdesc.num_variants -= 1
+    bad = ptab["first_step"].copy()
+    bad[0, 9, 10] = 7                                  # not a movement action
+    bdesc, bkeep = _native.make_policy_desc(t, dict(ptab, first_step=bad))
+    assert lib.cz_policy_create(h, C.byref(bdesc), C.byref(p)) == -1 and b"first_step" in lib.cz_last_error()
+    assert lib.cz_policy_create(h, C.byref(pdesc), C.byref(p)) == 0 and p.value
+    n = 40
+    state = torch.zeros((t.rows, n), dtype=torch.int32, device="cuda")
+    act = torch.zeros((n, 2), dtype=torch.uint8, device="cuda")
+    assert lib.cz_policy_act(p, None, None, act.data_ptr(), None, n, None) == -1
+    assert lib.cz_policy_act(p, state.data_ptr(), None, None, None, n, None) == -1
+    assert lib.cz_policy_act(p, state.data_ptr(), None, act.data_ptr(), None, -1, None) == -1
+    assert lib.cz_policy_act(p, state.data_ptr(), None, act.data_ptr(), None, 0, None) == 0
+    assert lib.cz_policy_destroy(p) == 0 and lib.cz_policy_destroy(None) == 0
+    obs32 = torch.zeros((n, 2, t.obs_len + 4), dtype=torch.float32, device="cuda")
+    assert lib.cz_observe_f32(h, state.data_ptr(), None, n, None) == -1
+    assert lib.cz_observe_f32(h, state.data_ptr(), obs32.data_ptr() + 4, n, None) == -1 and b"aligned" in lib.cz_last_error()
+    assert lib.cz_observe_f32(h, state.data_ptr(), obs32.data_ptr(), 0, None) == 0
+    assert lib.cz_observe(h, state.data_ptr(), None, n, None) == -1       # the f64 observer has no NULL mode
+    assert lib.cz_pipeline_wait_state(None, None) == -1
+    assert lib.cz_pipeline_wait_state(h, None) == 0                      # pipeline never started: nothing to wait for
+    assert lib.cz_tables_destroy(h) == 0
