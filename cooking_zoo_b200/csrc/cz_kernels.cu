@@ -33,6 +33,7 @@
 #endif
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
+#define CZ_FLAG_TILE_SHIFT 8  // internal bits 8-10 of the kernel's `flags`: log2(environments per warp)
 enum { OBS_TMA = 0, OBS_STG = 1, OBS_NONE = 2 };  // OBS_NONE: dynamics only (pipelined step: the observe kernel follows)
 #ifndef CZ_STAGE_SETS
 #define CZ_STAGE_SETS 1  // sets of staging rows per warp (2 = double buffered; measured: no gain, profiles/r01_notes.md)
@@ -337,15 +338,18 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
   const double* syl = bs->ylut + (T.H - 1);
   __syncthreads();
 
-  const int n_tiles = (n_envs + 31) >> 5;
+  // a tile is 32 environments unless the batch is too small to give every SM scheduler a warp: then the library
+  // shrinks it (CZ_FLAG_TILE_SHIFT bits of `flags`) so that the per-warp observation loop gets shorter
+  const int ts = (int)((flags >> CZ_FLAG_TILE_SHIFT) & 7u), TS = 1 << ts;
+  const int n_tiles = (n_envs + TS - 1) >> ts;
   const int warps_total = gridDim.x * CZ_WARPS_PER_BLOCK;
   const size_t N = (size_t)n_envs;
   const uint32_t* misc = state + (size_t)(D + A) * N;
   uint32_t* misc_out = state_out + (size_t)(D + A) * N;  // == misc unless the step is pipelined (ping-pong state)
 
   for (int tile = blockIdx.x * CZ_WARPS_PER_BLOCK + warp; tile < n_tiles; tile += warps_total) {
-    const int env = tile * 32 + lane;
-    const bool valid = env < n_envs;
+    const int env = (tile << ts) + lane;
+    const bool valid = lane < TS && env < n_envs;
     EnvRegs e;
     e.o = ws->obj + lane;
     e.ag = ws->ag + lane;
@@ -437,8 +441,8 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
     // hoisted above the dynamics (where they would be spilled: registers are capped for 28 warps/SM).
     int lane_o = lane;
     asm volatile("" : "+r"(lane_o));
-    const int n_here = min(32, n_envs - tile * 32);
-    double* genv = obs + (size_t)tile * 32 * A * T.L;
+    const int n_here = min(TS, n_envs - (tile << ts));
+    double* genv = obs + ((size_t)tile << ts) * A * T.L;
     const size_t env_doubles = (size_t)A * T.L;
     const int tab2 = T.tab_len >> 1, L2 = T.L >> 1;
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
@@ -876,8 +880,18 @@ extern "C" int cz_tables_destroy(cz_tables* t) {
 
 extern "C" int cz_state_rows(const cz_tables* t) { return t ? t->dev.rows : CZ_EINVAL; }
 
-static int cz_grid(const cz_tables* t, int n_envs) {
-  int tiles = (n_envs + 31) / 32;
+// Environments per warp (log2): 32 for large batches; halved while the batch leaves SM schedulers without a warp
+// (a step's latency is one warp's dynamics plus its observation loop, and the loop scales with the tile).
+static int cz_tile_shift(const cz_tables* t, int n_envs) {
+  int ts = 5;
+  while (ts > 0 && ((n_envs + (1 << (ts - 1)) - 1) >> (ts - 1)) <= t->num_sms * 8) --ts;
+  const char* f = getenv("CZ_TILE_SHIFT");
+  if (f && f[0] >= '0' && f[0] <= '5') ts = f[0] - '0';
+  return ts;
+}
+
+static int cz_grid(const cz_tables* t, int n_envs, int ts) {
+  int tiles = (n_envs + (1 << ts) - 1) >> ts;
   int blocks = (tiles + CZ_WARPS_PER_BLOCK - 1) / CZ_WARPS_PER_BLOCK;
   int cap = t->num_sms * 8;  // persistent tile loop beyond this many blocks
   return blocks < cap ? blocks : cap;
@@ -901,7 +915,9 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
     size_t want = (size_t)(227 * 1024) / t->pipe_dyn_blocks - 1024;
     if (want > smem && want <= t->smem_optin) smem = want;
   }
-  int grid = cz_grid(t, n_envs);
+  const int ts = cz_tile_shift(t, n_envs);
+  int grid = cz_grid(t, n_envs, ts);
+  flags = (flags & ~(7u << CZ_FLAG_TILE_SHIFT)) | ((uint32_t)ts << CZ_FLAG_TILE_SHIFT);
   cudaStream_t s = (cudaStream_t)stream;
 #define CZ_GO(O, NA)                                                                                                  \
   cz_env_kernel<MODE, O, NA><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, state_out, actions, layout_ids, recipe_ids, mask, obs, \
