@@ -190,6 +190,10 @@ __device__ __forceinline__ uint32_t pol_cook(const CzDev& T, const CzPolicyDev& 
     for (int j = pick + 1; j < n; ++j) {
       if (!(kids >> j & 1u)) continue;
       const uint32_t kid = __ldg(T.recipe_nodes + rid * CZ_MAX_NODES + j);
+      if (kid & 256u) {  // static child type (no_recipe's Floor): cells are unique, membership is one mask test
+        count += (int)((__ldg(T.static_masks + variant * 8 + (kid & 7u)) & near) >> mloc & 1ull);
+        continue;
+      }
       const PolList kl = pol_list(T, P, variant, kid);
       for (int q = 0; q < kl.n; ++q) {
         uint32_t loc, rec;
@@ -207,6 +211,18 @@ __device__ __forceinline__ uint32_t pol_cook(const CzDev& T, const CzPolicyDev& 
   for (int j = pick + 1; j < n; ++j) {
     if (!(kids >> j & 1u)) continue;
     const uint32_t kid = __ldg(T.recipe_nodes + rid * CZ_MAX_NODES + j);
+    if (kid & 256u) {
+      // static child type: when the cook stands on such a cell (distance 0, and only that cell is at distance 0) the
+      // list walk can only return it, unless an earlier candidate already sits at distance 0
+      const uint64_t cells = __ldg(T.static_masks + variant * 8 + (kid & 7u)) & near;
+      if ((cells >> me & 1ull) && main_cell >= 0 && (int)me != main_cell) {
+        if (0 < target_d) {
+          target_d = 0;
+          target = (int)me;
+        }
+        continue;
+      }
+    }
     const PolList kl = pol_list(T, P, variant, kid);
     for (int q = 0; q < kl.n; ++q) {
       uint32_t loc, rec;
