@@ -291,6 +291,72 @@ class BatchedCookingEnv:
                         "t": np.int32(int(misc[ROW_TINFO]) & 0xFFFFF)})
         return out if env is None else out[0]
 
+    def symbolic_observation(self, env):
+        """The reference's "symbolic" observation (cooking_env.py:279-284: world_objects by class name plus
+        "Agent") of one environment, rebuilt on the host from the device state — for debugging / rendering, not
+        a hot path.  Objects are plain records: name, location, content (list of records, in content order),
+        and the class's state attributes (chop_state / blend_state / free for food, status / toggle for
+        appliances, orientation / holding / active for agents)."""
+        from types import SimpleNamespace as Rec
+        from . import entities as E
+        from .policy import compile_policy_tables
+        t = self.tables
+        if getattr(self, "_static_lists", None) is None:
+            self._static_lists = compile_policy_tables(t)
+        lists, lens = self._static_lists["lists"], self._static_lists["list_len"]
+        col = self.state[:, env].cpu().numpy().astype(np.uint32)
+        D, A = t.num_dyn_slots, t.num_agents
+        misc = col[D + A:]
+        sb, var = int(misc[ROW_SBITS]), int(misc[ROW_VARIANT])
+        out = {}
+        by_cell = {}
+        code_name = {et.static_code: n for n, et in E.ENTITY_TYPES.items() if et.kind == "static"}
+        special = {E.ST_CUTBOARD: 0, E.ST_BLENDER: 1, E.ST_SWITCH: 2, E.ST_BLOCK: 3}
+        for code, name in code_name.items():
+            for k in range(int(lens[var, code])):
+                cell = int(lists[var, code, k])
+                r = Rec(name=name, location=(cell & 7, cell >> 3), content=[])
+                if code in special:
+                    sp = int(t.grid[var, cell]) >> 4
+                    if code == E.ST_CUTBOARD:
+                        r.status = "READY" if sb >> sp & 1 else "NOT_USABLE"
+                    elif code == E.ST_BLENDER:
+                        r.status = "READY" if sb >> (4 + sp) & 1 else "NOT_USABLE"
+                        r.toggle = bool(sb >> (8 + sp) & 1)
+                    elif code == E.ST_SWITCH:
+                        r.switch_active = bool(sb >> (12 + sp) & 1)
+                    else:
+                        r.walkable = bool(sb >> (16 + sp) & 1)
+                out.setdefault(name, []).append(r)
+                by_cell[cell] = r
+        recs = {}
+        for tid, name in enumerate(t.dyn_types):
+            fl = int(t.type_flags[tid])
+            for s_ in range(int(t.type_base[tid]), int(t.type_base[tid]) + int(t.type_count[tid])):
+                o = int(col[s_])
+                if not o >> 6 & 1:
+                    continue
+                r = Rec(name=name, location=(o & 7, (o >> 3) & 7), content=[], free=bool(o >> 9 & 1))
+                if fl & E.TF_CHOP:
+                    r.chop_state = "CHOPPED" if o >> 7 & 1 else "FRESH"
+                if fl & E.TF_BLEND:
+                    r.blend_state = "MASHED" if o >> 8 & 1 else "FRESH"
+                recs[s_] = (r, o)
+                out.setdefault(name, []).append(r)
+        agents = []
+        for i in range(A):
+            a = int(col[D + i])
+            agents.append(Rec(name=f"agent-{i + 1}", location=(a & 7, (a >> 3) & 7), orientation=(a >> 6) & 7,
+                              holding=recs[(a >> 10) & 31][0] if a >> 9 & 1 else None, active=bool(a >> 15 & 1)))
+        out["Agent"] = agents
+        for s_, (r, o) in sorted(recs.items(), key=lambda kv: (kv[1][1] >> 17) & 63):      # content order = position
+            ck, cid = (o >> 10) & 3, (o >> 12) & 31
+            if ck == 1:
+                by_cell[(o & 63)].content.append(r)
+            elif ck == 2:
+                recs[cid][0].content.append(r)
+        return out
+
     def teleport(self, env, agent, x, y):
         """Agent.move_to (world_objects.py:794-797) on one environment — test helper."""
         t = self.tables

@@ -71,3 +71,43 @@ def test_gym_single_and_multi_agent_shapes():
     assert trunc == [True, True] and term == [False, False]
     assert infos[0]["termination_info"] == "Terminating because 25 timesteps passed"
     ma.close()
+
+
+def test_symbolic_observation_rebuilt_from_device_state_matches_the_oracle_world():
+    """the "symbolic" view (world_objects by class name + Agent) of a device environment"""
+    import numpy as np
+    import torch
+    from oracle.cz_oracle import OracleEnv
+    from cooking_zoo_b200 import BatchedCookingEnv
+    recipes = ["TomatoLettuceSalad", "CarrotBanana"]
+    n = 6
+    env = BatchedCookingEnv(n, "coop_test", "example", 2, 300, recipes, end_condition_all_dishes=True,
+                            action_scheme="scheme3", layout_pool_size=8)
+    lids = np.arange(n, dtype=np.int32)
+    env.reset(layout_ids=lids)
+    oracles = [OracleEnv(env.tables.layouts[l], recipes, 300, end_condition_all_dishes=True) for l in lids]
+
+    for t in range(120):
+        act, _ = env.heuristic_actions()           # the cook moves things around: plates get filled, food chopped
+        env.step(act)
+        a = act.cpu().numpy()
+        for k, orc in enumerate(oracles):
+            orc.step(a[k])
+        if t % 10 != 9:
+            continue
+        for k, orc in enumerate(oracles):
+            sym = env.symbolic_observation(k)
+            for typ, lst in orc.by_type.items():
+                got = sym.get(typ, [])
+                assert [r.location for r in got] == [(o.x, o.y) for o in lst], (t, k, typ)
+                for r, o in zip(got, lst):
+                    assert [(c.name, c.location) for c in r.content] == [(c.type, (c.x, c.y)) for c in o.content], (t, k, typ)
+                    if hasattr(r, "chop_state"):
+                        assert (r.chop_state == "CHOPPED") == o.chopped and r.free == o.free
+                    if hasattr(r, "blend_state"):
+                        assert (r.blend_state == "MASHED") == (o.blend == 2)
+            for r, ag in zip(sym["Agent"], orc.agents):
+                assert r.location == (ag.x, ag.y) and r.orientation == ag.orientation
+                assert (r.holding is None) == (ag.holding is None)
+                if ag.holding is not None:
+                    assert (r.holding.name, r.holding.location) == (ag.holding.type, (ag.holding.x, ag.holding.y))
