@@ -51,21 +51,24 @@ struct CzDev {
 // use the L1 is only ~14 KB, so a __ldg of these is an L2 round trip in the middle of a
 // dependent chain).  Kernels instantiated with FAST=true require V <= CZ_SV and B <= CZ_SB and
 // read the shared copy; FAST=false reads global memory.
-#define CZ_SV 4
+#define CZ_SV 16
 #define CZ_SB 16
+struct VarTabs {  // per static variant (272 B); only the V variants of the tables occupy shared memory
+  uint64_t static_masks[8];
+  uint8_t grid[64];
+  uint8_t scan_order[CZ_MAX_DYN];
+  uint8_t special_cells[4 * CZ_MAX_SPECIAL];
+  uint8_t static_cells[CZ_MAX_STATIC_SLOTS];
+};
 struct SmemTabs {
-  uint64_t static_masks[CZ_SV][8];
   uint32_t recipe_nodes[CZ_SB][CZ_MAX_NODES];
   uint32_t recipe_spans[CZ_SB][CZ_MAX_NODES];
-  uint8_t grid[CZ_SV][64];
-  uint8_t scan_order[CZ_SV][CZ_MAX_DYN];
-  uint8_t special_cells[CZ_SV][4 * CZ_MAX_SPECIAL];
-  uint8_t static_cells[CZ_SV][CZ_MAX_STATIC_SLOTS];
   uint8_t slot_tf[CZ_MAX_DYN];  // type_flags[slot_type[s]]
   uint8_t slot_type[CZ_MAX_DYN];
   uint8_t type_base[CZ_MAX_TYPES];
   uint8_t type_count[CZ_MAX_TYPES];
   uint8_t recipe_len[CZ_SB];
+  VarTabs var[1];  // [V], V <= CZ_SV
 };
 
 // static kinds (grid low nibble) — cooking_zoo_b200/entities.py ST_*
@@ -113,13 +116,13 @@ enum { FV_NONE = 0, FV_ONE, FV_CHOP, FV_CHOPBLEND, FV_AGENT, FV_SWITCH, FV_BLOCK
 #define TI_DONE (1u << 20)
 #define TI_NLIVE(x) (((x) >> 21) & 7u)
 
-#define TAB_GRID(v, c) (FAST ? (uint32_t)st->grid[v][c] : (uint32_t)__ldg(T.grid + (v) * 64 + (c)))
-#define TAB_SCAN(v, k) (FAST ? (uint32_t)st->scan_order[v][k] : (uint32_t)__ldg(T.scan_order + (v) * T.D + (k)))
+#define TAB_GRID(v, c) (FAST ? (uint32_t)st->var[v].grid[c] : (uint32_t)__ldg(T.grid + (v) * 64 + (c)))
+#define TAB_SCAN(v, k) (FAST ? (uint32_t)st->var[v].scan_order[k] : (uint32_t)__ldg(T.scan_order + (v) * T.D + (k)))
 #define TAB_SPECIAL(v, kind, k) \
-  (FAST ? (uint32_t)st->special_cells[v][(kind) * CZ_MAX_SPECIAL + (k)] \
+  (FAST ? (uint32_t)st->var[v].special_cells[(kind) * CZ_MAX_SPECIAL + (k)] \
                : (uint32_t)__ldg(T.special_cells + ((v) * 4 + (kind)) * CZ_MAX_SPECIAL + (k)))
-#define TAB_SCELL(v, i) (FAST ? (uint32_t)st->static_cells[v][i] : (uint32_t)__ldg(T.static_cells + (v) * T.S + (i)))
-#define TAB_SMASK(v, k) (FAST ? st->static_masks[v][k] : __ldg(T.static_masks + (v) * 8 + (k)))
+#define TAB_SCELL(v, i) (FAST ? (uint32_t)st->var[v].static_cells[i] : (uint32_t)__ldg(T.static_cells + (v) * T.S + (i)))
+#define TAB_SMASK(v, k) (FAST ? st->var[v].static_masks[k] : __ldg(T.static_masks + (v) * 8 + (k)))
 #define TAB_RNODE(b, k) (FAST ? st->recipe_nodes[b][k] : __ldg(T.recipe_nodes + (b) * CZ_MAX_NODES + (k)))
 #define TAB_RSPAN(b, k) (FAST ? st->recipe_spans[b][k] : __ldg(T.recipe_spans + (b) * CZ_MAX_NODES + (k)))
 #define TAB_RLEN(b) (FAST ? (uint32_t)st->recipe_len[b] : (uint32_t)__ldg(T.recipe_len + (b)))

@@ -294,7 +294,11 @@ struct BlockSmem {
   SmemTabs tabs;
 };
 __host__ __device__ inline size_t cz_warp_words(int D, int A) { return (size_t)(D + A) * OSTRIDE + 32 * 3; }
-__host__ __device__ inline size_t cz_block_smem_head() { return (sizeof(BlockSmem) + 15) & ~(size_t)15; }
+// bytes of the image actually used by tables with V static variants (the VarTabs array is the tail of the struct)
+__host__ __device__ inline size_t cz_block_smem_head(int V) {
+  const int nv = V < 1 ? 1 : (V > CZ_SV ? 1 : V);  // tables with more variants run the generic kernels (global-memory tables)
+  return (sizeof(BlockSmem) + (size_t)(nv - 1) * sizeof(VarTabs) + 15) & ~(size_t)15;
+}
 
 template <int MODE, int OBS, int NA>
 __global__ void __launch_bounds__(CZ_THREADS, OBS == 2 ? CZ_DYN_MIN_BLOCKS : CZ_MIN_BLOCKS)
@@ -315,7 +319,7 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
   WarpSmem wsv;
   WarpSmem* ws = &wsv;
   {
-    uint32_t* base = reinterpret_cast<uint32_t*>(smem_raw + cz_block_smem_head()) + (size_t)warp * cz_warp_words(D, A);
+    uint32_t* base = reinterpret_cast<uint32_t*>(smem_raw + cz_block_smem_head(T.V)) + (size_t)warp * cz_warp_words(D, A);
     wsv.obj = base;
     wsv.ag = base + D * OSTRIDE;
     wsv.sbits = wsv.ag + A * OSTRIDE;
@@ -324,11 +328,11 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
   }
   // staging (the computed span of A rows) lives after the per-warp words, 16-byte aligned
   const size_t row_bytes = ((size_t)T.stage_len * 8 + 15) & ~(size_t)15;
-  unsigned char* stage_base = smem_raw + ((cz_block_smem_head() + cz_warp_words(D, A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15);
+  unsigned char* stage_base = smem_raw + ((cz_block_smem_head(T.V) + cz_warp_words(D, A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15);
   double* stage = reinterpret_cast<double*>(stage_base + (size_t)warp * CZ_STAGE_SETS * A * row_bytes);
   const int row_stride = (int)(row_bytes >> 3);
   // read-only block image: one 16-byte load per thread
-  for (int i = threadIdx.x; i < (int)(sizeof(BlockSmem) / 16); i += CZ_THREADS)
+  for (int i = threadIdx.x; i < (int)(cz_block_smem_head(T.V) / 16); i += CZ_THREADS)
     reinterpret_cast<uint4*>(bs)[i] = __ldg(reinterpret_cast<const uint4*>(T.blob) + i);
   // never-occupied slots stay zero: the staging rows are cleared once and only live slots are rewritten
   if (OBS != OBS_NONE)
@@ -666,7 +670,7 @@ static int upload(cz_tables* t, const Tp* host, size_t count, const Tp** out) {
 
 static size_t cz_smem_bytes(const CzDev& T) {
   size_t row_bytes = ((size_t)T.stage_len * 8 + 15) & ~(size_t)15;
-  return ((cz_block_smem_head() + cz_warp_words(T.D, T.A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15) +
+  return ((cz_block_smem_head(T.V) + cz_warp_words(T.D, T.A) * 4 * CZ_WARPS_PER_BLOCK + 15) & ~(size_t)15) +
          (size_t)CZ_WARPS_PER_BLOCK * CZ_STAGE_SETS * T.A * row_bytes;
 }
 
@@ -718,7 +722,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   const char* p = getenv("CZ_OBS_PATH");
   t->obs_path = (p && !strcmp(p, "stg")) ? OBS_STG : OBS_TMA;
   if (d->obs_len & 1) t->obs_path = OBS_STG;  // bulk copies need 16-byte rows
-  static_assert(sizeof(BlockSmem) % 16 == 0, "block image is copied in 16-byte units");
+  static_assert(sizeof(VarTabs) % 16 == 0 && sizeof(BlockSmem) % 8 == 0, "block image is copied in 16-byte units");
   CzDev& T = t->dev;
   T.W = d->width; T.H = d->height; T.A = d->num_agents; T.R = d->num_recipes; T.D = d->num_dyn_slots;
   T.S = d->num_static_slots; T.T = d->num_types; T.L = d->obs_len;
@@ -806,18 +810,21 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   }
 #undef UP
   if (rc == CZ_OK) {  // read-only shared-memory image of a block: LUTs + the small tables
-    static BlockSmem img;
-    memset(&img, 0, sizeof(img));
+    const size_t img_bytes = cz_block_smem_head(T.V);
+    static unsigned char img_buf[sizeof(BlockSmem) + CZ_SV * sizeof(VarTabs) + 16];
+    memset(img_buf, 0, sizeof(img_buf));
+    BlockSmem& img = *reinterpret_cast<BlockSmem*>(img_buf);
     for (int i = 0; i < 2 * T.W - 1; ++i) img.xlut[i] = d->xlut[i];
     for (int i = 0; i < 2 * T.H - 1; ++i) img.ylut[i] = d->ylut[i];
     SmemTabs& w = img.tabs;
-    const int nv = T.V < CZ_SV ? T.V : CZ_SV, nb = T.B < CZ_SB ? T.B : CZ_SB;
+    const int nv = T.V <= CZ_SV ? T.V : 1, nb = T.B < CZ_SB ? T.B : CZ_SB;
     for (int v = 0; v < nv; ++v) {
-      for (int k = 0; k < 8; ++k) w.static_masks[v][k] = d->static_masks[v * 8 + k];
-      for (int c = 0; c < 64; ++c) w.grid[v][c] = d->grid[v * 64 + c];
-      for (int k = 0; k < T.D; ++k) w.scan_order[v][k] = d->scan_order[v * T.D + k];
-      for (int k = 0; k < 4 * CZ_MAX_SPECIAL; ++k) w.special_cells[v][k] = d->special_cells[v * 4 * CZ_MAX_SPECIAL + k];
-      for (int k = 0; k < T.S; ++k) w.static_cells[v][k] = d->static_cells[v * T.S + k];
+      VarTabs& x = w.var[v];
+      for (int k = 0; k < 8; ++k) x.static_masks[k] = d->static_masks[v * 8 + k];
+      for (int c = 0; c < 64; ++c) x.grid[c] = d->grid[v * 64 + c];
+      for (int k = 0; k < T.D; ++k) x.scan_order[k] = d->scan_order[v * T.D + k];
+      for (int k = 0; k < 4 * CZ_MAX_SPECIAL; ++k) x.special_cells[k] = d->special_cells[v * 4 * CZ_MAX_SPECIAL + k];
+      for (int k = 0; k < T.S; ++k) x.static_cells[k] = d->static_cells[v * T.S + k];
     }
     for (int b = 0; b < nb; ++b) {
       for (int k = 0; k < CZ_MAX_NODES; ++k) {
@@ -828,8 +835,8 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     }
     for (int i = 0; i < T.D; ++i) { w.slot_type[i] = d->slot_type[i]; w.slot_tf[i] = d->type_flags[d->slot_type[i]]; }
     for (int i = 0; i < T.T; ++i) { w.type_base[i] = d->type_base[i]; w.type_count[i] = d->type_count[i]; }
-    const BlockSmem* dimg = nullptr;
-    rc = upload(t, &img, 1, &dimg);
+    const unsigned char* dimg = nullptr;
+    rc = upload(t, img_buf, img_bytes, &dimg);
     T.blob = dimg;
   }
   if (rc != CZ_OK) { cz_tables_destroy(t); return rc; }

@@ -105,6 +105,23 @@ def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_sche
     if W > 8 or H > 8 or W * H > MAX_CELLS:
         raise ValueError("levels larger than 8x8 are not supported by the kernels")
 
+    # get_objects_at scans the dynamic types in world_objects insertion order (cooking_world.py:232-241).  Only the
+    # relative order of the types a layout actually holds matters, so when every pooled layout's insertion order is a
+    # subsequence of the level file's first-appearance order, that one order serves all of them (OPTIONAL objects then
+    # do not multiply the static variants).
+    level_order = []
+    for entry in level_object.get("DYNAMIC_OBJECTS", []):
+        name = next(iter(entry))
+        if name not in level_order:
+            level_order.append(name)
+
+    def _subsequence(sub, full):
+        it = iter(full)
+        return all(x in it for x in sub)
+
+    shared_order = all(_subsequence([n for n, locs in lay["objects"] if E.entity(n).kind == "dynamic"], level_order)
+                       for lay in layouts)
+
     variants, variant_of = [], {}
     pool = np.zeros((len(layouts), rows), np.uint32)
     for li, lay in enumerate(layouts):
@@ -147,6 +164,8 @@ def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_sche
                 for k, (x, y) in enumerate(locs):
                     pool[li, type_base[tid] + k] = pack_obj(x, y)
         # scan order: present types in world_objects insertion order, then the rest
+        if shared_order:
+            dyn_order = [n for n in level_order if n in type_id]
         order = dyn_order + [n for n in dyn_types if n not in dyn_order]
         scan = np.array([type_base[type_id[n]] + k for n in order for k in range(type_count[type_id[n]])],
                         np.uint8)
