@@ -554,6 +554,17 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
 #define CZ_ENVS_MIN_BLOCKS 8
 #endif
 
+// A static slot among the computed ones (live Switch / Block, world_objects.py:174,221): its record is the cell with
+// the present bit, its one state flag comes from the SBITS word.  Shared by the warp-per-environment row writers.
+__device__ __forceinline__ void cz_live_static(const CzDev& T, const uint32_t* __restrict__ state, size_t N, int env, int A,
+                                               uint32_t var, uint32_t idx, uint32_t& rec, uint32_t& fb4) {
+  const uint32_t cell = __ldg(T.static_cells + var * T.S + idx);
+  rec = cell != 0xFFu ? (cell | O_PRESENT) : 0u;
+  const uint32_t g = __ldg(T.grid + var * 64 + (rec & 63u));
+  const uint32_t sbits = __ldg(state + (size_t)(T.D + A + CZ_ROW_SBITS) * N + env);
+  fb4 = ((g & 15u) == ST_SWITCH ? (sbits >> (12 + (g >> 4))) : (sbits >> (16 + (g >> 4)))) & 1u;
+}
+
 template <int NA>
 __global__ void __launch_bounds__(32 * ENVS_WARPS, CZ_ENVS_MIN_BLOCKS)
 cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, double* __restrict__ obs, int n_envs) {
@@ -568,11 +579,13 @@ cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__
 
   // this lane's (observer, slot) pair and the state words it needs
   const LaneSlot ls = cz_lane_slot_packed(T, lane);
-  const bool is_agent = ls.kind == 2;
+  const bool is_agent = ls.kind == 2, is_static = ls.kind == 0;
   uint32_t rec = 0;
-  if (ls.off >= 0) rec = __ldg(state + (size_t)(is_agent ? D + ls.idx : ls.idx) * N + env);
+  if (ls.off >= 0 && !is_static) rec = __ldg(state + (size_t)(is_agent ? D + ls.idx : ls.idx) * N + env);
   const uint32_t me = __ldg(state + (size_t)(D + ls.agent) * N + env);           // this pair's observer
   const uint32_t var = __ldg(state + (size_t)(D + NA + CZ_ROW_VARIANT) * N + env);
+  uint32_t static_fb = 0;
+  if (ls.off >= 0 && is_static) cz_live_static(T, state, N, env, NA, var, ls.idx, rec, static_fb);
   const double2* tab = reinterpret_cast<const double2*>(T.obs_table) + (size_t)var * 64 * tab2 + lane;
   double2* g2 = reinterpret_cast<double2*>(obs + (size_t)env * NA * T.L);
   // never-occupied slots are zeros: clear the staging rows, then fill the live slots
@@ -581,7 +594,7 @@ cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__
   if (ls.off >= 0) {
     const bool present = is_agent || (rec & O_PRESENT);
     const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
-    const uint32_t fb4 = is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2);
+    const uint32_t fb4 = is_static ? static_fb : (is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2));
     const uint32_t one = 1u << (ls.flen - 1);
     const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
     const bool self = is_agent && (int)ls.idx == ls.agent;

@@ -122,11 +122,13 @@ cz_obs32_fast_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict
   float2* stage2 = reinterpret_cast<float2*>(smem_f32) + (size_t)warp * NA * L2;  // NA * L floats, 16-byte aligned
 
   const LaneSlot ls = cz_lane_slot_packed(T, lane);  // ls.off is relative to stage_lo
-  const bool is_agent = ls.kind == 2;
+  const bool is_agent = ls.kind == 2, is_static = ls.kind == 0;
   uint32_t rec = 0;
-  if (ls.off >= 0) rec = __ldg(state + (size_t)(is_agent ? D + ls.idx : ls.idx) * N + env);
+  if (ls.off >= 0 && !is_static) rec = __ldg(state + (size_t)(is_agent ? D + ls.idx : ls.idx) * N + env);
   const uint32_t me = __ldg(state + (size_t)(D + ls.agent) * N + env);
   const uint32_t var = __ldg(state + (size_t)(D + NA + CZ_ROW_VARIANT) * N + env);
+  uint32_t static_fb = 0;
+  if (ls.off >= 0 && is_static) cz_live_static(T, state, N, env, NA, var, ls.idx, rec, static_fb);
   const float2* tab = reinterpret_cast<const float2*>(T.obs_table32) + (size_t)var * 64 * tab2 + lane;
   // table segments of every row: loads first
   float2 v0[NA], v1[NA];
@@ -152,7 +154,7 @@ cz_obs32_fast_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict
   if (ls.off >= 0) {
     const bool present = is_agent || (rec & O_PRESENT);
     const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
-    const uint32_t fb4 = is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2);
+    const uint32_t fb4 = is_static ? static_fb : (is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2));
     const uint32_t one = 1u << (ls.flen - 1);
     const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
     const bool self = is_agent && (int)ls.idx == ls.agent;

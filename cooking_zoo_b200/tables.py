@@ -319,6 +319,32 @@ def _compile_obs_plan(t, obs_slots):
             runs.append((a, b - a))
         j = k
     runs = sorted(sorted(runs, key=lambda r: -r[1])[:2]) if L % 2 == 0 else []
+
+    def n_ranges_and_slots(kept):
+        cover = np.zeros(L, bool)
+        for a, n in kept:
+            cover[a:a + n] = True
+        edges = np.flatnonzero(np.diff(np.concatenate([[True], cover, [True]]).astype(np.int8)) == -1)
+        live = 0
+        for off, fv, kind, idx in obs_slots:
+            if cover[off:off + E.FV_LEN[fv]].all():
+                continue
+            if kind == 2 and idx >= t.num_agents:
+                continue
+            if kind == 0 and bool((t.static_cells[:, idx] == 0xFF).all()):
+                continue
+            live += 1
+        return len(edges), live
+
+    # the specialised kernels want ONE computed range and at most 32 (observer, slot) pairs: a short table run that
+    # splits the computed part (e.g. the Deliversquare slots behind switch_test's live Switch / Block slots) is
+    # better computed than copied
+    if len(runs) == 2 and n_ranges_and_slots(runs)[0] > 1:
+        for kept in ([max(runs, key=lambda r: r[1])], [min(runs, key=lambda r: r[1])]):
+            nr, live = n_ranges_and_slots(kept)
+            if nr == 1 and live * t.num_agents <= 32:
+                runs = kept
+                break
     in_table = np.zeros(L, bool)
     for a, n in runs:
         in_table[a:a + n] = True

@@ -146,9 +146,11 @@ def test_auto_reset_and_shard_independence():
                 assert_obs_equal(np.stack([orc.observe(i) for i in range(2)]), o[k].cpu().numpy(), f"autoreset env {k}")
 
 
-def test_pipelined_step_is_bit_identical_to_the_in_place_step():
-    """throughput mode (cz_step_pipelined: two streams, ping-pong state) does the same work as cz_step"""
-    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=30,
+@pytest.mark.parametrize("level", ["coop_test", "switch_test", "coexistence_test"])
+def test_pipelined_step_is_bit_identical_to_the_in_place_step(level):
+    """throughput mode (cz_step_pipelined: two streams, ping-pong state) does the same work as cz_step;
+    switch_test adds live Switch / Block slots to the observation writer, coexistence_test 16 static variants"""
+    cfg = dict(level=level, meta_file="example", num_agents=2, max_steps=30,
                recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
     n = 5000
     a = _make(n, cfg, auto_reset=True, seed=3, layout_pool_size=64)
