@@ -565,8 +565,52 @@ __device__ __forceinline__ void cz_live_static(const CzDev& T, const uint32_t* _
   fb4 = ((g & 15u) == ST_SWITCH ? (sbits >> (12 + (g >> 4))) : (sbits >> (16 + (g >> 4)))) & 1u;
 }
 
+// State words of one (observer, slot) pair: the slot's record (or cell | present for a static slot) and its feature bits.
+struct PairRegs {
+  uint32_t rec, me, static_fb;
+};
+
 template <int NA>
-__global__ void __launch_bounds__(32 * ENVS_WARPS, CZ_ENVS_MIN_BLOCKS)
+__device__ __forceinline__ PairRegs cz_pair_load(const CzDev& T, const uint32_t* __restrict__ state, size_t N, int env,
+                                                 uint32_t var, const LaneSlot& ls) {
+  PairRegs p;
+  p.rec = 0;
+  p.static_fb = 0;
+  const bool is_agent = ls.kind == 2, is_static = ls.kind == 0;
+  if (ls.off >= 0 && !is_static) p.rec = __ldg(state + (size_t)(is_agent ? T.D + ls.idx : ls.idx) * N + env);
+  p.me = __ldg(state + (size_t)(T.D + ls.agent) * N + env);  // this pair's observer
+  if (ls.off >= 0 && is_static) cz_live_static(T, state, N, env, NA, var, ls.idx, p.rec, p.static_fb);
+  return p;
+}
+
+// [x, y, flags..., 1] of the pair into its staging row
+__device__ __forceinline__ void cz_pair_store(const CzDev& T, const LaneSlot& ls, const PairRegs& p, double2* stage, int stage2) {
+  if (ls.off < 0) return;
+  const bool is_agent = ls.kind == 2, is_static = ls.kind == 0;
+  const uint32_t rec = p.rec, me = p.me;
+  const bool present = is_agent || (rec & O_PRESENT);
+  const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+  const uint32_t fb4 = is_static ? p.static_fb : (is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2));
+  const uint32_t one = 1u << (ls.flen - 1);
+  const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
+  const bool self = is_agent && (int)ls.idx == ls.agent;
+  const int x = rec & 7u, y = (rec >> 3) & 7u;
+  // (x - ax) / W from the host-divided table; the observer's own entry is x / W (cooking_env.py:364-368)
+  double X = __ldg(T.xlut + (x - (self ? 0 : (int)(me & 7u)) + T.W - 1));
+  double Y = __ldg(T.ylut + (y - (self ? 0 : (int)((me >> 3) & 7u)) + T.H - 1));
+  if (!present) { X = 0.0; Y = 0.0; }
+  double* out = reinterpret_cast<double*>(stage + ls.agent * stage2) + ls.off;
+  out[0] = X;
+  out[1] = Y;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+    if (k < (int)ls.flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, (fb >> k & 1u) ? 0x3FF00000u : 0u);
+}
+
+// TWO = false: at most 32 (observer, slot) pairs, one per lane.  TWO = true: up to 64 pairs (3-4 agent kitchens),
+// a lane owns pairs `lane` and `lane + 32`.
+template <int NA, bool TWO>
+__global__ void __launch_bounds__(32 * ENVS_WARPS, (TWO || NA >= 3) ? 5 : CZ_ENVS_MIN_BLOCKS)
 cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, double* __restrict__ obs, int n_envs) {
   extern __shared__ __align__(16) unsigned char smem_rows[];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -577,39 +621,23 @@ cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__
   const int stage2 = (T.stage_len + 1) >> 1;  // double2 per staging row
   double2* stage = reinterpret_cast<double2*>(smem_rows) + (size_t)warp * NA * stage2;
 
-  // this lane's (observer, slot) pair and the state words it needs
-  const LaneSlot ls = cz_lane_slot_packed(T, lane);
-  const bool is_agent = ls.kind == 2, is_static = ls.kind == 0;
-  uint32_t rec = 0;
-  if (ls.off >= 0 && !is_static) rec = __ldg(state + (size_t)(is_agent ? D + ls.idx : ls.idx) * N + env);
-  const uint32_t me = __ldg(state + (size_t)(D + ls.agent) * N + env);           // this pair's observer
+  // this lane's (observer, slot) pair(s) and the state words they need
   const uint32_t var = __ldg(state + (size_t)(D + NA + CZ_ROW_VARIANT) * N + env);
-  uint32_t static_fb = 0;
-  if (ls.off >= 0 && is_static) cz_live_static(T, state, N, env, NA, var, ls.idx, rec, static_fb);
+  const LaneSlot ls = cz_lane_slot_packed(T, lane);
+  const PairRegs p = cz_pair_load<NA>(T, state, N, env, var, ls);
+  LaneSlot ls1;
+  PairRegs p1;
+  if constexpr (TWO) {
+    ls1 = cz_lane_slot_packed(T, lane + 32);
+    p1 = cz_pair_load<NA>(T, state, N, env, var, ls1);
+  }
   const double2* tab = reinterpret_cast<const double2*>(T.obs_table) + (size_t)var * 64 * tab2 + lane;
   double2* g2 = reinterpret_cast<double2*>(obs + (size_t)env * NA * T.L);
   // never-occupied slots are zeros: clear the staging rows, then fill the live slots
   for (int k = lane; k < NA * stage2; k += 32) stage[k] = make_double2(0.0, 0.0);
   __syncwarp();
-  if (ls.off >= 0) {
-    const bool present = is_agent || (rec & O_PRESENT);
-    const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
-    const uint32_t fb4 = is_static ? static_fb : (is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2));
-    const uint32_t one = 1u << (ls.flen - 1);
-    const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
-    const bool self = is_agent && (int)ls.idx == ls.agent;
-    const int x = rec & 7u, y = (rec >> 3) & 7u;
-    // (x - ax) / W from the host-divided table; the observer's own entry is x / W (cooking_env.py:364-368)
-    double X = __ldg(T.xlut + (x - (self ? 0 : (int)(me & 7u)) + T.W - 1));
-    double Y = __ldg(T.ylut + (y - (self ? 0 : (int)((me >> 3) & 7u)) + T.H - 1));
-    if (!present) { X = 0.0; Y = 0.0; }
-    double* out = reinterpret_cast<double*>(stage + ls.agent * stage2) + ls.off;
-    out[0] = X;
-    out[1] = Y;
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-      if (k < (int)ls.flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, (fb >> k & 1u) ? 0x3FF00000u : 0u);
-  }
+  cz_pair_store(T, ls, p, stage, stage2);
+  if constexpr (TWO) cz_pair_store(T, ls1, p1, stage, stage2);
   __syncwarp();
   {
     const int n2 = T.ranges[0][1] >> 1, o2 = T.ranges[0][0] >> 1, s2 = (T.ranges[0][0] - T.stage_lo) >> 1;
@@ -621,7 +649,9 @@ cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__
     double2 v0[NA], v1[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
-      const uint32_t cell = __shfl_sync(0xffffffffu, me, a * T.n_comp) & 63u;  // lane a*n_comp observes for agent a
+      uint32_t cell;
+      if constexpr (TWO) cell = __ldg(state + (size_t)(D + a) * N + env) & 63u;
+      else cell = __shfl_sync(0xffffffffu, p.me, a * T.n_comp) & 63u;  // lane a*n_comp observes for agent a
       if (ls.t0 >= 0) v0[a] = __ldg(tab + cell * tab2);
       if (ls.t1 >= 0) v1[a] = __ldg(tab + cell * tab2 + 32);
     }
@@ -654,6 +684,7 @@ struct cz_tables {
   int device;
   int obs_path;
   int simple;
+  int simple2;
   int num_sms;
   void* allocs[32];
   int n_allocs;
@@ -807,19 +838,19 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   UP(spawn_y, d->spawn_y, (size_t)T.A * 8);
   UP(spawn_n, d->spawn_n, (size_t)T.A * 2);
   if (rc == CZ_OK) {  // per-lane maps of the packed (observer, slot) layout
-    int4 lm[32];
+    int4 lm[64];  // entries 32-63: the second pair of a lane (kitchens with 33-64 (observer, slot) pairs)
     const int n0 = T.n_segs > 0 ? T.segs[0][1] >> 1 : 0, n1 = T.n_segs > 1 ? T.segs[1][1] >> 1 : 0;
-    for (int l = 0; l < 32; ++l) {
+    for (int l = 0; l < 64; ++l) {
       const bool live = T.n_comp > 0 && l < T.A * T.n_comp;
       int tt[2];
       for (int k = 0; k < 2; ++k) {
-        const int e = l + 32 * k;
+        const int e = (l & 31) + 32 * k;
         tt[k] = e < n0 ? (T.segs[0][0] >> 1) + e : (e < n0 + n1 ? (T.segs[1][0] >> 1) + e - n0 : -1);
       }
       // the computed-slot descriptor itself travels in the map: one load instead of a dependent pair
       lm[l] = make_int4(live ? (int)d->comp_slots[l % T.n_comp] : -1, live ? l / T.n_comp : 0, tt[0], tt[1]);
     }
-    rc = upload(t, lm, 32, &T.lane_map);
+    rc = upload(t, lm, 64, &T.lane_map);
   }
 #undef UP
   if (rc == CZ_OK) {  // read-only shared-memory image of a block: LUTs + the small tables
@@ -857,11 +888,13 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   if (smem > (size_t)prop.sharedMemPerBlockOptin) { cz_tables_destroy(t); return cz_fail(CZ_ELIMIT, "%s", "obs_len too large for shared memory staging"); }
   // the specialised kernels: one lane per (observer, slot) pair, one computed range, two table loads per
   // lane, small tables resident in shared memory
-  t->simple = T.A * T.n_comp <= 32 && T.n_comp > 0 && T.n_ranges == 1 && T.tab_len <= 128 && (T.L & 1) == 0 &&
-              T.V <= CZ_SV && T.B <= CZ_SB;
+  const bool packed = T.n_comp > 0 && T.n_ranges == 1 && T.tab_len <= 128 && (T.L & 1) == 0 && T.V <= CZ_SV && T.B <= CZ_SB;
+  t->simple = packed && T.A * T.n_comp <= 32;
+  // 33-64 pairs (3-4 agent kitchens): specialised dynamics kernel + the warp-per-environment writer with two pairs per lane
+  t->simple2 = packed && !t->simple && T.A * T.n_comp <= 64;
   {
     const char* g = getenv("CZ_GENERIC");
-    if (g && g[0] == '1') t->simple = 0;
+    if (g && g[0] == '1') t->simple = t->simple2 = 0;
   }
 #define SET_SMEM(K) CZ_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin))
 #define SET_MODE(M)                                                                                    \
@@ -942,7 +975,7 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
 #define CZ_GO(O, NA)                                                                                                  \
   cz_env_kernel<MODE, O, NA><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, state_out, actions, layout_ids, recipe_ids, mask, obs, \
                                                            reward, term, trunc, err, n_envs, flags, seed, env_offset)
-  if (dyn_only && t->simple) {
+  if (dyn_only && (t->simple || t->simple2)) {
     switch (t->dev.A) {
       case 1: CZ_GO(OBS_NONE, 1); break;
       case 2: CZ_GO(OBS_NONE, 2); break;
@@ -976,9 +1009,38 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
   return CZ_OK;
 }
 
+// The warp-per-environment float64 row writer (packed plans) on `s`.
+static int cz_launch_obs64(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, cudaStream_t s) {
+  if (!state || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
+  if (n_envs <= 0) return CZ_OK;
+  const int blocks = (n_envs + ENVS_WARPS - 1) / ENVS_WARPS;
+  const size_t smem = (size_t)ENVS_WARPS * t->dev.A * ((t->dev.stage_len + 1) / 2) * 16;
+#define CZ_OBS_GO(NA)                                                                                               \
+  if (t->simple2) cz_obs_envs_kernel<NA, true><<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs);    \
+  else cz_obs_envs_kernel<NA, false><<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs)
+  switch (t->dev.A) {
+    case 1: CZ_OBS_GO(1); break;
+    case 2: CZ_OBS_GO(2); break;
+    case 3: CZ_OBS_GO(3); break;
+    default: CZ_OBS_GO(4); break;
+  }
+#undef CZ_OBS_GO
+  g_launches.fetch_add(1);
+  CZ_CUDA(cudaGetLastError());
+  return CZ_OK;
+}
+
 extern "C" int cz_reset(const cz_tables* t, uint32_t* state, const int32_t* layout_ids, const uint8_t* recipe_ids,
                         const uint8_t* mask, double* obs, int n_envs, void* stream) {
   if (!layout_ids) return cz_fail(CZ_EINVAL, "%s", "layout_ids is required");
+  if (t && t->simple2 && obs) {  // state first, then the rows of every environment that was reset
+    if (mask) return cz_fail(CZ_EINVAL, "%s", "masked reset with observations is not available for 33-64 pair plans: pass obs = NULL and call cz_observe");
+    int rc = cz_launch<MODE_RESET>(t, state, state, true, nullptr, layout_ids, recipe_ids, mask, nullptr, nullptr, nullptr, nullptr,
+                                   nullptr, n_envs, 0, 0, 0, stream);
+    if (rc != CZ_OK) return rc;
+    return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream);
+  }
   return cz_launch<MODE_RESET>(t, state, state, false, nullptr, layout_ids, recipe_ids, mask, obs, nullptr, nullptr, nullptr, nullptr,
                                n_envs, 0, 0, 0, stream);
 }
@@ -987,6 +1049,12 @@ extern "C" int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actio
                        uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, uint32_t flags,
                        uint64_t seed, int64_t env_offset, void* stream) {
   if (!actions || !reward || !terminated || !truncated) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (t && t->simple2 && obs && !(flags & CZ_STEP_OBS_F32)) {  // dynamics, then the two-pairs-per-lane row writer
+    int rc = cz_launch<MODE_STEP>(t, state, state, true, actions, nullptr, nullptr, nullptr, nullptr, reward, terminated, truncated,
+                                  error_flags, n_envs, flags, seed, env_offset, stream);
+    if (rc != CZ_OK) return rc;
+    return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream);
+  }
   if ((flags & CZ_STEP_OBS_F32) && obs) {  // dynamics, then the float32 row writer on the same stream
     int rc = cz_launch<MODE_STEP>(t, state, state, true, actions, nullptr, nullptr, nullptr, nullptr, reward, terminated, truncated,
                                   error_flags, n_envs, flags, seed, env_offset, stream);
@@ -1002,6 +1070,7 @@ extern "C" int cz_observe_f32(const cz_tables* t, const uint32_t* state, float* 
 }
 
 extern "C" int cz_observe(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, void* stream) {
+  if (t && t->simple2) return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream);
   return cz_launch<MODE_OBSERVE>(t, state, const_cast<uint32_t*>(state), false, nullptr, nullptr, nullptr, nullptr, obs, nullptr,
                                  nullptr, nullptr, nullptr, n_envs, 0, 0, 0, stream);
 }
@@ -1037,7 +1106,7 @@ extern "C" int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* 
                                  uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, uint32_t flags,
                                  uint64_t seed, int64_t env_offset, void* stream) {
   if (!t || !state2 || !actions || !obs || !reward || !terminated || !truncated) return cz_fail(CZ_EINVAL, "%s", "null argument");
-  if (!t->simple) return cz_fail(CZ_EINVAL, "%s", "the pipelined step needs the specialised kernels (see DESIGN.md)");
+  if (!t->simple && !t->simple2) return cz_fail(CZ_EINVAL, "%s", "the pipelined step needs the specialised kernels (see DESIGN.md)");
   int rc = cz_pipe_init(t);
   if (rc != CZ_OK) return rc;
   const size_t half = (size_t)t->dev.rows * n_envs;
@@ -1060,16 +1129,8 @@ extern "C" int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* 
     rc = cz_launch_obs32(t, out, reinterpret_cast<float*>(obs), n_envs, t->pipe_obs);
     if (rc != CZ_OK) return rc;
   } else {
-    const int blocks = (n_envs + ENVS_WARPS - 1) / ENVS_WARPS;
-    const size_t smem = (size_t)ENVS_WARPS * t->dev.A * ((t->dev.stage_len + 1) / 2) * 16;
-    switch (t->dev.A) {
-      case 1: cz_obs_envs_kernel<1><<<blocks, 32 * ENVS_WARPS, smem, t->pipe_obs>>>(t->dev, out, obs, n_envs); break;
-      case 2: cz_obs_envs_kernel<2><<<blocks, 32 * ENVS_WARPS, smem, t->pipe_obs>>>(t->dev, out, obs, n_envs); break;
-      case 3: cz_obs_envs_kernel<3><<<blocks, 32 * ENVS_WARPS, smem, t->pipe_obs>>>(t->dev, out, obs, n_envs); break;
-      default: cz_obs_envs_kernel<4><<<blocks, 32 * ENVS_WARPS, smem, t->pipe_obs>>>(t->dev, out, obs, n_envs); break;
-    }
-    g_launches.fetch_add(1);
-    CZ_CUDA(cudaGetLastError());
+    rc = cz_launch_obs64(t, out, obs, n_envs, t->pipe_obs);
+    if (rc != CZ_OK) return rc;
   }
   CZ_CUDA(cudaEventRecord(t->ev_obs[nxt], t->pipe_obs));
   t->pipe_obs_pending[nxt] = 1;

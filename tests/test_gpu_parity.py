@@ -146,19 +146,27 @@ def test_auto_reset_and_shard_independence():
                 assert_obs_equal(np.stack([orc.observe(i) for i in range(2)]), o[k].cpu().numpy(), f"autoreset env {k}")
 
 
-@pytest.mark.parametrize("level", ["coop_test", "switch_test", "coexistence_test"])
-def test_pipelined_step_is_bit_identical_to_the_in_place_step(level):
+@pytest.mark.parametrize("level,agents", [("coop_test", 2), ("switch_test", 2), ("coexistence_test", 2),
+                                          ("open4", 3), ("open4", 4)])
+def test_pipelined_step_is_bit_identical_to_the_in_place_step(level, agents):
     """throughput mode (cz_step_pipelined: two streams, ping-pong state) does the same work as cz_step;
-    switch_test adds live Switch / Block slots to the observation writer, coexistence_test 16 static variants"""
-    cfg = dict(level=level, meta_file="example", num_agents=2, max_steps=30,
-               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    switch_test adds live Switch / Block slots to the observation writer, coexistence_test 16 static variants,
+    the open kitchen with 3-4 agents the two-pairs-per-lane writer"""
+    import os
+    from tests.replay import ROOT
+    cfg = dict(level=level, meta_file="example", num_agents=agents, max_steps=30,
+               recipes=["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"][:agents], end_all=True,
+               reward_scheme=None)
+    if level == "open4":
+        cfg.update(level=os.path.join(ROOT, "tests/golden/levels/open4.json"),
+                   meta_file=os.path.join(ROOT, "tests/golden/levels/meta4.json"))
     n = 5000
     a = _make(n, cfg, auto_reset=True, seed=3, layout_pool_size=64)
     b = _make(n, cfg, auto_reset=True, seed=3, layout_pool_size=64, pipelined=True)
     a.reset(); b.reset()
     rng = np.random.default_rng(1)
     for t in range(70):
-        act = torch.from_numpy(rng.integers(0, 5, size=(n, 2)).astype(np.uint8)).cuda()
+        act = torch.from_numpy(rng.integers(0, 5, size=(n, agents)).astype(np.uint8)).cuda()
         oa, ra, ta, ua, _ = a.step(act)
         ob, rb, tb, ub, _ = b.step(act)
         if t % 7 == 0 or t > 60:
