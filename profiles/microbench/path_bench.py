@@ -33,3 +33,7 @@ R = ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"]
 for a in (1, 2, 3, 4):
     run(f"open4 A={a}", 65536, "tests/golden/levels/open4.json", "tests/golden/levels/meta4.json", a, R[:a])
 run("open4 A=4 f32", 65536, "tests/golden/levels/open4.json", "tests/golden/levels/meta4.json", 4, R, obs_dtype=torch.float32)
+run("open4 A=4 pipelined", 65536, "tests/golden/levels/open4.json", "tests/golden/levels/meta4.json", 4, R, pipelined=True)
+run("open4 A=3 pipelined", 65536, "tests/golden/levels/open4.json", "tests/golden/levels/meta4.json", 3, R[:3], pipelined=True)
+run("switch2 pipelined", N, "switch_test", "example", 2, BOOK[1:3], pipelined=True)
+run("coexist2 pipelined", N, "coexistence_test", "example", 2, BOOK[1:3], pipelined=True)
