@@ -110,8 +110,31 @@ cz_obs32_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ st
 // Specialised writer for the packed (observer, slot) plans of the specialised step kernels (`simple` tables, NA * L a
 // even): a lane owns one (observer, slot) pair and two table float2 per row, exactly the lane map of
 // cz_obs_envs_kernel; the A rows are staged as one 16-byte aligned block and leave as float4.
-template <int NA>
-__global__ void __launch_bounds__(32 * CZ_OBS32_MAX_WARPS, 8)
+// [x, y, flags..., 1] of one (observer, slot) pair as floats into its staging row (L2 float2 per row)
+__device__ __forceinline__ void cz_pair_store32(const CzDev& T, const LaneSlot& ls, const PairRegs& p, float2* stage2, int L2) {
+  if (ls.off < 0) return;
+  const bool is_agent = ls.kind == 2, is_static = ls.kind == 0;
+  const uint32_t rec = p.rec, me = p.me;
+  const bool present = is_agent || (rec & O_PRESENT);
+  const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+  const uint32_t fb4 = is_static ? p.static_fb : (is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2));
+  const uint32_t one = 1u << (ls.flen - 1);
+  const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
+  const bool self = is_agent && (int)ls.idx == ls.agent;
+  const int x = rec & 7u, y = (rec >> 3) & 7u;
+  float X = __ldg(T.xlut32 + (x - (self ? 0 : (int)(me & 7u)) + T.W - 1));
+  float Y = __ldg(T.ylut32 + (y - (self ? 0 : (int)((me >> 3) & 7u)) + T.H - 1));
+  if (!present) { X = 0.0f; Y = 0.0f; }
+  float* out = reinterpret_cast<float*>(stage2 + ls.agent * L2) + T.stage_lo + ls.off;  // ls.off is relative to stage_lo
+  out[0] = X;
+  out[1] = Y;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+    if (k < (int)ls.flen) out[2 + k] = (fb >> k & 1u) ? 1.0f : 0.0f;
+}
+
+template <int NA, bool TWO>
+__global__ void __launch_bounds__(32 * CZ_OBS32_MAX_WARPS, (TWO || NA >= 3) ? 5 : 8)
 cz_obs32_fast_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, float* __restrict__ obs, int n_envs) {
   extern __shared__ __align__(16) unsigned char smem_f32[];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -121,20 +144,23 @@ cz_obs32_fast_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict
   const size_t N = (size_t)n_envs;
   float2* stage2 = reinterpret_cast<float2*>(smem_f32) + (size_t)warp * NA * L2;  // NA * L floats, 16-byte aligned
 
-  const LaneSlot ls = cz_lane_slot_packed(T, lane);  // ls.off is relative to stage_lo
-  const bool is_agent = ls.kind == 2, is_static = ls.kind == 0;
-  uint32_t rec = 0;
-  if (ls.off >= 0 && !is_static) rec = __ldg(state + (size_t)(is_agent ? D + ls.idx : ls.idx) * N + env);
-  const uint32_t me = __ldg(state + (size_t)(D + ls.agent) * N + env);
   const uint32_t var = __ldg(state + (size_t)(D + NA + CZ_ROW_VARIANT) * N + env);
-  uint32_t static_fb = 0;
-  if (ls.off >= 0 && is_static) cz_live_static(T, state, N, env, NA, var, ls.idx, rec, static_fb);
+  const LaneSlot ls = cz_lane_slot_packed(T, lane);
+  const PairRegs p = cz_pair_load<NA>(T, state, N, env, var, ls);
+  LaneSlot ls1;
+  PairRegs p1;
+  if constexpr (TWO) {
+    ls1 = cz_lane_slot_packed(T, lane + 32);
+    p1 = cz_pair_load<NA>(T, state, N, env, var, ls1);
+  }
   const float2* tab = reinterpret_cast<const float2*>(T.obs_table32) + (size_t)var * 64 * tab2 + lane;
   // table segments of every row: loads first
   float2 v0[NA], v1[NA];
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
-    const uint32_t cell = __shfl_sync(0xffffffffu, me, a * T.n_comp) & 63u;  // lane a*n_comp observes for agent a
+    uint32_t cell;
+    if constexpr (TWO) cell = __ldg(state + (size_t)(D + a) * N + env) & 63u;
+    else cell = __shfl_sync(0xffffffffu, p.me, a * T.n_comp) & 63u;  // lane a*n_comp observes for agent a
     if (ls.t0 >= 0) v0[a] = __ldg(tab + cell * tab2);
     if (ls.t1 >= 0) v1[a] = __ldg(tab + cell * tab2 + 32);
   }
@@ -151,24 +177,8 @@ cz_obs32_fast_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict
     if (ls.t1 >= 0) stage2[a * L2 + ls.t1] = v1[a];
   }
   __syncwarp();
-  if (ls.off >= 0) {
-    const bool present = is_agent || (rec & O_PRESENT);
-    const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
-    const uint32_t fb4 = is_static ? static_fb : (is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2));
-    const uint32_t one = 1u << (ls.flen - 1);
-    const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
-    const bool self = is_agent && (int)ls.idx == ls.agent;
-    const int x = rec & 7u, y = (rec >> 3) & 7u;
-    float X = __ldg(T.xlut32 + (x - (self ? 0 : (int)(me & 7u)) + T.W - 1));
-    float Y = __ldg(T.ylut32 + (y - (self ? 0 : (int)((me >> 3) & 7u)) + T.H - 1));
-    if (!present) { X = 0.0f; Y = 0.0f; }
-    float* out = reinterpret_cast<float*>(stage2 + ls.agent * L2) + T.stage_lo + ls.off;
-    out[0] = X;
-    out[1] = Y;
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-      if (k < (int)ls.flen) out[2 + k] = (fb >> k & 1u) ? 1.0f : 0.0f;
-  }
+  cz_pair_store32(T, ls, p, stage2, L2);
+  if constexpr (TWO) cz_pair_store32(T, ls1, p1, stage2, L2);
   __syncwarp();
   if (((NA * T.L) & 3) == 0) {  // every environment (and every warp's staging block) starts 16-byte aligned
     float4* g4 = reinterpret_cast<float4*>(obs + (size_t)env * NA * T.L);
@@ -184,16 +194,20 @@ static int cz_launch_obs32(const cz_tables* t, const uint32_t* state, float* obs
   if (!t || !state || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (n_envs <= 0) return CZ_OK;
   if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
-  if (t->simple) {
+  if (t->simple || t->simple2) {
     const int blocks = (n_envs + CZ_OBS32_MAX_WARPS - 1) / CZ_OBS32_MAX_WARPS;
     const size_t smem = (size_t)CZ_OBS32_MAX_WARPS * t->dev.A * t->dev.L * 4;
     if (smem <= 48 * 1024) {
+#define CZ_O32_GO(NA)                                                                                                       \
+  if (t->simple2) cz_obs32_fast_kernel<NA, true><<<blocks, 32 * CZ_OBS32_MAX_WARPS, smem, s>>>(t->dev, state, obs, n_envs);  \
+  else cz_obs32_fast_kernel<NA, false><<<blocks, 32 * CZ_OBS32_MAX_WARPS, smem, s>>>(t->dev, state, obs, n_envs)
       switch (t->dev.A) {
-        case 1: cz_obs32_fast_kernel<1><<<blocks, 32 * CZ_OBS32_MAX_WARPS, smem, s>>>(t->dev, state, obs, n_envs); break;
-        case 2: cz_obs32_fast_kernel<2><<<blocks, 32 * CZ_OBS32_MAX_WARPS, smem, s>>>(t->dev, state, obs, n_envs); break;
-        case 3: cz_obs32_fast_kernel<3><<<blocks, 32 * CZ_OBS32_MAX_WARPS, smem, s>>>(t->dev, state, obs, n_envs); break;
-        default: cz_obs32_fast_kernel<4><<<blocks, 32 * CZ_OBS32_MAX_WARPS, smem, s>>>(t->dev, state, obs, n_envs); break;
+        case 1: CZ_O32_GO(1); break;
+        case 2: CZ_O32_GO(2); break;
+        case 3: CZ_O32_GO(3); break;
+        default: CZ_O32_GO(4); break;
       }
+#undef CZ_O32_GO
       g_launches.fetch_add(1);
       CZ_CUDA(cudaGetLastError());
       return CZ_OK;
