@@ -549,9 +549,11 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
 // zero-fills and fills its private staging rows, then streams the computed range and the table
 // segments out with 128-bit stores.  No TMA, no proxy fence, no block-level barrier.
 // =========================================================================================
+#ifndef ENVS_WARPS
 #define ENVS_WARPS 8
+#endif
 #ifndef CZ_ENVS_MIN_BLOCKS
-#define CZ_ENVS_MIN_BLOCKS 8
+#define CZ_ENVS_MIN_BLOCKS (64 / ENVS_WARPS)
 #endif
 
 // A static slot among the computed ones (live Switch / Block, world_objects.py:174,221): its record is the cell with
