@@ -687,6 +687,7 @@ struct cz_tables {
   int obs_path;
   int simple;
   int simple2;
+  int two_kernel_min_envs;  // in-place step of at least this many environments: dynamics kernel, then the row-writer kernel
   int num_sms;
   void* allocs[32];
   int n_allocs;
@@ -897,6 +898,8 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   {
     const char* g = getenv("CZ_GENERIC");
     if (g && g[0] == '1') t->simple = t->simple2 = 0;
+    const char* k = getenv("CZ_TWO_KERNEL_MIN_ENVS");
+    t->two_kernel_min_envs = k ? atoi(k) : 49152;  // measured crossover between 32768 and 65536 (profiles/r01_two_kernel_sweep.txt)
   }
 #define SET_SMEM(K) CZ_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin))
 #define SET_MODE(M)                                                                                    \
@@ -1051,7 +1054,10 @@ extern "C" int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actio
                        uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, uint32_t flags,
                        uint64_t seed, int64_t env_offset, void* stream) {
   if (!actions || !reward || !terminated || !truncated) return cz_fail(CZ_EINVAL, "%s", "null argument");
-  if (t && t->simple2 && obs && !(flags & CZ_STEP_OBS_F32)) {  // dynamics, then the two-pairs-per-lane row writer
+  // 33-64 pair plans always, and large batches of the other packed plans (the short-block row writer streams faster than the
+  // observation phase of the fused kernel; small batches keep the single launch): dynamics, then the row writer
+  if (t && obs && !(flags & CZ_STEP_OBS_F32) &&
+      (t->simple2 || (t->simple && t->two_kernel_min_envs > 0 && n_envs >= t->two_kernel_min_envs))) {
     int rc = cz_launch<MODE_STEP>(t, state, state, true, actions, nullptr, nullptr, nullptr, nullptr, reward, terminated, truncated,
                                   error_flags, n_envs, flags, seed, env_offset, stream);
     if (rc != CZ_OK) return rc;
