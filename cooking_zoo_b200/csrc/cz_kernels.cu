@@ -1039,8 +1039,7 @@ static int cz_launch_obs64(const cz_tables* t, const uint32_t* state, double* ob
 extern "C" int cz_reset(const cz_tables* t, uint32_t* state, const int32_t* layout_ids, const uint8_t* recipe_ids,
                         const uint8_t* mask, double* obs, int n_envs, void* stream) {
   if (!layout_ids) return cz_fail(CZ_EINVAL, "%s", "layout_ids is required");
-  if (t && t->simple2 && obs) {  // state first, then the rows of every environment that was reset
-    if (mask) return cz_fail(CZ_EINVAL, "%s", "masked reset with observations is not available for 33-64 pair plans: pass obs = NULL and call cz_observe");
+  if (t && t->simple2 && obs && !mask) {  // state first, then every row (a masked reset takes the generic kernel below)
     int rc = cz_launch<MODE_RESET>(t, state, state, true, nullptr, layout_ids, recipe_ids, mask, nullptr, nullptr, nullptr, nullptr,
                                    nullptr, n_envs, 0, 0, 0, stream);
     if (rc != CZ_OK) return rc;
