@@ -362,6 +362,8 @@ def run_gpu_arm(args):
         env3p.close()
         cfg3 = {"workload": "cfg3: 4096 two-agent coop_test envs, 1 GPU, random actions, feature_vector obs",
                 "per_launch_env_steps_per_s": per_launch, "cuda_graph_env_steps_per_s": graphed,
+                "k_steps_per_launch": {"K": ring, "env_steps_per_s": graphed,
+                                       "how": f"one CUDA graph launch = {ring} consecutive cz_step kernels (actions for the K steps resident)"},
                 "pipelined_env_steps_per_s": piped,
                 "note": "20 MB per step: launch/latency bound, not HBM bound"}
         env3.close()

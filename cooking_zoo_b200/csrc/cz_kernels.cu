@@ -820,7 +820,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   }
   UP(recipe_nodes, d->recipe_nodes, (size_t)T.B * CZ_MAX_NODES);
   UP(recipe_len, d->recipe_len, T.B);
-  static uint32_t spans[256 * CZ_MAX_NODES];  // per node: first slot | slots << 8 | required record bits << 16
+  uint32_t spans[256 * CZ_MAX_NODES];  // (stack: the library may be called from several host threads) per node: first slot | slots << 8 | required record bits << 16
   for (int b = 0; b < T.B; ++b)
     for (int k = 0; k < CZ_MAX_NODES; ++k) {
       const uint32_t node = d->recipe_nodes[b * CZ_MAX_NODES + k], ty = node & 255u, cond = (node >> 9) & 3u;
@@ -858,7 +858,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
 #undef UP
   if (rc == CZ_OK) {  // read-only shared-memory image of a block: LUTs + the small tables
     const size_t img_bytes = cz_block_smem_head(T.V);
-    static unsigned char img_buf[sizeof(BlockSmem) + CZ_SV * sizeof(VarTabs) + 16];
+    alignas(16) unsigned char img_buf[sizeof(BlockSmem) + CZ_SV * sizeof(VarTabs) + 16];
     memset(img_buf, 0, sizeof(img_buf));
     BlockSmem& img = *reinterpret_cast<BlockSmem*>(img_buf);
     for (int i = 0; i < 2 * T.W - 1; ++i) img.xlut[i] = d->xlut[i];
