@@ -202,3 +202,31 @@ def test_masked_reset_touches_only_the_selected_environments(agents):
     assert torch.equal(env.obs[~m].view(torch.int64), moved_obs[~m].view(torch.int64))
     # episode counters differ after a second reset: compare everything but the EPISODE row
     assert torch.equal(env.state[:-1, m], first_state[:-1, m]) and torch.equal(env.state[:, ~m], moved_state[:, ~m])
+
+
+def test_large_batch_two_kernel_step_equals_the_fused_kernel_on_a_ragged_batch(monkeypatch):
+    """in-place steps of >= 49152 environments run the dynamics kernel and then the row-writer kernel; the fused kernel
+    (forced here through CZ_TWO_KERNEL_MIN_ENVS=0, read when the tables are created) must give the same bits.
+    50001 environments: neither a whole tile nor a whole writer block at the end."""
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=40,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    n = 50001
+    a = _make(n, cfg, auto_reset=True, seed=8, layout_pool_size=64)
+    monkeypatch.setenv("CZ_TWO_KERNEL_MIN_ENVS", "0")
+    b = _make(n, cfg, auto_reset=True, seed=8, layout_pool_size=64)
+    monkeypatch.delenv("CZ_TWO_KERNEL_MIN_ENVS")
+    oa, ob = a.reset(), b.reset()
+    assert torch.equal(oa.view(torch.int64), ob.view(torch.int64))
+    rng = np.random.default_rng(2)
+    l0 = a.lib.cz_launch_count()
+    for t in range(45):
+        act = torch.from_numpy(rng.integers(0, 5, size=(n, 2)).astype(np.uint8)).cuda()
+        oa, ra, ta, ua, _ = a.step(act)
+        l1 = a.lib.cz_launch_count()
+        ob, rb, tb, ub, _ = b.step(act)
+        l2 = a.lib.cz_launch_count()
+        assert (l1 - l0, l2 - l1) == (2, 1)          # two kernels vs one fused kernel
+        l0 = l2
+        assert torch.equal(oa.view(torch.int64), ob.view(torch.int64)), t
+        assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(ta, tb) and torch.equal(ua, ub)
+    assert torch.equal(a.state, b.state)
