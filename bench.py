@@ -305,148 +305,157 @@ def run_gpu_arm(args):
     # ---- BASELINE config 3 (4096 two-agent envs on one GPU): launch-bound, reported beside the headline
     cfg3 = None
     if rank == 0 and world == 1 and not args.no_cfg3:
-        n3 = 4096
-        env3 = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
-                                 device=str(dev), layout_pool_size=400, layout_seed=0, auto_reset=True, seed=7)
-        env3.reset()
-        act3 = torch.randint(0, 5, (ring, n3, A), generator=g, dtype=torch.uint8).to(dev)
-        for s in range(20):
-            env3.step(act3[s % ring])
-        torch.cuda.synchronize(dev)
-        k3 = 2000
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for s in range(k3):
-            env3.step(act3[s % ring])
-        a1.record()
-        torch.cuda.synchronize(dev)
-        per_launch = n3 * k3 / (a0.elapsed_time(a1) / 1e3)
-        # the same launches captured once in a CUDA graph (one graph = `ring` steps) and replayed
-        graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for s in range(ring):
-                env3.step(act3[s])
-            side.synchronize()
-            with torch.cuda.graph(graph, stream=side):
+        try:
+            n3 = 4096
+            env3 = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
+                                     device=str(dev), layout_pool_size=400, layout_seed=0, auto_reset=True, seed=7)
+            env3.reset()
+            act3 = torch.randint(0, 5, (ring, n3, A), generator=g, dtype=torch.uint8).to(dev)
+            for s in range(20):
+                env3.step(act3[s % ring])
+            torch.cuda.synchronize(dev)
+            k3 = 2000
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for s in range(k3):
+                env3.step(act3[s % ring])
+            a1.record()
+            torch.cuda.synchronize(dev)
+            per_launch = n3 * k3 / (a0.elapsed_time(a1) / 1e3)
+            # the same launches captured once in a CUDA graph (one graph = `ring` steps) and replayed
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
                 for s in range(ring):
                     env3.step(act3[s])
-        torch.cuda.current_stream(dev).wait_stream(side)
-        for _ in range(5):
-            graph.replay()
-        torch.cuda.synchronize(dev)
-        reps = 200
-        a0.record()
-        for _ in range(reps):
-            graph.replay()
-        a1.record()
-        torch.cuda.synchronize(dev)
-        graphed = n3 * ring * reps / (a0.elapsed_time(a1) / 1e3)
-        # pipelined throughput mode at this size
-        env3p = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
-                                  action_scheme="scheme3", device=str(dev), layout_pool_size=400, layout_seed=0,
-                                  auto_reset=True, seed=7, pipelined=True)
-        env3p.reset()
-        for s in range(20):
-            env3p.step(act3[s % ring])
-        env3p.wait()
-        torch.cuda.synchronize(dev)
-        a0.record()
-        for s in range(k3):
-            env3p.step(act3[s % ring])
-        env3p.wait()
-        a1.record()
-        torch.cuda.synchronize(dev)
-        piped = n3 * k3 / (a0.elapsed_time(a1) / 1e3)
-        env3p.close()
-        cfg3 = {"workload": "cfg3: 4096 two-agent coop_test envs, 1 GPU, random actions, feature_vector obs",
-                "per_launch_env_steps_per_s": per_launch, "cuda_graph_env_steps_per_s": graphed,
-                "k_steps_per_launch": {"K": ring, "env_steps_per_s": graphed,
-                                       "how": f"one CUDA graph launch = {ring} consecutive cz_step kernels (actions for the K steps resident)"},
-                "pipelined_env_steps_per_s": piped,
-                "note": "20 MB per step: launch/latency bound, not HBM bound"}
-        env3.close()
+                side.synchronize()
+                with torch.cuda.graph(graph, stream=side):
+                    for s in range(ring):
+                        env3.step(act3[s])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            for _ in range(5):
+                graph.replay()
+            torch.cuda.synchronize(dev)
+            reps = 200
+            a0.record()
+            for _ in range(reps):
+                graph.replay()
+            a1.record()
+            torch.cuda.synchronize(dev)
+            graphed = n3 * ring * reps / (a0.elapsed_time(a1) / 1e3)
+            # pipelined throughput mode at this size
+            env3p = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+                                      action_scheme="scheme3", device=str(dev), layout_pool_size=400, layout_seed=0,
+                                      auto_reset=True, seed=7, pipelined=True)
+            env3p.reset()
+            for s in range(20):
+                env3p.step(act3[s % ring])
+            env3p.wait()
+            torch.cuda.synchronize(dev)
+            a0.record()
+            for s in range(k3):
+                env3p.step(act3[s % ring])
+            env3p.wait()
+            a1.record()
+            torch.cuda.synchronize(dev)
+            piped = n3 * k3 / (a0.elapsed_time(a1) / 1e3)
+            env3p.close()
+            cfg3 = {"workload": "cfg3: 4096 two-agent coop_test envs, 1 GPU, random actions, feature_vector obs",
+                    "per_launch_env_steps_per_s": per_launch, "cuda_graph_env_steps_per_s": graphed,
+                    "k_steps_per_launch": {"K": ring, "env_steps_per_s": graphed,
+                                           "how": f"one CUDA graph launch = {ring} consecutive cz_step kernels (actions for the K steps resident)"},
+                    "pipelined_env_steps_per_s": piped,
+                    "note": "20 MB per step: launch/latency bound, not HBM bound"}
+            env3.close()
+        except Exception as ex:      # a side measurement must never cost the headline line
+            cfg3 = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
     # ---- closed loop with the device policy: CookingAgent decisions + step, no host in between
     cook = None
     if rank == 0 and world == 1 and not args.no_cfg3:
-        env.wait()
-        torch.cuda.synchronize(dev)
-        envc = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
-                                 action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size=400,
-                                 layout_seed=0, auto_reset=True, seed=2026)
-        envc.reset(recipe_ids=recipe_ids)
-        for _ in range(5):
-            envc.step(envc.heuristic_actions()[0])
-        torch.cuda.synchronize(dev)
-        kc = 200
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(kc):
-            envc.step(envc.heuristic_actions()[0])
-        c1.record()
-        torch.cuda.synchronize(dev)
-        loop_ms = c0.elapsed_time(c1) / kc
-        c0.record()
-        for _ in range(kc):
-            envc.heuristic_actions()
-        c1.record()
-        torch.cuda.synchronize(dev)
-        pol_ms = c0.elapsed_time(c1) / kc
-        envc.close()
-        envc = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
-                                 action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size=400,
-                                 layout_seed=0, auto_reset=True, seed=2026, pipelined=True)
-        envc.reset(recipe_ids=recipe_ids)
-        for _ in range(5):
-            envc.step(envc.heuristic_actions()[0])
-        envc.wait()
-        torch.cuda.synchronize(dev)
-        c0.record()
-        for _ in range(kc):
-            envc.step(envc.heuristic_actions()[0])
-        envc.wait()
-        c1.record()
-        torch.cuda.synchronize(dev)
-        loop_p_ms = c0.elapsed_time(c1) / kc
-        cook = {"workload": f"{N} two-agent envs, every action from cz_policy_act (the scripted cook)",
-                "closed_loop_env_steps_per_s": N / (loop_ms / 1e3),
-                "closed_loop_pipelined_env_steps_per_s": N / (loop_p_ms / 1e3), "policy_ms_per_launch": pol_ms,
-                "policy_decisions_per_s": N * A / (pol_ms / 1e3),
-                "recipes_done_now": float(envc.info()["recipe_done"].sum())}
-        envc.close()
+        try:
+            env.wait()
+            torch.cuda.synchronize(dev)
+            envc = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+                                     action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size=400,
+                                     layout_seed=0, auto_reset=True, seed=2026)
+            envc.reset(recipe_ids=recipe_ids)
+            for _ in range(5):
+                envc.step(envc.heuristic_actions()[0])
+            torch.cuda.synchronize(dev)
+            kc = 200
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(kc):
+                envc.step(envc.heuristic_actions()[0])
+            c1.record()
+            torch.cuda.synchronize(dev)
+            loop_ms = c0.elapsed_time(c1) / kc
+            c0.record()
+            for _ in range(kc):
+                envc.heuristic_actions()
+            c1.record()
+            torch.cuda.synchronize(dev)
+            pol_ms = c0.elapsed_time(c1) / kc
+            envc.close()
+            envc = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+                                     action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size=400,
+                                     layout_seed=0, auto_reset=True, seed=2026, pipelined=True)
+            envc.reset(recipe_ids=recipe_ids)
+            for _ in range(5):
+                envc.step(envc.heuristic_actions()[0])
+            envc.wait()
+            torch.cuda.synchronize(dev)
+            c0.record()
+            for _ in range(kc):
+                envc.step(envc.heuristic_actions()[0])
+            envc.wait()
+            c1.record()
+            torch.cuda.synchronize(dev)
+            loop_p_ms = c0.elapsed_time(c1) / kc
+            cook = {"workload": f"{N} two-agent envs, every action from cz_policy_act (the scripted cook)",
+                    "closed_loop_env_steps_per_s": N / (loop_ms / 1e3),
+                    "closed_loop_pipelined_env_steps_per_s": N / (loop_p_ms / 1e3), "policy_ms_per_launch": pol_ms,
+                    "policy_decisions_per_s": N * A / (pol_ms / 1e3),
+                    "recipes_done_now": float(envc.info()["recipe_done"].sum())}
+            envc.close()
+        except Exception as ex:      # a side measurement must never cost the headline line
+            cook = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
     # ---- float32 observation mode (reported separately; rows = the f64 rows rounded element-wise)
     f32 = None
     if world == 1 and not args.no_cfg3:
-        env.wait()
-        torch.cuda.synchronize(dev)
-        envf, ms_f, _, _ = timed_run(True, False, torch.float32)
-        envf.close()
-        envf, ms_fs, _, _ = timed_run(False, False, torch.float32)
-        h_obs32 = torch.empty((N, A, L), dtype=torch.float32).pin_memory()
+        try:
+            env.wait()
+            torch.cuda.synchronize(dev)
+            envf, ms_f, _, _ = timed_run(True, False, torch.float32)
+            envf.close()
+            envf, ms_fs, _, _ = timed_run(False, False, torch.float32)
+            h_obs32 = torch.empty((N, A, L), dtype=torch.float32).pin_memory()
 
-        def host_step32():
-            _native.check(lib.cz_step_host(envf._handle, envf.state.data_ptr(), h_act.data_ptr(), h_obs32.data_ptr(),
-                                           h_rew.data_ptr(), h_term.data_ptr(), h_trunc.data_ptr(), N,
-                                           _native.STEP_AUTO_RESET | _native.STEP_OBS_F32, 2026, rank * N, stream))
-        for _ in range(3):
-            host_step32()
-        torch.cuda.synchronize(dev)
-        e0.record()
-        for _ in range(e2e_steps):
-            host_step32()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        b32 = A * L * 4 + A * 8 + 2 * A + A + 2 * envf.tables.rows * 4
-        f32 = {"dtype": "f32 observations (f64 rewards)", "bytes_per_env_step": b32,
-               "pipelined_env_steps_per_s": N * args.steps / (ms_f / 1e3),
-               "pipelined_gbs": N * b32 / (ms_f / args.steps / 1e3) / 1e9,
-               "in_place_env_steps_per_s": N * args.steps / (ms_fs / 1e3),
-               "e2e_env_steps_per_s": N * e2e_steps / (e0.elapsed_time(e1) / 1e3),
-               "d2h_bytes_per_step": N * A * L * 4 + N * A * 8 + 2 * N * A}
-        envf.close()
+            def host_step32():
+                _native.check(lib.cz_step_host(envf._handle, envf.state.data_ptr(), h_act.data_ptr(), h_obs32.data_ptr(),
+                                               h_rew.data_ptr(), h_term.data_ptr(), h_trunc.data_ptr(), N,
+                                               _native.STEP_AUTO_RESET | _native.STEP_OBS_F32, 2026, rank * N, stream))
+            for _ in range(3):
+                host_step32()
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(e2e_steps):
+                host_step32()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            b32 = A * L * 4 + A * 8 + 2 * A + A + 2 * envf.tables.rows * 4
+            f32 = {"dtype": "f32 observations (f64 rewards)", "bytes_per_env_step": b32,
+                   "pipelined_env_steps_per_s": N * args.steps / (ms_f / 1e3),
+                   "pipelined_gbs": N * b32 / (ms_f / args.steps / 1e3) / 1e9,
+                   "in_place_env_steps_per_s": N * args.steps / (ms_fs / 1e3),
+                   "e2e_env_steps_per_s": N * e2e_steps / (e0.elapsed_time(e1) / 1e3),
+                   "d2h_bytes_per_step": N * A * L * 4 + N * A * 8 + 2 * N * A}
+            envf.close()
+        except Exception as ex:      # a side measurement must never cost the headline line
+            f32 = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -463,7 +472,11 @@ def run_gpu_arm(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         cpu = None
         if not args.no_cpu:
-            v, procs, wall = cpu_port_throughput(args.cpu_steps, 200)
+            try:
+                v, procs, wall = cpu_port_throughput(args.cpu_steps, 200)
+            except Exception as ex:     # e.g. no fork / spawn on the box: one process, in this interpreter
+                sys.stderr.write(f"cpu_baseline: process pool failed ({ex!r}); timing a single process\n")
+                v, procs, wall = cpu_port_throughput(args.cpu_steps, 200, procs=1)
             cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
                    "sample": f"{procs} processes x {args.cpu_steps} env-steps of oracle/cz_oracle.py (Python restatement "
                              f"of the Python reference), same level/recipes/action distribution, {wall:.1f} s wall"}
