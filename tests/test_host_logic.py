@@ -84,3 +84,47 @@ def test_tables_compile_for_golden_configs(path):
     for d, c in enumerate(t.canon_of_dev):
         if objs[c, 0]:
             assert (int(dev[d]) & 7, (int(dev[d]) >> 3) & 7) == (objs[c, 1], objs[c, 2])
+
+
+def test_planner_keeps_the_shipped_levels_in_the_specialised_class():
+    """what cz_tables_create needs for the specialised kernels + pipelined mode: few variants, one computed
+    range, at most 64 (observer, slot) pairs, even rows, table run <= 128 doubles"""
+    rec = ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"]
+    cases = [("coop_test", "example", 2), ("switch_test", "example", 2), ("coexistence_test", "example", 2)]
+    cases += [(os.path.join(ROOT, "tests/golden/levels/open4.json"), os.path.join(ROOT, "tests/golden/levels/meta4.json"), a)
+              for a in (1, 2, 3, 4)]
+    for level, meta, agents in cases:
+        t = compile_tables(level, meta, agents, 100, rec[:agents], layout_pool_size=300, layout_seed=1)
+        assert t.num_variants <= 16, (level, t.num_variants)
+        assert t.num_obs_ranges == 1 and t.obs_len % 2 == 0 and t.obs_table_len <= 128, level
+        assert 0 < agents * t.num_comp_slots <= 64, (level, agents)
+        # rows are partitioned into table segments and the computed range
+        covered = np.zeros(t.obs_len, int)
+        for k in range(t.num_obs_segs):
+            covered[t.obs_segs[k, 0]:t.obs_segs[k, 0] + t.obs_segs[k, 1]] += 1
+        covered[t.obs_ranges[0, 0]:t.obs_ranges[0, 0] + t.obs_ranges[0, 1]] += 1
+        assert (covered == 1).all(), level
+
+
+def test_scan_order_is_shared_only_when_every_layout_agrees_with_the_level_file():
+    """OPTIONAL objects: layouts whose type insertion order is a subsequence of the level file's order share one scan order
+    (variants do not multiply); a level whose optional first entry can move a type behind another keeps per-layout orders"""
+    t = compile_tables("coexistence_test", "example", 2, 100, ["TomatoLettuceSalad", "CarrotBanana"], layout_pool_size=200)
+    assert len({s.tobytes() for s in t.scan_order}) == 1
+    lvl = dict(levels.load_level_object("coexistence_test"))
+    # Tomato may appear before or after Lettuce: first entry optional, second entry later in the file
+    dyn = [dict(e) for e in lvl["DYNAMIC_OBJECTS"]]
+    tomato = next(e for e in dyn if "Tomato" in e)
+    early = {"Tomato": dict(tomato["Tomato"], OPTIONAL=0.5)}
+    late = {"Tomato": dict(tomato["Tomato"], OPTIONAL=1.0, X_POSITION=[6], Y_POSITION=[5])}
+    dyn = [early] + [e for e in dyn if "Tomato" not in e] + [late]
+    lvl["DYNAMIC_OBJECTS"] = dyn
+    import json
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(lvl, f)
+    try:
+        t2 = compile_tables(f.name, "example", 2, 100, ["TomatoLettuceSalad", "CarrotBanana"], layout_pool_size=200)
+    finally:
+        os.unlink(f.name)
+    assert len({s.tobytes() for s in t2.scan_order}) > 1
