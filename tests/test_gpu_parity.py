@@ -55,8 +55,8 @@ def test_cuda_replays_golden(path):
     assert int(env.error_flags.abs().sum()) == 0
 
 
-def _oracle_lockstep(n_envs, check, steps, A, recipes, seed, max_steps=400, end_all=True):
-    cfg = dict(level="coop_test", meta_file="example", num_agents=A, max_steps=max_steps, recipes=recipes,
+def _oracle_lockstep(n_envs, check, steps, A, recipes, seed, max_steps=400, end_all=True, level="coop_test", meta="example"):
+    cfg = dict(level=level, meta_file=meta, num_agents=A, max_steps=max_steps, recipes=recipes,
                end_all=end_all, reward_scheme=None)
     env = _make(n_envs, cfg, layout_pool_size=64, layout_seed=seed)
     lids = np.random.default_rng(seed).integers(0, 64, size=n_envs).astype(np.int32)
@@ -92,6 +92,16 @@ def _oracle_lockstep(n_envs, check, steps, A, recipes, seed, max_steps=400, end_
 def test_cuda_vs_oracle_4096_envs():
     """BASELINE config 3 shape (4096 two-agent coop_test envs): 96 sampled envs in lockstep with the oracle."""
     _oracle_lockstep(4096, 96, 120, 2, ["TomatoLettuceSalad", "CarrotBanana"], seed=5)
+
+
+def test_cuda_vs_oracle_per_layout_scan_orders():
+    """a level whose OPTIONAL first Tomato entry can move the type behind the others: layouts disagree on the scan
+    order of get_objects_at, so every layout keeps its own (tests/golden/levels/interleaved_optional.json)"""
+    import os
+    from tests.replay import ROOT
+    env = _oracle_lockstep(2048, 64, 120, 2, ["TomatoLettuceSalad", "CarrotBanana"], seed=12,
+                           level=os.path.join(ROOT, "tests/golden/levels/interleaved_optional.json"))
+    assert len({s.tobytes() for s in env.tables.scan_order}) > 1
 
 
 def test_cuda_vs_oracle_ragged_batch():
