@@ -38,6 +38,29 @@ UNIT = "env-steps/s"
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPUs of its GPU's NUMA node, so that the pinned host buffers of the e2e leg (first touch)
+    and the copy-engine traffic stay on the socket the GPU hangs off.  Best effort: returns the node or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def workload_config(n_gpus, envs_per_gpu):
     return {"workload": f"cfg4 shard: {envs_per_gpu} envs/GPU x {n_gpus} GPU, coop_test/example, 2 agents, "
                         f"per-env recipe pairs from the 8-recipe book, scheme3 uniform random actions, "
@@ -201,6 +224,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     dev = torch.device(f"cuda:{local}")
     N, A = args.envs, NUM_AGENTS
 
@@ -499,7 +523,8 @@ def run_gpu_arm(args):
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step)",
-                        "host_link_gbs": (h2d + d2h) * e2e_value / N / 1e9 / world},
+                        "host_link_gbs": (h2d + d2h) * e2e_value / N / 1e9 / world,
+                        "numa_node_of_rank0": numa_node},
                 "gpu_launches": int(launches), "clocks": clocks, "cfg3": cfg3, "device_policy": cook, "f32_obs": f32,
                 "mode": args.mode,
                 "sync_step": {"value": sync_value, "ms_per_step": ms_sync / args.steps,
