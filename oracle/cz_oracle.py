@@ -110,6 +110,25 @@ RECIPES = {
 }
 
 
+CUSTOM_RECIPES = {}      # name -> root node key; kept apart from the book (RECIPES / NUM_GOALS stay the reference's defaults)
+
+
+def register_recipe(name, tree):
+    """recipe_drawer.register_recipe (:34-35) for the oracle: `tree` = (type name, condition or None, [child trees]).
+    Node ids continue after the book's, as get_next_id would allot them."""
+    if name in CUSTOM_RECIPES:
+        return
+
+    def add(t, path):
+        typ, cond, kids = t
+        key = f"{name}/{path}"
+        kid_keys = [add(k, f"{path}.{j}") for j, k in enumerate(kids)]
+        BOOK_NODES[key] = (NUM_GOALS + sum(1 for k in BOOK_NODES if "/" in k), typ, cond, kid_keys)
+        return key
+
+    CUSTOM_RECIPES[name] = add(tree, "0")
+
+
 class _Node:
     __slots__ = ("id", "type", "cond", "kids", "marked", "hits")
 
@@ -130,7 +149,7 @@ def _expand(node):
 
 
 def make_recipe(name):
-    root = _Node(RECIPES[name])
+    root = _Node(RECIPES[name] if name in RECIPES else CUSTOM_RECIPES[name])
     return [root] + _expand(root)          # node_list, recipe.py:31-33
 
 

@@ -39,7 +39,44 @@ def _path(p):
     return os.path.join(ROOT, p) if p.endswith(".json") else p
 
 
+def register_reference_recipes(custom):
+    """cfg["custom_recipes"] = {name: (type, condition, [children])} -> the reference's own registry
+    (recipe_drawer.register_recipe, :34-35).  Returns a callable that empties RECIPE_STORE again."""
+    from oracle.ref_harness import load_reference
+    load_reference()                       # puts /root/reference (behind oracle/refshim) on the path
+    from cooking_zoo.cooking_book import recipe_drawer as rd
+    from cooking_zoo.cooking_book.recipe import Recipe, RecipeNode
+    from cooking_zoo.cooking_world import world_objects as wo
+    from cooking_zoo.cooking_world.constants import ChopFoodStates, BlenderFoodStates
+    conds = {"chopped": [("chop_state", ChopFoodStates.CHOPPED)], "mashed": [("blend_state", BlenderFoodStates.MASHED)],
+             None: None}
+
+    def build(t):
+        typ, cond, kids = t
+        return RecipeNode(root_type=getattr(wo, typ), id_num=rd.get_next_id(), name=typ, conditions=conds[cond],
+                          contains=[build(k) for k in kids])
+    roots = {name: build(t) for name, t in custom.items()}
+    for name, root in roots.items():
+        rd.register_recipe(Recipe(root, rd.NUM_GOALS), name)
+    # cooking_env copies NUM_GOALS by value when it is imported (cooking_env.py:7), so a user has to register before
+    # importing the environment; the harness imported it already, so the copy is refreshed to what that order gives
+    import cooking_zoo.environment.cooking_env as ce
+    stale = ce.NUM_GOALS
+    ce.NUM_GOALS = rd.NUM_GOALS
+
+    def undo():
+        rd.RECIPE_STORE.clear()
+        ce.NUM_GOALS = stale
+    return undo
+
+
 def record(cfg, seeds, T, policy, teleports=None):
+    if cfg.get("custom_recipes"):
+        undo = register_reference_recipes(cfg["custom_recipes"])
+        try:
+            return record({k: v for k, v in cfg.items() if k != "custom_recipes"}, seeds, T, policy, teleports)
+        finally:
+            undo()
     traces = []
     for n_trace, seed in enumerate(seeds):
         spawn = cfg.get("spawn")      # {"respawn", "despawn", "grace", "seed"}: trace n is environment n of the stream
@@ -216,9 +253,28 @@ def main_policy():
     save("policy_switch", c, record(c, range(1190, 1194), 300, Heuristic(0.1)), 300)
 
 
+def main_custom():
+    """recipes registered through the reference's register_recipe hook (cooking_env.py:100-105): a root with two
+    children that each have their own child, and a Counter root — shapes the book does not have.  The cooks follow book
+    recipes with the same ingredients (CookingAgent reads RECIPES, not the store: base_agent.py:36)."""
+    base = {"level": "coop_test", "meta_file": "example", "max_steps": 300, "num_agents": 2, "end_all": True}
+    custom = {"TwoPlates": ("Deliversquare", None, [("Plate", None, [("Tomato", "chopped", [])]),
+                                                    ("Plate", None, [("Lettuce", "chopped", [])])]),
+              "CounterSalad": ("Counter", None, [("Plate", None, [("Tomato", "chopped", []), ("Lettuce", "chopped", [])])]),
+              "BareCarrot": ("Carrot", "mashed", [])}
+    cfg = dict(base, recipes=["TwoPlates", "CounterSalad"], custom_recipes=custom,
+               policy_recipes=["TomatoLettuceSalad", "TomatoLettuceSalad"],
+               reward_scheme={"recipe_reward": 20, "max_time_penalty": -5, "recipe_penalty": -40, "recipe_node_reward": 1.5})
+    save("custom_recipes", cfg, record(cfg, range(1300, 1308), 300, Heuristic(0.15)), 300)
+    cfg2 = dict(cfg, recipes=["BareCarrot", "TwoPlates"], end_all=False, policy_recipes=["MashedCarrotBanana", "TomatoSalad"])
+    save("custom_recipes_any", cfg2, record(cfg2, range(1310, 1314), 300, Heuristic(0.15)), 300)
+
+
 def main():
     if sys.argv[1:] == ["policy"]:
         return main_policy()
+    if sys.argv[1:] == ["custom"]:
+        return main_custom()
     base = {"level": "coop_test", "meta_file": "example", "max_steps": 400, "reward_scheme": None}
     # BASELINE config 1: single agent, TomatoLettuceSalad
     cfg1 = dict(base, num_agents=1, recipes=["TomatoLettuceSalad"], end_all=False)
@@ -290,6 +346,7 @@ def main():
     cfgsp4 = dict(cfg4a, max_steps=10000, spawn={"respawn": 0.2, "despawn": 0.15, "grace": 3, "seed": 77})
     save("spawn_open4", cfgsp4, record(cfgsp4, range(810, 816), 200, uniform), 200)
     main_policy()
+    main_custom()
 
 
 if __name__ == "__main__":

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle.cz_oracle import OracleEnv
-from tests.replay import golden_files, load_golden, assert_state_equal, assert_obs_equal, bits, STATE_KEYS
+from tests.replay import golden_files, load_golden, assert_state_equal, assert_obs_equal, bits, STATE_KEYS, package_recipes
 
 pytestmark = pytest.mark.gpu
 
@@ -27,7 +27,8 @@ def test_cuda_replays_golden(path):
     g = load_golden(path)
     cfg = g["config"]
     n, A = len(g["layouts"]), cfg["num_agents"]
-    env = _make(n, cfg, layouts=g["layouts"])
+    with package_recipes(cfg):          # recipes registered through register_recipe (custom_recipes*.npz)
+        env = _make(n, cfg, layouts=g["layouts"])
     obs = env.reset(layout_ids=np.arange(n)).cpu().numpy()
     states = env.export_state()
     for k in range(n):

@@ -73,10 +73,12 @@ def test_compile_rejects_what_the_reference_rejects():
 
 @pytest.mark.parametrize("path", golden_files()[:4], ids=lambda p: p.split("/")[-1][:-4])
 def test_tables_compile_for_golden_configs(path):
+    from tests.replay import package_recipes
     g = load_golden(path)
     cfg = g["config"]
-    t = compile_tables(cfg["level"], cfg["meta_file"], cfg["num_agents"], cfg["max_steps"], cfg["recipes"],
-                       cfg["reward_scheme"], cfg["end_all"], layouts=g["layouts"])
+    with package_recipes(cfg):
+        t = compile_tables(cfg["level"], cfg["meta_file"], cfg["num_agents"], cfg["max_steps"], cfg["recipes"],
+                           cfg["reward_scheme"], cfg["end_all"], layouts=g["layouts"])
     assert t.num_layouts == len(g["layouts"])
     # pooled initial records decode to the recorded initial object positions
     objs = g["objs"][0, 0]
