@@ -194,10 +194,12 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each "step" = every host core advances its own environment once; bounded so the arm ends in minutes
-    value, procs, wall = cpu_port_throughput(args.steps, args.warmup)
+    # each "step" = every host core advances its own environment once; the timed sample is bounded on both sides:
+    # at least 2000 env-steps per core (a short --steps would time little more than noise), at most 60000 (minutes)
+    timed, warm = min(max(args.steps, 2000), 60000), min(max(args.warmup, 50), 2000)
+    value, procs, wall = cpu_port_throughput(timed, warm)
     ms = 1000.0 * procs / value
-    sample = (f"{procs} processes x ({args.warmup} warm-up + {args.steps} timed) env-steps of the oracle port "
+    sample = (f"{procs} processes x ({warm} warm-up + {timed} timed) env-steps of the oracle port "
               f"(oracle/cz_oracle.py), one two-agent coop_test env per process, observe() for both agents")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
