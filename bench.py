@@ -348,28 +348,32 @@ def run_gpu_arm(args):
             a1.record()
             torch.cuda.synchronize(dev)
             per_launch = n3 * k3 / (a0.elapsed_time(a1) / 1e3)
-            # the same launches captured once in a CUDA graph (one graph = `ring` steps) and replayed
-            graph = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                for s in range(ring):
-                    env3.step(act3[s])
-                side.synchronize()
-                with torch.cuda.graph(graph, stream=side):
+            # the same launches captured once in a CUDA graph (one graph = `ring` steps) and replayed: with the actions of the
+            # K steps resident, and with the actions generated on the device inside the graph (cz_random_actions)
+            def graphed_rate(next_actions):
+                graph = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
                     for s in range(ring):
-                        env3.step(act3[s])
-            torch.cuda.current_stream(dev).wait_stream(side)
-            for _ in range(5):
-                graph.replay()
-            torch.cuda.synchronize(dev)
-            reps = 200
-            a0.record()
-            for _ in range(reps):
-                graph.replay()
-            a1.record()
-            torch.cuda.synchronize(dev)
-            graphed = n3 * ring * reps / (a0.elapsed_time(a1) / 1e3)
+                        env3.step(next_actions(s))
+                    side.synchronize()
+                    with torch.cuda.graph(graph, stream=side):
+                        for s in range(ring):
+                            env3.step(next_actions(s))
+                torch.cuda.current_stream(dev).wait_stream(side)
+                for _ in range(5):
+                    graph.replay()
+                torch.cuda.synchronize(dev)
+                reps = 200
+                a0.record()
+                for _ in range(reps):
+                    graph.replay()
+                a1.record()
+                torch.cuda.synchronize(dev)
+                return n3 * ring * reps / (a0.elapsed_time(a1) / 1e3)
+            graphed = graphed_rate(lambda s: act3[s])
+            graphed_dev = graphed_rate(lambda s: env3.random_actions(s))
             # pipelined throughput mode at this size
             env3p = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
                                       action_scheme="scheme3", device=str(dev), layout_pool_size=400, layout_seed=0,
@@ -390,7 +394,9 @@ def run_gpu_arm(args):
             cfg3 = {"workload": "cfg3: 4096 two-agent coop_test envs, 1 GPU, random actions, feature_vector obs",
                     "per_launch_env_steps_per_s": per_launch, "cuda_graph_env_steps_per_s": graphed,
                     "k_steps_per_launch": {"K": ring, "env_steps_per_s": graphed,
-                                           "how": f"one CUDA graph launch = {ring} consecutive cz_step kernels (actions for the K steps resident)"},
+                                           "how": f"one CUDA graph launch = {ring} consecutive cz_step kernels, actions of the K steps resident",
+                                           "device_actions_env_steps_per_s": graphed_dev,
+                                           "device_actions_how": f"one CUDA graph launch = {ring} x (cz_random_actions + cz_step)"},
                     "pipelined_env_steps_per_s": piped,
                     "note": "20 MB per step: launch/latency bound, not HBM bound"}
             env3.close()

@@ -174,6 +174,18 @@ class BatchedCookingEnv:
             with torch.cuda.device(self.device):
                 _native.check(self.lib.cz_pipeline_wait(self._handle, self._stream()))
 
+    def random_actions(self, step, out=None):
+        """Uniform random actions generated on the device (the synthetic streams of BASELINE configs 3 / 4): a
+        counter-based draw keyed by (seed, global environment, step, agent) -> u8 [N, A]."""
+        if out is None:
+            if getattr(self, "_rand_actions", None) is None:
+                self._rand_actions = torch.zeros((self.num_envs, self.num_agents), dtype=torch.uint8, device=self.device)
+            out = self._rand_actions
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.cz_random_actions(self._handle, out.data_ptr(), self.num_envs, self.seed, int(step),
+                                                     self.env_offset, self._stream()))
+        return out
+
     def heuristic_actions(self, cook_recipes=None):
         """One decision of the reference's scripted cook (CookingAgent.step, cooking_agents/cooking_agent.py:9-17)
         per agent of every environment, computed on the device from the current state.

@@ -345,3 +345,29 @@ extern "C" int cz_policy_act(const cz_policy* p, const uint32_t* state, const ui
   CZ_CUDA(cudaGetLastError());
   return CZ_OK;
 }
+
+// ---- synthetic action streams on the device -------------------------------------------
+#define CZ_ACTION_STREAM 0xA5A5A5A5A5A5A5A5ull  // keeps the action stream apart from the spawn stream of the same seed
+
+__global__ void cz_random_actions_kernel(uint8_t* __restrict__ actions, int n_envs, int A, int num_actions, uint64_t seed,
+                                         uint64_t step, int64_t env_offset) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_envs * A) return;
+  const int env = k / A, i = k - env * A;
+  const double u = cz_uniform(seed ^ CZ_ACTION_STREAM, (uint64_t)(env_offset + env), 0, step, (uint64_t)i);
+  const int a = (int)(u * num_actions);
+  actions[k] = (uint8_t)(a < num_actions ? a : num_actions - 1);
+}
+
+extern "C" int cz_random_actions(const cz_tables* t, uint8_t* actions, int n_envs, uint64_t seed, uint64_t step,
+                                 int64_t env_offset, void* stream) {
+  if (!t || !actions) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (n_envs < 0) return cz_fail(CZ_EINVAL, "%s", "negative n_envs");
+  if (n_envs == 0) return CZ_OK;
+  const int total = n_envs * t->dev.A, num_actions = t->dev.scheme == 1 ? 8 : 5;  // len(ACTIONS), actions.py:2-17, 39-50
+  cz_random_actions_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(actions, n_envs, t->dev.A, num_actions, seed, step,
+                                                                               env_offset);
+  g_launches.fetch_add(1);
+  CZ_CUDA(cudaGetLastError());
+  return CZ_OK;
+}

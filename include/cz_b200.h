@@ -237,6 +237,13 @@ int cz_policy_destroy(cz_policy* p);
 int cz_policy_act(const cz_policy* p, const uint32_t* state, const uint8_t* cook_recipes, uint8_t* actions,
                   uint8_t* crashed, int n_envs, void* stream);
 
+/* Synthetic action streams generated on the device (uniform random actions):
+ * actions[e][i] = floor(u * len(ACTIONS)) with u = cz_spawn_uniform(seed ^ 0xA5A5A5A5A5A5A5A5, env_offset + e, 0, step, i),
+ * len(ACTIONS) = 5 under scheme3, 8 under scheme1 (cooking_world/actions.py:2-17, 39-50).  Counter-based: the stream
+ * of an environment does not depend on the batch it is stepped in. */
+int cz_random_actions(const cz_tables* t, uint8_t* actions, int n_envs, uint64_t seed, uint64_t step,
+                      int64_t env_offset, void* stream);
+
 /* Number of kernels launched by this library since load (the bench's gpu_launches claim). */
 uint64_t cz_launch_count(void);
 

@@ -241,3 +241,32 @@ def test_large_batch_two_kernel_step_equals_the_fused_kernel_on_a_ragged_batch(m
         assert torch.equal(oa.view(torch.int64), ob.view(torch.int64)), t
         assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(ta, tb) and torch.equal(ua, ub)
     assert torch.equal(a.state, b.state)
+
+
+def test_device_action_stream_matches_its_definition_and_is_shard_independent():
+    """cz_random_actions: floor(cz_spawn_uniform(seed ^ 0xA5.., env, 0, step, agent) * len(ACTIONS)); scheme1 draws from 8
+    actions, scheme3 from 5; the stream of an environment does not depend on the shard it lives in"""
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=50,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    for scheme, n_act in (("scheme3", 5), ("scheme1", 8)):
+        c = dict(cfg, action_scheme=scheme)
+        whole = _make(1000, c, seed=77)
+        part = _make(300, c, seed=77, env_offset=700)
+        lib = whole.lib
+        for step in (0, 1, 12345):
+            a = whole.random_actions(step).cpu().numpy()
+            b = part.random_actions(step).cpu().numpy()
+            assert np.array_equal(a[700:], b)
+            assert a.max() == n_act - 1 and a.min() == 0
+            for e in (0, 1, 499, 999):
+                for i in range(2):
+                    u = lib.cz_spawn_uniform(77 ^ 0xA5A5A5A5A5A5A5A5, e, 0, step, i)
+                    assert a[e, i] == int(u * n_act)
+        counts = np.bincount(whole.random_actions(5).cpu().numpy().ravel(), minlength=n_act)
+        assert counts.min() > 0.6 * 2000 / n_act
+    # the stream drives a whole rollout without the host: 200 steps, every environment keeps stepping
+    env = _make(4096, cfg, auto_reset=True, seed=3)
+    env.reset()
+    for t in range(200):
+        env.step(env.random_actions(t))
+    assert int(env.error_flags.abs().sum()) == 0 and int(env.info()["t"].max()) <= 50
