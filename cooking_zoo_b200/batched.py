@@ -26,13 +26,13 @@ class _LazyInfo:
         return self._env.info()[key]
 
     def keys(self):
-        return ("t", "recipe_done", "active", "error_flags")
+        return ("t", "done", "recipe_done", "active", "error_flags")
 
     def __iter__(self):
         return iter(self.keys())
 
     def __len__(self):
-        return 4
+        return 5
 
 
 class BatchedCookingEnv:
@@ -129,6 +129,12 @@ class BatchedCookingEnv:
             mk = torch.as_tensor(mask).to(torch.uint8).to(self.device).contiguous()
         with torch.cuda.device(self.device):
             f32 = self.obs_dtype == torch.float32
+            if self.pipelined:
+                # drain the internal streams (dynamics / row writer still in flight) and keep stepping from the half
+                # that holds the current state: a masked reset must land next to the untouched environments
+                cur = max(0, self.lib.cz_pipeline_current(self._handle))
+                _native.check(self.lib.cz_pipeline_reset(self._handle, cur))
+                self.state = self._state2[cur]
             _native.check(self.lib.cz_reset(self._handle, self.state.data_ptr(), lid.data_ptr(),
                                             rid.data_ptr() if rid is not None else None,
                                             mk.data_ptr() if mk is not None else None,
@@ -136,9 +142,6 @@ class BatchedCookingEnv:
             if f32:
                 _native.check(self.lib.cz_observe_f32(self._handle, self.state.data_ptr(), self.obs.data_ptr(), N,
                                                       self._stream()))
-            if self.pipelined:
-                torch.cuda.current_stream(self.device).synchronize()
-                _native.check(self.lib.cz_pipeline_reset(self._handle, 0))
         return self.obs
 
     def step(self, actions):
@@ -231,13 +234,14 @@ class BatchedCookingEnv:
         return self.obs
 
     def info(self):
-        """Info tensors decoded from the packed state: t[N], recipe_done[N, R], active[N, A], error_flags[N]
+        """Info tensors decoded from the packed state: t[N], done[N], recipe_done[N, R], active[N, A], error_flags[N]
         (cooking_env.py:248, 329-330).  Decoding launches small torch kernels, so step() returns a lazy
         mapping (`info["t"]`) instead of calling this on the hot path."""
         t = self.tables
         misc = self.state[t.num_dyn_slots + t.num_agents:]
         agents = self.state[t.num_dyn_slots:t.num_dyn_slots + t.num_agents]
         return {"t": misc[ROW_TINFO] & 0xFFFFF,
+                "done": (misc[ROW_TINFO] >> 20) & 1,       # episode over: recipes complete or t >= max_steps
                 "recipe_done": torch.stack([(misc[ROW_MARKS] >> (8 * r)) & 1 for r in range(t.num_recipes)], 1),
                 "active": ((agents >> 15) & 1).T,
                 "error_flags": self.error_flags}
