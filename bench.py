@@ -165,6 +165,54 @@ def cpu_port_throughput(steps_per_worker, warm, procs=None):
     return total / max(times), procs, wall
 
 
+def _ref_worker(args):
+    """One process of the reference arm: the UNMODIFIED reference environment (oracle/_ref or /root/reference behind the
+    import stubs of oracle/refshim), driven below its PettingZoo wrapper exactly as SURVEY.md §8(c) prescribes:
+    accumulated_step(actions) + observe(agent) for every agent, reset() when the episode ends."""
+    wid, n_steps, warm, seed = args
+    import random
+    from oracle.ref_loader import load_reference
+    ce = load_reference()
+    random.seed(seed * 1000 + wid)
+    np.random.seed(seed * 1000 + wid)
+    rng = np.random.default_rng(seed * 1000 + wid)
+    rec = [BOOK[int(rng.integers(8))], BOOK[int(rng.integers(8))]]
+    env = ce.CookingEnvironment(level=LEVEL, meta_file=META, num_agents=NUM_AGENTS, max_steps=MAX_STEPS, recipes=rec,
+                                obs_spaces=["feature_vector"] * NUM_AGENTS, end_condition_all_dishes=True,
+                                action_scheme="scheme3")
+    env.reset()
+    agents = list(env.possible_agents)
+    acts = rng.integers(0, 5, size=(n_steps + warm, NUM_AGENTS)).tolist()
+    t0 = None
+    for s in range(n_steps + warm):
+        if s == warm:
+            t0 = time.perf_counter()
+        env.accumulated_step(acts[s])
+        for a in agents:
+            env.observe(a)
+        if any(env.terminations.values()) or any(env.truncations.values()):
+            env.reset()
+    return time.perf_counter() - t0
+
+
+def reference_available():
+    try:
+        from oracle.ref_loader import reference_available as ok
+        return ok()
+    except Exception:
+        return False
+
+
+def cpu_reference_throughput(steps_per_worker, warm, procs=None):
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        t0 = time.perf_counter()
+        times = pool.map(_ref_worker, [(w, steps_per_worker, warm, 7) for w in range(procs)])
+        wall = time.perf_counter() - t0
+    return steps_per_worker * procs / max(times), procs, wall
+
+
 def cpu_port_c_throughput(n_envs=4096, steps=60, warm=5):
     """The compiled restatement (oracle/cz_oracle.c) on all host threads: an honest compiled-CPU data point
     beside the Python-port baseline (the reference itself is Python)."""
@@ -191,21 +239,43 @@ def cpu_port_c_throughput(n_envs=4096, steps=60, warm=5):
 
 
 def run_reference_arm(args):
+    """bench.py --impl reference: the reference's own CPU implementation of the path on every host core.  The reference
+    is pure Python; `python -m oracle.make_ref` (run by __graft_entry__.build()) copies it verbatim into the git-ignored
+    oracle/_ref/, which travels to the box.  Only when that copy is missing does the arm fall back to the oracle port
+    (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     # each "step" = every host core advances its own environment once; the timed sample is bounded on both sides:
     # at least 2000 env-steps per core (a short --steps would time little more than noise), at most 60000 (minutes)
     timed, warm = min(max(args.steps, 2000), 60000), min(max(args.warmup, 50), 2000)
-    value, procs, wall = cpu_port_throughput(timed, warm)
+    extra = {}
+    if reference_available():
+        kind = "reference"
+        value, procs, wall = cpu_reference_throughput(timed, warm)
+        from oracle.ref_loader import REFERENCE_ROOT
+        what = (f"the unmodified reference (cooking_zoo.environment.cooking_env.CookingEnvironment from {REFERENCE_ROOT}, "
+                f"behind the import stubs of oracle/refshim): accumulated_step + observe() for both agents, reset() on episode end")
+        try:        # the oracle port beside it (informational: same loop, the restatement instead of the reference)
+            pv, _, _ = cpu_port_throughput(timed, warm)
+            extra["oracle_port"] = {"value": pv, "unit": UNIT, "cores": procs, "kind": "port"}
+        except Exception as ex:
+            extra["oracle_port"] = {"unavailable": str(ex)[:120]}
+    else:
+        kind = "port"
+        value, procs, wall = cpu_port_throughput(timed, warm)
+        what = "the oracle port (oracle/cz_oracle.py): oracle/_ref is missing, run `python -m oracle.make_ref`"
     ms = 1000.0 * procs / value
-    sample = (f"{procs} processes x ({warm} warm-up + {timed} timed) env-steps of the oracle port "
-              f"(oracle/cz_oracle.py), one two-agent coop_test env per process, observe() for both agents")
+    sample = (f"{procs} processes x ({warm} warm-up + {timed} timed) env-steps of {what}; one two-agent coop_test "
+              f"environment per process, recipe pair drawn from the 8-recipe book, uniform random scheme3 actions")
+    cfg = workload_config(args.gpus, ENVS_PER_GPU)
+    cfg["reference_arm"] = (f"same environment configuration, stepped as {procs} independent single-environment processes "
+                            f"(a multiprocessing vector env over the host cores), not as one {ENVS_PER_GPU}-environment batch")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, ENVS_PER_GPU),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "config": cfg,
+            "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample}, **extra),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -504,14 +574,28 @@ def run_gpu_arm(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         cpu = None
         if not args.no_cpu:
+            port = None
             try:
                 v, procs, wall = cpu_port_throughput(args.cpu_steps, 200)
-            except Exception as ex:     # e.g. no fork / spawn on the box: one process, in this interpreter
-                sys.stderr.write(f"cpu_baseline: process pool failed ({ex!r}); timing a single process\n")
-                v, procs, wall = cpu_port_throughput(args.cpu_steps, 200, procs=1)
-            cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
-                   "sample": f"{procs} processes x {args.cpu_steps} env-steps of oracle/cz_oracle.py (Python restatement "
-                             f"of the Python reference), same level/recipes/action distribution, {wall:.1f} s wall"}
+                port = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+                        "sample": f"{procs} processes x {args.cpu_steps} env-steps of oracle/cz_oracle.py (Python restatement "
+                                  f"of the Python reference), same level/recipes/action distribution, {wall:.1f} s wall"}
+            except Exception as ex:     # e.g. no fork / spawn on the box
+                port = {"unavailable": f"{type(ex).__name__}: {str(ex)[:120]}"}
+            if reference_available():
+                try:
+                    v, procs, wall = cpu_reference_throughput(args.cpu_steps, 200)
+                    cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "reference",
+                           "sample": f"{procs} processes x {args.cpu_steps} env-steps of the unmodified reference "
+                                     f"(CookingEnvironment.accumulated_step + observe for both agents, reset on episode end; "
+                                     f"oracle/_ref behind oracle/refshim), same level / recipe book / action distribution, "
+                                     f"{wall:.1f} s wall"}
+                except Exception as ex:
+                    sys.stderr.write(f"cpu_baseline: the reference arm failed ({ex!r}); reporting the port\n")
+            if cpu is None:
+                cpu = dict(port)
+            else:
+                cpu["oracle_port"] = port
             try:
                 vc, thr = cpu_port_c_throughput()
                 cpu["compiled_port"] = {"value": vc, "unit": UNIT, "threads": thr,

@@ -11,9 +11,13 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CZ_B200_LIB") or os.path.join(HERE, "libcz_b200.so")   # override: A/B builds of the same ABI
-ABI_VERSION = 1
+ABI_VERSION = 2
 STEP_AUTO_RESET = 1
 STEP_OBS_F32 = 2
+STEP_DEVICE_ACTIONS = 4
+STEP_KEEP_ALL = 8
+ERR_BITS = {1: "CUTBOARD_NONE", 2: "REMOVE", 4: "SWITCH_LINK", 8: "SPAWN_LOC", 16: "TRUNC_DESPAWN", 32: "OBS_OVERFLOW",
+            64: "OFFGRID", 128: "BAD_ID"}
 
 _P = C.c_void_p
 
@@ -50,8 +54,10 @@ SIGNATURES = {
     "cz_tables_create": (C.c_int, [C.POINTER(TableDesc), C.c_int, C.POINTER(_P)]),
     "cz_tables_destroy": (C.c_int, [_P]),
     "cz_state_rows": (C.c_int, [_P]),
-    "cz_reset": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
-    "cz_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint64, C.c_int64, _P]),
+    "cz_reset": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "cz_layout_ids": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_int64, C.c_uint64, _P]),
+    "cz_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_int64,
+                          C.c_uint64, _P]),
     "cz_observe": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "cz_observe_f32": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "cz_step_pipelined": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint64, C.c_int64, _P]),

@@ -114,16 +114,25 @@ class BatchedCookingEnv:
         recipe_ids [N, R] index tables.recipe_names; mask selects the environments to reset."""
         N = self.num_envs
         if layout_ids is None:
-            layout_ids = self.default_layout_ids(episode=0)
-        lid = torch.as_tensor(layout_ids, dtype=torch.int32).to(self.device).contiguous()
+            lid = self.default_layout_ids(episode=0)
+        else:
+            if not isinstance(layout_ids, torch.Tensor) or not layout_ids.is_cuda:
+                # host arrays are checked on the host; device tensors are range-checked by the kernel
+                # (CZ_ERR_BAD_ID in error_flags) so that a reset never forces a device synchronisation
+                chk = np.asarray(layout_ids)
+                if chk.size and (chk.min() < 0 or chk.max() >= self.tables.num_layouts):
+                    raise ValueError("layout id out of range")
+            lid = torch.as_tensor(layout_ids, dtype=torch.int32).to(self.device).contiguous()
         if lid.shape != (N,):
             raise ValueError("layout_ids must have shape [num_envs]")
-        if int(lid.min()) < 0 or int(lid.max()) >= self.tables.num_layouts:
-            raise ValueError("layout id out of range")
         rid = mk = None
         if recipe_ids is not None:
+            if not isinstance(recipe_ids, torch.Tensor) or not recipe_ids.is_cuda:
+                chk = np.asarray(recipe_ids)
+                if chk.size and (chk.min() < 0 or chk.max() >= len(self.tables.recipe_names)):
+                    raise ValueError("recipe_ids must be [num_envs, R] indices into tables.recipe_names")
             rid = torch.as_tensor(recipe_ids, dtype=torch.uint8).to(self.device).contiguous()
-            if rid.shape != (N, self.tables.num_recipes) or int(rid.max()) >= len(self.tables.recipe_names):
+            if rid.shape != (N, self.tables.num_recipes):
                 raise ValueError("recipe_ids must be [num_envs, R] indices into tables.recipe_names")
         if mask is not None:
             mk = torch.as_tensor(mask).to(torch.uint8).to(self.device).contiguous()
@@ -138,7 +147,8 @@ class BatchedCookingEnv:
             _native.check(self.lib.cz_reset(self._handle, self.state.data_ptr(), lid.data_ptr(),
                                             rid.data_ptr() if rid is not None else None,
                                             mk.data_ptr() if mk is not None else None,
-                                            None if f32 else self.obs.data_ptr(), N, self._stream()))
+                                            None if f32 else self.obs.data_ptr(), self.error_flags.data_ptr(), N,
+                                            self._stream()))
             if f32:
                 _native.check(self.lib.cz_observe_f32(self._handle, self.state.data_ptr(), self.obs.data_ptr(), N,
                                                       self._stream()))
@@ -151,6 +161,8 @@ class BatchedCookingEnv:
         if a.shape != (self.num_envs, self.num_agents):
             raise ValueError("actions must have shape [num_envs, num_agents]")
         if a.dtype != torch.uint8 or a.device != self.device or not a.is_contiguous():
+            # staging copy on the caller's stream: in pipelined mode that stream trails the previous step's dynamics
+            # (cz_step_pipelined orders it), so the buffer is never overwritten while a dynamics kernel still reads it
             self._actions.copy_(a)
             a = self._actions
         if self.pipelined:
@@ -158,9 +170,45 @@ class BatchedCookingEnv:
         with torch.cuda.device(self.device):
             _native.check(self.lib.cz_step(self._handle, self.state.data_ptr(), a.data_ptr(), self.obs.data_ptr(),
                                            self.reward.data_ptr(), self.terminated.data_ptr(),
-                                           self.truncated.data_ptr(), self.error_flags.data_ptr(), self.num_envs,
-                                           self._flags, self.seed, self.env_offset, self._stream()))
+                                           self.truncated.data_ptr(), self.error_flags.data_ptr(), self.num_envs, 1,
+                                           self._flags, self.seed, self.env_offset, 0, self._stream()))
         return self.obs, self.reward, self.terminated, self.truncated, self._info
+
+    def step_k(self, k_steps, actions=None, action_step=0, keep_all=False):
+        """k_steps consecutive steps in one call (cz_step's k_steps: one launch of the warp-per-environment kernel when
+        the tables and the batch size allow it, the per-step kernels otherwise; same results either way).
+
+        actions: uint8 [k_steps, N, A] on the device, or None: step j's actions are drawn on the device from the
+        counter stream of random_actions() at step index action_step + j.  keep_all=False: the usual output buffers
+        hold the LAST step's observations / rewards / flags.  keep_all=True: returns fresh [k_steps, ...] tensors with
+        every step's outputs.  Not available in pipelined mode."""
+        if self.pipelined:
+            raise _native.NativeError("step_k runs on the in-place state (pipelined=False)")
+        N, A, L, K = self.num_envs, self.num_agents, self.obs_len, int(k_steps)
+        flags = self._flags
+        a_ptr = None
+        if actions is None:
+            flags |= _native.STEP_DEVICE_ACTIONS
+        else:
+            a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
+            if a.shape != (K, N, A):
+                raise ValueError("actions must have shape [k_steps, num_envs, num_agents]")
+            a = a.to(device=self.device, dtype=torch.uint8).contiguous()
+            self._k_actions = a          # keep alive until the launch has consumed it
+            a_ptr = a.data_ptr()
+        if keep_all:
+            flags |= _native.STEP_KEEP_ALL
+            obs = torch.empty((K, N, A, L), dtype=self.obs_dtype, device=self.device)
+            rew = torch.empty((K, N, A), dtype=torch.float64, device=self.device)
+            term = torch.empty((K, N, A), dtype=torch.uint8, device=self.device)
+            trunc = torch.empty((K, N, A), dtype=torch.uint8, device=self.device)
+        else:
+            obs, rew, term, trunc = self.obs, self.reward, self.terminated, self.truncated
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.cz_step(self._handle, self.state.data_ptr(), a_ptr, obs.data_ptr(), rew.data_ptr(),
+                                           term.data_ptr(), trunc.data_ptr(), self.error_flags.data_ptr(), N, K, flags,
+                                           self.seed, self.env_offset, int(action_step), self._stream()))
+        return obs, rew, term, trunc, self._info
 
     def _step_pipelined(self, a):
         with torch.cuda.device(self.device):
@@ -247,9 +295,13 @@ class BatchedCookingEnv:
                 "error_flags": self.error_flags}
 
     def default_layout_ids(self, episode=0):
-        P = self.tables.num_layouts
-        return np.array([self.lib.cz_layout_draw(self.seed, self.env_offset + e, episode) % P
-                         for e in range(self.num_envs)], np.int32)
+        """int32 [N] on the device: pool index cz_layout_draw(seed, env_offset + e, episode) % P of every environment
+        (one small kernel: the draw CZ_STEP_AUTO_RESET makes inside the step kernels)."""
+        out = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.cz_layout_ids(self._handle, out.data_ptr(), self.num_envs, self.seed, self.env_offset,
+                                                 int(episode), self._stream()))
+        return out
 
     # ------------------------------------------------------------------ state import/export
     def export_state(self, env=None):

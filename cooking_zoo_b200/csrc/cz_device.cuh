@@ -68,6 +68,7 @@ struct SmemTabs {
   uint8_t type_base[CZ_MAX_TYPES];
   uint8_t type_count[CZ_MAX_TYPES];
   uint8_t recipe_len[CZ_SB];
+  uint8_t recipe_desc[CZ_SB][CZ_MAX_NODES];  // per node: bit j set iff node j is the node itself or one of its descendants (cz_warp.cuh)
   VarTabs var[1];  // [V], V <= CZ_SV
 };
 

@@ -384,9 +384,19 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
         write_obs = do_reset;
         if (do_reset) {
           layout = layout_ids[env];
+          if ((unsigned)layout >= (unsigned)T.P) {  // a direct C caller passed an id outside the pool: clamp and flag
+            layout = 0;
+            e.err |= CZ_ERR_BAD_ID;
+          }
           uint32_t rids = 0;
-          for (int r = 0; r < T.R; ++r)
-            rids |= (uint32_t)(recipe_ids ? recipe_ids[(size_t)env * T.R + r] : __ldg(T.default_recipes + r)) << (8 * r);
+          for (int r = 0; r < T.R; ++r) {
+            uint32_t id = recipe_ids ? recipe_ids[(size_t)env * T.R + r] : __ldg(T.default_recipes + r);
+            if (id >= (uint32_t)T.B) {
+              id = 0;
+              e.err |= CZ_ERR_BAD_ID;
+            }
+            rids |= id << (8 * r);
+          }
           e.rids = rids;
         }
       } else if (MODE == MODE_STEP) {
@@ -688,6 +698,10 @@ struct cz_tables {
   int simple;
   int simple2;
   int two_kernel_min_envs;  // in-place step of at least this many environments: dynamics kernel, then the row-writer kernel
+  int warp_max_envs;        // single in-place step of at most this many environments: warp-per-environment kernel (cz_warp.cuh)
+  int warp_k_max_envs;      // k_steps > 1 with at most this many environments: one persistent launch of that kernel
+  uint8_t* d_rand;          // scratch for device-generated actions outside the warp kernel
+  int rand_envs;
   int num_sms;
   void* allocs[32];
   int n_allocs;
@@ -722,6 +736,7 @@ static size_t cz_smem_bytes(const CzDev& T) {
 }
 
 #include "cz_obs32.cuh"
+#include "cz_warp.cuh"
 
 extern "C" int cz_abi_version(void) { return CZ_ABI_VERSION; }
 extern "C" const char* cz_last_error(void) { return g_err; }
@@ -879,6 +894,14 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
         w.recipe_spans[b][k] = spans[b * CZ_MAX_NODES + k];
       }
       w.recipe_len[b] = d->recipe_len[b];
+      // descendants of every node (children come later in node_list, so one backward pass closes the relation)
+      for (int k = CZ_MAX_NODES - 1; k >= 0; --k) {
+        uint32_t desc = 1u << k;
+        const uint32_t kids = d->recipe_nodes[b * CZ_MAX_NODES + k] >> 16;
+        for (int j = k + 1; j < CZ_MAX_NODES; ++j)
+          if (kids >> j & 1u) desc |= w.recipe_desc[b][j];
+        w.recipe_desc[b][k] = (uint8_t)desc;
+      }
     }
     for (int i = 0; i < T.D; ++i) { w.slot_type[i] = d->slot_type[i]; w.slot_tf[i] = d->type_flags[d->slot_type[i]]; }
     for (int i = 0; i < T.T; ++i) { w.type_base[i] = d->type_base[i]; w.type_count[i] = d->type_count[i]; }
@@ -900,6 +923,10 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     if (g && g[0] == '1') t->simple = t->simple2 = 0;
     const char* k = getenv("CZ_TWO_KERNEL_MIN_ENVS");
     t->two_kernel_min_envs = k ? atoi(k) : 49152;  // measured crossover between 32768 and 65536 (profiles/r01_two_kernel_sweep.txt)
+    const char* w = getenv("CZ_WARP_MAX_ENVS");
+    t->warp_max_envs = w ? atoi(w) : 8192;
+    const char* wk = getenv("CZ_WARP_K_MAX_ENVS");
+    t->warp_k_max_envs = wk ? atoi(wk) : 32768;
   }
 #define SET_SMEM(K) CZ_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin))
 #define SET_MODE(M)                                                                                    \
@@ -913,6 +940,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   SET_SMEM((cz_env_kernel<M, OBS_NONE, 3>)); SET_SMEM((cz_env_kernel<M, OBS_NONE, 4>))
   SET_MODE(MODE_STEP); SET_MODE(MODE_RESET); SET_MODE(MODE_OBSERVE);
   SET_SMEM(cz_obs32_kernel);
+  SET_SMEM(cz_warp_kernel<1>); SET_SMEM(cz_warp_kernel<2>); SET_SMEM(cz_warp_kernel<3>); SET_SMEM(cz_warp_kernel<4>);
 #undef SET_MODE
 #undef SET_SMEM
   *out = t;
@@ -928,6 +956,7 @@ extern "C" int cz_tables_destroy(cz_tables* t) {
   if (t->d_reward) cudaFree(t->d_reward);
   if (t->d_term) cudaFree(t->d_term);
   if (t->d_trunc) cudaFree(t->d_trunc);
+  if (t->d_rand) cudaFree(t->d_rand);
   if (t->pipe_ready) {
     cudaStreamDestroy(t->pipe_dyn); cudaStreamDestroy(t->pipe_obs);
     cudaEventDestroy(t->ev_user); cudaEventDestroy(t->ev_dyn); cudaEventDestroy(t->ev_obs[0]); cudaEventDestroy(t->ev_obs[1]);
@@ -1037,22 +1066,41 @@ static int cz_launch_obs64(const cz_tables* t, const uint32_t* state, double* ob
 }
 
 extern "C" int cz_reset(const cz_tables* t, uint32_t* state, const int32_t* layout_ids, const uint8_t* recipe_ids,
-                        const uint8_t* mask, double* obs, int n_envs, void* stream) {
+                        const uint8_t* mask, double* obs, uint32_t* error_flags, int n_envs, void* stream) {
   if (!layout_ids) return cz_fail(CZ_EINVAL, "%s", "layout_ids is required");
   if (t && t->simple2 && obs && !mask) {  // state first, then every row (a masked reset takes the generic kernel below)
     int rc = cz_launch<MODE_RESET>(t, state, state, true, nullptr, layout_ids, recipe_ids, mask, nullptr, nullptr, nullptr, nullptr,
-                                   nullptr, n_envs, 0, 0, 0, stream);
+                                   error_flags, n_envs, 0, 0, 0, stream);
     if (rc != CZ_OK) return rc;
     return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream);
   }
-  return cz_launch<MODE_RESET>(t, state, state, false, nullptr, layout_ids, recipe_ids, mask, obs, nullptr, nullptr, nullptr, nullptr,
+  return cz_launch<MODE_RESET>(t, state, state, false, nullptr, layout_ids, recipe_ids, mask, obs, nullptr, nullptr, nullptr, error_flags,
                                n_envs, 0, 0, 0, stream);
 }
 
-extern "C" int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actions, double* obs, double* reward,
+// default layout ids of an episode: cz_layout_draw(seed, env_offset + e, episode) % P for every environment
+__global__ void cz_layout_ids_kernel(int32_t* __restrict__ out, int n_envs, int P, uint64_t seed, int64_t env_offset, uint64_t episode) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n_envs) out[e] = (int32_t)(cz_mix(seed, (uint64_t)(env_offset + e), episode) % (uint64_t)P);
+}
+
+extern "C" int cz_layout_ids(const cz_tables* t, int32_t* layout_ids, int n_envs, uint64_t seed, int64_t env_offset, uint64_t episode,
+                             void* stream) {
+  if (!t || !layout_ids) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (n_envs <= 0) return CZ_OK;
+  cz_layout_ids_kernel<<<(n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(layout_ids, n_envs, t->dev.P, seed, env_offset, episode);
+  g_launches.fetch_add(1);
+  CZ_CUDA(cudaGetLastError());
+  return CZ_OK;
+}
+
+extern "C" int cz_random_actions(const cz_tables* t, uint8_t* actions, int n_envs, uint64_t seed, uint64_t step,
+                                 int64_t env_offset, void* stream);
+
+// one in-place step with resident actions on the lane-per-environment kernels
+static int cz_step_one(const cz_tables* t, uint32_t* state, const uint8_t* actions, double* obs, double* reward,
                        uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, uint32_t flags,
                        uint64_t seed, int64_t env_offset, void* stream) {
-  if (!actions || !reward || !terminated || !truncated) return cz_fail(CZ_EINVAL, "%s", "null argument");
   // 33-64 pair plans always, and large batches of the other packed plans (the short-block row writer streams faster than the
   // observation phase of the fused kernel; small batches keep the single launch): dynamics, then the row writer
   if (t && obs && !(flags & CZ_STEP_OBS_F32) &&
@@ -1070,6 +1118,70 @@ extern "C" int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actio
   }
   return cz_launch<MODE_STEP>(t, state, state, false, actions, nullptr, nullptr, nullptr, obs, reward, terminated, truncated,
                               error_flags, n_envs, flags, seed, env_offset, stream);
+}
+
+// k_steps consecutive steps of every environment in ONE launch of the warp-per-environment kernel
+static int cz_launch_warp(const cz_tables* t, uint32_t* state, const uint8_t* actions, double* obs, double* reward,
+                          uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, int k_steps, uint32_t flags,
+                          uint64_t seed, int64_t env_offset, uint64_t action_step, void* stream) {
+  if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
+  const CzDev& T = t->dev;
+  const int blocks = (n_envs + WK_WARPS - 1) / WK_WARPS;
+  const size_t smem = cz_block_smem_head(T.V) + (size_t)WK_WARPS * 104 * 4 + (size_t)WK_WARPS * T.A * ((T.stage_len + 1) / 2) * 16;
+  cudaStream_t s = (cudaStream_t)stream;
+#define CZ_WARP_GO(NA)                                                                                                     \
+  cz_warp_kernel<NA><<<blocks, 32 * WK_WARPS, smem, s>>>(t->dev, state, actions, obs, reward, terminated, truncated, error_flags, \
+                                                         n_envs, k_steps, flags, seed, env_offset, action_step, t->simple2)
+  switch (T.A) {
+    case 1: CZ_WARP_GO(1); break;
+    case 2: CZ_WARP_GO(2); break;
+    case 3: CZ_WARP_GO(3); break;
+    default: CZ_WARP_GO(4); break;
+  }
+#undef CZ_WARP_GO
+  g_launches.fetch_add(1);
+  CZ_CUDA(cudaGetLastError());
+  return CZ_OK;
+}
+
+extern "C" int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actions, double* obs, double* reward,
+                       uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, int k_steps, uint32_t flags,
+                       uint64_t seed, int64_t env_offset, uint64_t action_step, void* stream) {
+  if (!t || !state || !reward || !terminated || !truncated) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (k_steps < 1) return cz_fail(CZ_EINVAL, "%s", "k_steps must be at least 1");
+  const bool dev_actions = (flags & CZ_STEP_DEVICE_ACTIONS) != 0;
+  if (!actions && !dev_actions) return cz_fail(CZ_EINVAL, "%s", "actions is NULL and CZ_STEP_DEVICE_ACTIONS is not set");
+  if (dev_actions) actions = nullptr;
+  if (n_envs <= 0) return CZ_OK;
+  const CzDev& T = t->dev;
+  const bool warp_ok = (t->simple || t->simple2) && !(flags & CZ_STEP_OBS_F32);
+  if (warp_ok && (k_steps > 1 ? n_envs <= t->warp_k_max_envs : n_envs <= t->warp_max_envs))
+    return cz_launch_warp(t, state, actions, obs, reward, terminated, truncated, error_flags, n_envs, k_steps, flags, seed,
+                          env_offset, action_step, stream);
+  // everything else (generic tables, float32 rows, large batches): k_steps launches of the per-step kernels
+  cz_tables* tm = const_cast<cz_tables*>(t);
+  if (dev_actions && n_envs > t->rand_envs) {
+    if (tm->d_rand) cudaFree(tm->d_rand);
+    tm->rand_envs = 0;
+    CZ_CUDA(cudaMalloc((void**)&tm->d_rand, (size_t)n_envs * T.A));
+    tm->rand_envs = n_envs;
+  }
+  const size_t na = (size_t)n_envs * T.A;
+  const bool keep = (flags & CZ_STEP_KEEP_ALL) != 0 && k_steps > 1;
+  const size_t obs_bytes = na * T.L * ((flags & CZ_STEP_OBS_F32) ? sizeof(float) : sizeof(double));
+  for (int k = 0; k < k_steps; ++k) {
+    const uint8_t* a = actions ? actions + (size_t)k * na : t->d_rand;
+    if (dev_actions) {
+      int rc = cz_random_actions(t, tm->d_rand, n_envs, seed, action_step + (uint64_t)k, env_offset, stream);
+      if (rc != CZ_OK) return rc;
+    }
+    const size_t o = keep ? (size_t)k : 0;
+    double* obs_k = obs ? reinterpret_cast<double*>(reinterpret_cast<char*>(obs) + o * obs_bytes) : nullptr;
+    int rc = cz_step_one(t, state, a, obs_k, reward + o * na, terminated + o * na, truncated + o * na, error_flags, n_envs,
+                         flags & ~(CZ_STEP_DEVICE_ACTIONS | CZ_STEP_KEEP_ALL), seed, env_offset, stream);
+    if (rc != CZ_OK) return rc;
+  }
+  return CZ_OK;
 }
 
 extern "C" int cz_observe_f32(const cz_tables* t, const uint32_t* state, float* obs32, int n_envs, void* stream) {
@@ -1132,6 +1244,9 @@ extern "C" int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* 
   CZ_CUDA(cudaEventRecord(t->ev_dyn, t->pipe_dyn));
   CZ_CUDA(cudaStreamWaitEvent(t->pipe_obs, t->ev_dyn, 0));
   CZ_CUDA(cudaStreamWaitEvent(t->pipe_obs, t->ev_user, 0));
+  // the caller's stream trails the dynamics: whatever it does next (overwrite or free the action buffer, read the
+  // rewards / flags / state, run a policy) is ordered after this step's dynamics; only the rows need cz_pipeline_wait
+  CZ_CUDA(cudaStreamWaitEvent(user, t->ev_dyn, 0));
   if (flags & CZ_STEP_OBS_F32) {
     rc = cz_launch_obs32(t, out, reinterpret_cast<float*>(obs), n_envs, t->pipe_obs);
     if (rc != CZ_OK) return rc;
@@ -1183,8 +1298,8 @@ extern "C" int cz_step_host(cz_tables* t, uint32_t* state_dev, const uint8_t* ac
   cudaStream_t s = (cudaStream_t)stream;
   size_t na = (size_t)n_envs * T.A;
   CZ_CUDA(cudaMemcpyAsync(t->d_actions, actions_host, na, cudaMemcpyHostToDevice, s));
-  int rc = cz_step(t, state_dev, t->d_actions, t->d_obs, t->d_reward, t->d_term, t->d_trunc, nullptr, n_envs, flags, seed,
-                   env_offset, stream);
+  int rc = cz_step(t, state_dev, t->d_actions, t->d_obs, t->d_reward, t->d_term, t->d_trunc, nullptr, n_envs, 1, flags, seed,
+                   env_offset, 0, stream);
   if (rc != CZ_OK) return rc;
   CZ_CUDA(cudaMemcpyAsync(obs_host, t->d_obs, na * T.L * ((flags & CZ_STEP_OBS_F32) ? sizeof(float) : sizeof(double)),
                           cudaMemcpyDeviceToHost, s));

@@ -347,7 +347,6 @@ extern "C" int cz_policy_act(const cz_policy* p, const uint32_t* state, const ui
 }
 
 // ---- synthetic action streams on the device -------------------------------------------
-#define CZ_ACTION_STREAM 0xA5A5A5A5A5A5A5A5ull  // keeps the action stream apart from the spawn stream of the same seed
 
 __global__ void cz_random_actions_kernel(uint8_t* __restrict__ actions, int n_envs, int A, int num_actions, uint64_t seed,
                                          uint64_t step, int64_t env_offset) {

@@ -1,0 +1,740 @@
+// cz_warp.cuh — ONE WARP PER ENVIRONMENT: the latency-optimised step, persistent over K steps (sm_100a).
+//
+// The lane-per-environment kernels (cz_device.cuh) walk ~2.4 k dependent instructions per step: right for
+// 131072 environments (one instruction stream serves 32 environments), wrong for BASELINE config 3's 4096, where
+// a step is bounded by that chain and not by bytes.  Here lane s owns dynamic-object slot s, so every `for slot`
+// loop of the dynamics collapses into a ballot / a warp reduction, and agents, static bits, recipe marks and the
+// clock are warp-uniform registers.  The whole environment lives in registers across the K steps of one launch:
+// state is read once and written once, actions come from a resident [K][n][A] array or from the counter stream of
+// cz_random_actions, and the A observation rows leave through the same staging rows / 128-bit stores as
+// cz_obs_envs_kernel after every step.
+//
+// Semantics are those of cz_step_env (cz_device.cuh), statement by statement; citations there and below are to
+// /root/reference/cooking_zoo/...  Bit-identity with cz_step x K is tested in tests/test_gpu_ksteps.py.
+// Included by cz_kernels.cu (needs BlockSmem, LaneSlot, cz_lane_slot_packed).
+#pragma once
+
+#ifndef WK_WARPS
+#define WK_WARPS 4  // environments (warps) per block
+#endif
+#define WK_FULL 0xffffffffu
+#define CZ_ACTION_STREAM 0xA5A5A5A5A5A5A5A5ull  // keeps the action stream apart from the spawn stream of the same seed
+
+template <int NA>
+struct WEnv {
+  uint32_t rec;    // this lane's dynamic-object record (0 for lanes >= D)
+  uint32_t tf;     // type flags of this lane's slot
+  uint32_t rank;   // position of this lane's slot in get_objects_at's scan order (cooking_world.py:232-241)
+  uint32_t m_none, m_chop, m_mash;  // (recipe, node) pairs this slot's type can satisfy: always / when chopped / when mashed
+  uint32_t ag[NA];                  // agent records (warp-uniform)
+  uint32_t sbits, tinfo, marks, variant, rids, episode, err;  // warp-uniform
+  uint32_t pairs_static, pairs_static_only;  // warp-uniform masks over (recipe, node) pairs
+  uint64_t walk64, block64;  // cells whose static object is always walkable / is a Block (walkable by state)
+  const SmemTabs* st;
+  uint32_t* cells;   // [64] per-warp scratch: pairs satisfied per cell
+  uint32_t* skp;     // [8]  pairs satisfied by a static kind
+  int lane;
+};
+
+template <int NA>
+__device__ __forceinline__ uint32_t wk_sel(const uint32_t (&a)[NA], int i) {
+  uint32_t v = a[0];
+#pragma unroll
+  for (int j = 1; j < NA; ++j)
+    if (i == j) v = a[j];
+  return v;
+}
+
+template <int NA>
+__device__ __forceinline__ bool wk_agent_on(const WEnv<NA>& e, uint32_t cell) {
+  bool on = false;
+#pragma unroll
+  for (int j = 0; j < NA; ++j)
+    if (A_XY(e.ag[j]) == cell) on = true;
+  return on;
+}
+
+template <int NA>
+__device__ __forceinline__ bool wk_walkable(const CzDev& T, const WEnv<NA>& e, uint32_t cell) {
+  constexpr bool FAST = true;
+  const SmemTabs* st = e.st;
+  if ((e.walk64 >> cell) & 1ull) return true;
+  if ((e.block64 >> cell) & 1ull) return (e.sbits & SB_BLK_WALK(TAB_GRID(e.variant, cell) >> 4)) != 0;
+  return false;
+}
+
+// everything that depends on the static variant of the current layout (changes only on reset)
+template <int NA>
+__device__ __forceinline__ void wk_variant_consts(const CzDev& T, WEnv<NA>& e, uint32_t* scratch) {
+  constexpr bool FAST = true;
+  const SmemTabs* st = e.st;
+  e.walk64 = TAB_SMASK(e.variant, ST_FLOOR) | TAB_SMASK(e.variant, ST_SWITCH);
+  e.block64 = TAB_SMASK(e.variant, ST_BLOCK);
+  if (e.lane < T.D) scratch[TAB_SCAN(e.variant, e.lane)] = (uint32_t)e.lane;
+  __syncwarp();
+  e.rank = e.lane < T.D ? scratch[e.lane] : 0u;
+  __syncwarp();
+}
+
+// (recipe, node) pair p = 8 r + k, the bit layout of the MARKS word.  Per lane: the pairs an object in this slot
+// satisfies on its own (type + condition, recipe.py:96-98); per warp: the pairs a static kind satisfies.
+template <int NA>
+__device__ __forceinline__ void wk_recipe_consts(const CzDev& T, WEnv<NA>& e) {
+  constexpr bool FAST = true;
+  const SmemTabs* st = e.st;
+  const uint32_t my_type = e.lane < T.D ? TAB_STYPE(e.lane) : 0xFEu;
+  e.m_none = e.m_chop = e.m_mash = 0;
+  e.pairs_static = 0;
+  if (e.lane < 8) e.skp[e.lane] = 0;
+  __syncwarp();
+  for (int r = 0; r < T.R; ++r) {
+    const uint32_t rid = (e.rids >> (8 * r)) & 255u;
+    const int n = TAB_RLEN(rid);
+    for (int k = 0; k < n; ++k) {
+      const uint32_t node = TAB_RNODE(rid, k), bit = 1u << (8 * r + k);
+      if (node & 256u) {
+        e.pairs_static |= bit;
+        if (e.lane == 0) e.skp[node & 7u] |= bit;
+      } else if ((node & 255u) == my_type) {
+        const uint32_t cond = (node >> 9) & 3u;
+        if (cond == 1u) e.m_chop |= bit;
+        else if (cond == 2u) e.m_mash |= bit;
+        else e.m_none |= bit;
+      }
+    }
+  }
+  __syncwarp();
+  // a node whose whole subtree is static is decided by the static masks alone
+  e.pairs_static_only = 0;
+  for (int r = 0; r < T.R; ++r) {
+    const uint32_t rid = (e.rids >> (8 * r)) & 255u;
+    const int n = TAB_RLEN(rid);
+    for (int k = 0; k < n; ++k) {
+      const uint32_t d = (uint32_t)st->recipe_desc[rid][k] << (8 * r);
+      if ((d & ~e.pairs_static) == 0) e.pairs_static_only |= 1u << (8 * r + k);
+    }
+  }
+}
+
+// Recipe.update_recipe_state for every recipe of the environment at once (recipe.py:77-104).  A node is marked iff
+// some cell holds, for the node and every descendant, an object that satisfies that node on its own (the AND of the
+// children's cell masks in cz_recipe_marks, unrolled over the subtree).  Lanes OR their slot's pairs into a per-cell
+// word, read back everything satisfied at their own cell, and one vote per node decides it.
+template <int NA>
+__device__ __forceinline__ uint32_t wk_recipe_marks(const CzDev& T, WEnv<NA>& e) {
+  constexpr bool FAST = true;
+  const SmemTabs* st = e.st;
+  const uint32_t rec = e.rec;
+  const bool present = (rec & O_PRESENT) != 0;
+  const uint32_t sat = present ? (e.m_none | ((rec & O_CHOP) ? e.m_chop : 0u) | ((rec & O_MASH) ? e.m_mash : 0u)) : 0u;
+  e.cells[e.lane] = 0;
+  e.cells[e.lane + 32] = 0;
+  __syncwarp();
+  if (sat) atomicOr(e.cells + O_XY(rec), sat);
+  __syncwarp();
+  uint32_t here = 0;
+  if (present) here = e.cells[O_XY(rec)] | e.skp[TAB_GRID(e.variant, O_XY(rec)) & 7u];
+  __syncwarp();
+  uint32_t marks = 0;
+  for (int r = 0; r < T.R; ++r) {
+    const uint32_t rid = (e.rids >> (8 * r)) & 255u;
+    const int n = TAB_RLEN(rid);
+    for (int k = 0; k < n; ++k) {
+      const uint32_t bit = 1u << (8 * r + k);
+      const uint32_t d = (uint32_t)st->recipe_desc[rid][k] << (8 * r);
+      bool ok;
+      if (e.pairs_static_only & bit) {
+        uint64_t m = ~0ull;
+        for (int j = 0; j < n; ++j)
+          if (d >> (8 * r + j) & 1u) m &= TAB_SMASK(e.variant, TAB_RNODE(rid, j) & 7u);
+        ok = m != 0;
+      } else {
+        ok = __any_sync(WK_FULL, (here & d) == d);
+      }
+      if (ok) marks |= bit;
+    }
+  }
+  return marks;
+}
+
+// Object.move_to / Plate.move_to (abstract_classes.py:21-22, world_objects.py:393-396): slot s and, for a Plate that
+// carries items, its content.  `carries` = s is a plate with a non-zero item count.
+template <int NA>
+__device__ __forceinline__ void wk_move_obj(WEnv<NA>& e, uint32_t s, bool carries, uint32_t xy) {
+  if ((uint32_t)e.lane == s || (carries && O_ON_PLATE(e.rec, s))) e.rec = O_WITH_XY(e.rec, xy);
+}
+
+// list.remove(obj) on the content of the static object at `cell`: later items shift down
+template <int NA>
+__device__ __forceinline__ void wk_remove_from_static(WEnv<NA>& e, uint32_t cell, uint32_t pos) {
+  if (O_IN_STATIC_AT(e.rec, cell) && O_POS(e.rec) > pos) e.rec -= 1u << 17;
+}
+
+// free-flag refresh of one container (cooking_world.py:82-88): last item free, the others not
+template <int NA>
+__device__ __forceinline__ void wk_refresh_free(WEnv<NA>& e, bool in) {
+  const uint32_t top = __reduce_max_sync(WK_FULL, in ? O_POS(e.rec) + 1u : 0u);
+  if (in) e.rec = (O_POS(e.rec) + 1u == top) ? (e.rec | O_FREE) : (e.rec & ~O_FREE);
+}
+
+// resolve_interaction -> resolve_execute_action | resolve_primary_interaction -> attempt_merge (cz_interact)
+template <int NA>
+__device__ __forceinline__ uint32_t wk_interact(const CzDev& T, WEnv<NA>& e, const int i, uint32_t cell, uint32_t mode, bool& stale) {
+  constexpr bool FAST = true;
+  const SmemTabs* st = e.st;
+  const int lane = e.lane;
+  const uint32_t agent_rec = e.ag[i];
+  const uint32_t g = TAB_GRID(e.variant, cell);
+  const uint32_t kind = g & 15u, sp = g >> 4;
+  // the objects at the faced cell, in scan order (cooking_world.py:232-241)
+  const bool at = O_AT(e.rec, cell);
+  const uint32_t m_at = __ballot_sync(WK_FULL, at);
+  const int n_dyn = __popc(m_at);
+  const uint32_t m_plate = __ballot_sync(WK_FULL, at && (e.tf & TF_PLATE));
+  const int n_plates = __popc(m_plate);
+  const int plate = n_plates ? 31 - __clz(m_plate) : -1;  // only used when there is exactly one
+  const bool any_not_done = __any_sync(WK_FULL, at && !(e.tf & TF_PLATE) && !(e.rec & (O_CHOP | O_MASH)));
+  const int n_content = __popc(__ballot_sync(WK_FULL, at && O_CK(e.rec) == CK_STATIC));
+  const uint32_t k_last = __reduce_max_sync(WK_FULL, at ? ((e.rank << 5) | (uint32_t)lane) + 1u : 0u);
+  const uint32_t k_free = __reduce_max_sync(WK_FULL, (at && (e.rec & O_FREE)) ? (((63u - e.rank) << 5) | (uint32_t)lane) + 1u : 0u);
+  const int last = k_last ? (int)((k_last - 1u) & 31u) : -1;
+  const int first_free = k_free ? (int)((k_free - 1u) & 31u) : -1;
+  const bool blocked = wk_agent_on(e, cell);
+
+  if (mode == 6u) {
+    // ---- resolve_interaction_pick_up_special (cooking_world.py:138-154)
+    if (blocked || A_HAS(agent_rec) || n_dyn == 0 || n_plates != 1) return 0xFFu;
+    const uint32_t k_top = __reduce_max_sync(WK_FULL, O_ON_PLATE(e.rec, plate) ? ((O_POS(e.rec) << 5) | (uint32_t)lane) + 1u : 0u);
+    if (!k_top) return 0xFFu;
+    const int ts = (int)((k_top - 1u) & 31u);
+    if (lane == plate) e.rec -= O_PCOUNT_ONE;
+    if (lane == ts) e.rec = O_WITH_XY(O_WITH_CONT(e.rec, CK_HELD, i, 0), A_XY(agent_rec));
+    e.ag[i] = (agent_rec & ~(0x3Fu << 9)) | (1u << 9) | ((uint32_t)ts << 10);
+    return (uint32_t)plate;
+  }
+  if (mode == 7u || (mode == 0u && (kind == ST_CUTBOARD || kind == ST_BLENDER) && any_not_done)) {
+    // ---- resolve_execute_action (cooking_world.py:156-170)
+    if (blocked) return 0xFFu;
+    if (kind != ST_CUTBOARD && kind != ST_BLENDER) return 0xFFu;
+    if (kind == ST_CUTBOARD) {  // Cutboard.action (world_objects.py:250-269)
+      if (!(e.sbits & SB_CUT_READY(sp))) return 0xFFu;
+      for (int p = 0; p < n_content; ++p) {
+        const uint32_t m = __ballot_sync(WK_FULL, O_IN_STATIC_AT(e.rec, cell) && O_POS(e.rec) == (uint32_t)p);
+        if (!m) break;
+        const int s = 31 - __clz(m);
+        const uint32_t r = __shfl_sync(WK_FULL, e.rec, s);
+        const uint32_t tf = __shfl_sync(WK_FULL, e.tf, s);
+        if (!(tf & TF_CHOP)) return 0xFFu;
+        if (r & O_CHOP) continue;
+        if (lane == s) e.rec = r | O_CHOP;
+        e.sbits &= ~SB_CUT_READY(sp);
+        if (tf & TF_SPAWN) {  // Bread.chop spawns a chopped twin (world_objects.py:738-745)
+          const uint32_t tid = TAB_STYPE(s);
+          const int base = TAB_TBASE(tid), cnt = TAB_TCOUNT(tid);
+          const uint32_t m_free = __ballot_sync(WK_FULL, lane >= base && lane < base + cnt && !(e.rec & O_PRESENT));
+          if (!m_free) {
+            e.err |= CZ_ERR_OBS_OVERFLOW;
+          } else {
+            if (lane == __ffs(m_free) - 1) e.rec = O_WITH_CONT(cell | O_PRESENT | O_CHOP | O_FREE, CK_STATIC, 0, n_content);
+            stale = true;
+          }
+        }
+        return 0xFFu;
+      }
+      e.err |= CZ_ERR_CUTBOARD_NONE;
+    } else {  // Blender.action (world_objects.py:356-360)
+      if (e.sbits & SB_BL_READY(sp)) e.sbits ^= SB_BL_TOGGLE(sp);
+    }
+    return 0xFFu;
+  }
+
+  // ---- resolve_primary_interaction (cooking_world.py:114-136)
+  if (blocked) return 0xFFu;
+  const uint32_t axy = A_XY(agent_rec);
+  if (!A_HAS(agent_rec)) {
+    if (n_dyn == 0) return 0xFFu;
+    bool rel = true;  // StaticObject.releases() with side effects
+    if (kind == ST_DELIVER) rel = false;
+    else if (kind == ST_CUTBOARD) {
+      if (n_content == 1) e.sbits &= ~SB_CUT_READY(sp);
+    } else if (kind == ST_BLENDER) {
+      if (e.sbits & SB_BL_TOGGLE(sp)) rel = false;
+      else if (n_content - 1 == 0) e.sbits &= ~SB_BL_READY(sp);
+    }
+    if (!rel) return 0xFFu;
+    const int gs = first_free >= 0 ? first_free : last;
+    const uint32_t r = __shfl_sync(WK_FULL, e.rec, gs);
+    const uint32_t gtf = __shfl_sync(WK_FULL, e.tf, gs);
+    if (O_CK(r) != CK_STATIC) return 0xFFu;  // `object_to_grab in static_object.content`
+    if (n_content > 1) {
+      wk_remove_from_static(e, cell, O_POS(r));
+      stale = true;
+    }
+    if (lane == gs) e.rec = O_WITH_CONT(r, CK_HELD, i, 0);
+    wk_move_obj(e, (uint32_t)gs, (gtf & TF_PLATE) && O_PCOUNT(r), axy);  // Agent.grab (world_objects.py:786-788)
+    e.ag[i] = (agent_rec & ~(0x3Fu << 9)) | (1u << 9) | ((uint32_t)gs << 10);
+    return 0xFFu;
+  }
+
+  // ---- attempt_merge (cooking_world.py:243-261)
+  const uint32_t h = A_HOLD(agent_rec);
+  const uint32_t hr = __shfl_sync(WK_FULL, e.rec, h);
+  const uint32_t htf = __shfl_sync(WK_FULL, e.tf, h);
+  const uint32_t dropped = agent_rec & ~(0x3Fu << 9);
+  if (n_plates == 1) {
+    if ((htf & (TF_CHOP | TF_BLEND)) && (hr & (O_CHOP | O_MASH))) {  // Plate.accepts (world_objects.py:408-409)
+      const uint32_t n = O_PCOUNT(__shfl_sync(WK_FULL, e.rec, plate));
+      if (n < 64) {
+        if (n && O_ON_PLATE(e.rec, plate)) e.rec &= ~O_FREE;
+        if (lane == plate) e.rec += O_PCOUNT_ONE;
+        if (lane == (int)h) e.rec = O_WITH_XY(O_WITH_CONT(hr, CK_PLATE, plate, n) | O_FREE, cell);
+        e.ag[i] = dropped;
+      }
+    }
+  } else if ((htf & TF_PLATE) && n_dyn > 0) {
+    const uint32_t pr = __shfl_sync(WK_FULL, e.rec, last);
+    const uint32_t ptf = __shfl_sync(WK_FULL, e.tf, last);
+    if ((ptf & (TF_CHOP | TF_BLEND)) && (pr & (O_CHOP | O_MASH))) {
+      const uint32_t n = O_PCOUNT(hr);
+      if (n < 64) {
+        if (n && O_ON_PLATE(e.rec, h)) e.rec &= ~O_FREE;
+        if (lane == (int)h) e.rec = hr + O_PCOUNT_ONE;
+        if (O_CK(pr) == CK_STATIC) {
+          if (n_content > 1) {
+            wk_remove_from_static(e, cell, O_POS(pr));
+            stale = true;
+          }
+        } else {
+          e.err |= CZ_ERR_REMOVE;
+        }
+        if (lane == last) e.rec = O_WITH_XY(O_WITH_CONT(pr, CK_PLATE, h, n) | O_FREE, axy);
+      }
+    }
+  } else {
+    bool ok = false;  // StaticObject.accepts
+    if (kind == ST_COUNTER || kind == ST_DELIVER) ok = n_content < 1;
+    else if (kind == ST_CUTBOARD) ok = (htf & TF_CHOP) && n_content < 1 && !(hr & O_CHOP);
+    else if (kind == ST_BLENDER)
+      ok = (htf & TF_BLEND) && !(e.sbits & SB_BL_TOGGLE(sp)) && n_content + 1 <= 1 && !(hr & O_MASH);
+    if (ok) {
+      if (kind == ST_CUTBOARD) e.sbits |= SB_CUT_READY(sp);
+      if (kind == ST_BLENDER) e.sbits |= SB_BL_READY(sp);
+      if (lane == (int)h) e.rec = O_WITH_CONT(hr, CK_STATIC, 0, n_content) | O_FREE;
+      wk_move_obj(e, h, (htf & TF_PLATE) && O_PCOUNT(hr), cell);
+      e.ag[i] = dropped;
+    }
+  }
+  return 0xFFu;
+}
+
+// CookingEnvironment.accumulated_step (cooking_env.py:243-269) for the warp's environment (cz_step_env).
+// rw / te / tr: reward, terminated, truncated of every agent (warp-uniform).
+template <int NA>
+__device__ __forceinline__ void wk_step_env(const CzDev& T, WEnv<NA>& e, const uint32_t act_packed, double (&rw)[NA],
+                                            uint32_t& term_mask, uint32_t& trunc_out, uint64_t seed, uint64_t genv) {
+  constexpr bool FAST = true;
+  constexpr int A = NA;
+  const SmemTabs* st = e.st;
+  const bool scheme1 = T.scheme == 1;
+  const uint32_t t = TI_T(e.tinfo) + 1;
+  uint32_t active = 0;
+#pragma unroll
+  for (int i = 0; i < A; ++i)
+    if (A_ACTIVE(e.ag[i])) active |= 1u << i;
+  uint32_t changed = 0;
+
+  // ---- action_scheme3.perform_agent_actions (action_scheme3.py:4-16)
+  uint32_t apack = 0, fpack = 0, epack = 0x80808080u;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    if (!(active >> i & 1u)) continue;
+    uint32_t ai = (act_packed >> (8 * i)) & 255u;
+    if (ai > (scheme1 ? 7u : 4u)) ai = 0;
+    uint32_t rec = e.ag[i];
+    const int x = rec & 7u, y = (rec >> 3) & 7u;
+    uint32_t faced = A_XY(rec);
+    if (ai >= 1u && ai <= 4u) {
+      rec = (rec & ~(7u << 6)) | (ai << 6);
+      e.ag[i] = rec;
+      const int tx = x + (ai == 2) - (ai == 1), ty = y + (ai == 3) - (ai == 4);
+      if (tx < 0 || ty < 0 || tx > T.W - 1 || ty > T.H - 1) ai = 0;
+      else faced = (uint32_t)(tx | ty << 3);
+    }
+    const uint32_t tgt = (ai >= 1u && ai <= 4u) ? faced : A_XY(rec);
+    const bool w = wk_walkable(T, e, tgt);
+    const uint32_t endc = (w ? tgt : A_XY(rec)) | (w ? 0x40u : 0u);
+    apack |= ai << (8 * i);
+    fpack |= faced << (8 * i);
+    epack = (epack & ~(0xFFu << (8 * i))) | (endc << (8 * i));
+  }
+  uint32_t cancel = 0;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    const uint32_t ei = (epack >> (8 * i)) & 255u;
+    if (!(ei & 0x40u) || (ei & 0x80u)) continue;
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+      const uint32_t ej = (epack >> (8 * j)) & 255u;
+      if (j != i && !(ej & 0x80u) && (ej & 63u) == (ei & 63u)) cancel |= 1u << i;
+    }
+  }
+  uint32_t pressed = 0, dirty = 0xFFFFFFFFu, dirty_plate = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    if (!(active >> i & 1u)) continue;
+    uint32_t rec = e.ag[i];
+    const uint32_t ai = (cancel >> i & 1u) ? 0u : ((apack >> (8 * i)) & 255u);
+    if (scheme1) {
+      if (ai == 0u) continue;
+      if (ai >= 5u) {
+        const uint32_t o = A_ORI(rec);
+        const int fx = (int)(rec & 7u) + (o == 2) - (o == 1), fy = (int)((rec >> 3) & 7u) + (o == 3) - (o == 4);
+        if (fx < 0 || fy < 0 || fx > T.W - 1 || fy > T.H - 1) { e.err |= CZ_ERR_OFFGRID; continue; }
+        const uint32_t cell = (uint32_t)(fx | fy << 3);
+        bool stale = false;
+        const uint32_t p = wk_interact(T, e, i, cell, ai, stale);
+        if (stale) dirty = (dirty & ~(0xFFu << (8 * i))) | (cell << (8 * i));
+        dirty_plate = (dirty_plate & ~(0xFFu << (8 * i))) | (p << (8 * i));
+        continue;
+      }
+    }
+    const uint32_t tgt = ai ? ((fpack >> (8 * i)) & 63u) : A_XY(rec);
+    if (wk_walkable(T, e, tgt)) {  // resolve_walking_action (action_scheme3.py:26-34)
+      rec = (rec & ~63u) | tgt;
+      e.ag[i] = rec;
+      if (A_HAS(rec)) {  // Agent.move_to (world_objects.py:793-796): the held object and a held plate's content follow
+        const uint32_t h = A_HOLD(rec);
+        if ((uint32_t)e.lane == h || O_ON_PLATE(e.rec, h)) e.rec = O_WITH_XY(e.rec, tgt);
+      }
+      const uint32_t g = TAB_GRID(e.variant, tgt);
+      if ((g & 15u) == ST_SWITCH) {
+        e.sbits ^= SB_SW_ACTIVE(g >> 4);
+        pressed |= 1u << (g >> 4);
+      }
+    } else if (ai && !scheme1) {
+      bool stale = false;
+      wk_interact(T, e, i, tgt, 0u, stale);
+      if (stale) dirty = (dirty & ~(0xFFu << (8 * i))) | (tgt << (8 * i));
+    }
+  }
+
+  // ---- progress_world (cooking_world.py:77-88)
+  if (e.sbits & (0xFu << 8)) {
+    for (int k = 0; k < CZ_MAX_SPECIAL; ++k) {
+      if (!(e.sbits & SB_BL_TOGGLE(k))) continue;
+      const uint32_t cell = TAB_SPECIAL(e.variant, 1, k);
+      if (cell == 0xFFu) continue;
+      const bool in = O_IN_STATIC_AT(e.rec, cell);
+      if (in && !(e.rec & (O_CHOP | O_MASH))) e.rec |= O_MASH;  // BlenderFood.blend (abstract_classes.py:266-273)
+      const bool any_in = __any_sync(WK_FULL, in);
+      const bool unmashed = __any_sync(WK_FULL, in && !(e.rec & O_MASH));
+      if (any_in && !unmashed) e.sbits &= ~(SB_BL_TOGGLE(k) | SB_BL_READY(k));
+    }
+  }
+  if (dirty != 0xFFFFFFFFu) {
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      const uint32_t c = (dirty >> (8 * i)) & 255u;
+      if (c != 0xFFu) wk_refresh_free(e, O_IN_STATIC_AT(e.rec, c));
+    }
+  }
+  if (dirty_plate != 0xFFFFFFFFu) {
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      const uint32_t p = (dirty_plate >> (8 * i)) & 255u;
+      if (p != 0xFFu) wk_refresh_free(e, O_ON_PLATE(e.rec, p));
+    }
+  }
+  // ---- resolve_linked_interactions (cooking_world.py:90-92)
+  if (pressed) {
+    uint32_t blocks = 0, n_sw = 0;
+    for (int k = 0; k < CZ_MAX_SPECIAL; ++k) {
+      if (TAB_SPECIAL(e.variant, 3, k) != 0xFFu) blocks |= SB_BLK_WALK(k);
+      if (TAB_SPECIAL(e.variant, 2, k) != 0xFFu) ++n_sw;
+    }
+    if (n_sw > 1) e.err |= CZ_ERR_SWITCH_LINK;
+    for (int k = 0; k < CZ_MAX_SPECIAL; ++k)
+      if (pressed >> k & 1u) e.sbits ^= blocks;
+  }
+  // ---- handle_agent_spawn (cooking_world.py:267-277)
+  if (T.respawn > 0.0 || T.despawn > 0.0) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      const uint32_t rec = e.ag[i];
+      if (A_GRACE(rec) > 0) { e.ag[i] = rec - (1u << 16); continue; }
+      const bool act_i = active >> i & 1u;
+      if (__popc(active) > 1 && act_i) {
+        if (cz_uniform(seed, genv, e.episode, t, c++) < T.despawn) {
+          if (!A_HAS(rec)) {
+            active &= ~(1u << i);
+            changed |= 1u << i;
+          }
+        }
+      } else if (!act_i) {
+        if (cz_uniform(seed, genv, e.episode, t, c++) < T.respawn) {
+          active |= 1u << i;
+          changed |= 1u << i;
+          const int nx = __ldg(T.spawn_n + 2 * i), ny = __ldg(T.spawn_n + 2 * i + 1);
+          uint32_t cell = A_XY(rec);
+          bool found = false;
+          for (int tries = 0; tries < 1002 && !found; ++tries) {  // parsing.generate_location :154-167
+            const int x = __ldg(T.spawn_x + 8 * i + min(nx - 1, (int)(cz_uniform(seed, genv, e.episode, t, c++) * nx)));
+            const int y = __ldg(T.spawn_y + 8 * i + min(ny - 1, (int)(cz_uniform(seed, genv, e.episode, t, c++) * ny)));
+            const uint32_t cand = (uint32_t)(x | y << 3);
+            if (x < T.W && y < T.H && (TAB_GRID(e.variant, cand) & 15u) == ST_FLOOR && !wk_agent_on(e, cand)) {
+              cell = cand;
+              found = true;
+            }
+          }
+          if (!found) e.err |= CZ_ERR_SPAWN_LOC;
+          e.ag[i] = (rec & 0xFFC0u) | cell | ((uint32_t)T.grace << 16);
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < A; ++i)
+      if (A_GRACE(e.ag[i]) > 0) e.ag[i] -= 1u << 16;
+  }
+
+  uint32_t relevant = active | changed;
+
+  // ---- compute_rewards / compute_truncated (cooking_env.py:290-350)
+  const bool time_up = t >= (uint32_t)T.max_steps;
+  uint32_t trunc_mask = 0;
+  if (time_up) {
+    if (TI_NLIVE(e.tinfo) < (uint32_t)A) e.err |= CZ_ERR_TRUNC_DESPAWN;
+    trunc_mask = relevant;
+    changed = relevant;
+    active = 0;
+  }
+  trunc_mask |= changed & ~active & relevant;
+  relevant = active | changed;
+  const uint32_t new_marks = wk_recipe_marks(T, e);
+  bool all_done = true, any_done = false;
+#pragma unroll
+  for (int i = 0; i < A; ++i) rw[i] = 0.0;
+  for (int r = 0; r < T.R; ++r) {
+    const uint32_t before = (e.marks >> (8 * r)) & 255u;
+    const uint32_t after = (new_marks >> (8 * r)) & 255u;
+    const bool was = before & 1u, now = after & 1u;
+    const int delta = __popc(after) - __popc(before);
+    double v = 0.0;
+    v = __dadd_rn(v, __dmul_rn((double)delta, T.r_node));
+    v = __dadd_rn(v, (now && !was) ? T.r_recipe : 0.0);
+    v = __dadd_rn(v, (!now && was) ? T.r_penalty : 0.0);
+    v = __dadd_rn(v, T.r_time);
+    all_done = all_done && now;
+    any_done = any_done || now;
+    uint32_t m = relevant;  // the r-th relevant agent receives entry r of the recipe lists (cooking_env.py:250-262)
+    for (int q = 0; q < r; ++q) m &= m - 1;
+    if (m) {
+      const int who = __ffs(m) - 1;
+#pragma unroll
+      for (int i = 0; i < A; ++i)
+        if (i == who) rw[i] = v;
+    }
+  }
+  e.marks = new_marks;
+  const bool done = T.end_all ? all_done : any_done;
+  int k = 0;
+  term_mask = 0;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    const bool rel = relevant >> i & 1u;
+    if (!rel || k >= T.R) rw[i] = 0.0;
+    if (rel) ++k;
+    if (rel && done) term_mask |= 1u << i;
+    e.ag[i] = (e.ag[i] & ~(1u << 15)) | ((active >> i & 1u) << 15);
+  }
+  trunc_out = trunc_mask;
+  const uint32_t n_live = __popc(relevant);
+  e.tinfo = (t & 0xFFFFFu) | ((done || time_up) ? TI_DONE : 0u) | (n_live << 21);
+}
+
+// [x, y, flags..., 1] of one (observer, slot) pair into its staging row (cz_pair_store, with the state in registers)
+template <int NA>
+__device__ __forceinline__ void wk_pair_store(const CzDev& T, const WEnv<NA>& e, const LaneSlot& ls, const double* sxl,
+                                              const double* syl, double2* stage, int stage2) {
+  constexpr bool FAST = true;
+  const SmemTabs* st = e.st;
+  // every lane takes part in the shuffle; idle lanes read slot 0
+  const uint32_t dyn = __shfl_sync(WK_FULL, e.rec, (int)(ls.idx & 31u));
+  if (ls.off < 0) return;
+  const bool is_agent = ls.kind == 2, is_static = ls.kind == 0;
+  uint32_t rec = is_agent ? wk_sel(e.ag, (int)ls.idx) : dyn;
+  uint32_t static_fb = 0;
+  if (is_static) {  // live Switch / Block (world_objects.py:174,221)
+    const uint32_t cell = TAB_SCELL(e.variant, ls.idx);
+    rec = cell != 0xFFu ? (cell | O_PRESENT) : 0u;
+    const uint32_t g = TAB_GRID(e.variant, rec & 63u);
+    static_fb = ((g & 15u) == ST_SWITCH ? (e.sbits >> (12 + (g >> 4))) : (e.sbits >> (16 + (g >> 4)))) & 1u;
+  }
+  const uint32_t me = wk_sel(e.ag, ls.agent);
+  const bool present = is_agent || (rec & O_PRESENT);
+  const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+  const uint32_t fb4 = is_static ? static_fb : (is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2));
+  const uint32_t one = 1u << (ls.flen - 1);
+  const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
+  const bool self = is_agent && (int)ls.idx == ls.agent;
+  const int x = rec & 7u, y = (rec >> 3) & 7u;
+  double X = sxl[x - (self ? 0 : (int)(me & 7u))];
+  double Y = syl[y - (self ? 0 : (int)((me >> 3) & 7u))];
+  if (!present) { X = 0.0; Y = 0.0; }
+  double* out = reinterpret_cast<double*>(stage + ls.agent * stage2) + ls.off;
+  out[0] = X;
+  out[1] = Y;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+    if (k < (int)ls.flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, (fb >> k & 1u) ? 0x3FF00000u : 0u);
+}
+
+template <int NA>
+__global__ void __launch_bounds__(32 * WK_WARPS, 7)
+cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, const uint8_t* __restrict__ actions,
+               double* __restrict__ obs, double* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
+               uint32_t* __restrict__ errflags, int n_envs, int k_steps, uint32_t flags, uint64_t seed, int64_t env_offset,
+               uint64_t action_step, int two) {
+  constexpr bool FAST = true;
+  extern __shared__ __align__(16) unsigned char smem_wk[];
+  const int warp = __shfl_sync(WK_FULL, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int env = blockIdx.x * WK_WARPS + warp;
+  BlockSmem* bs = reinterpret_cast<BlockSmem*>(smem_wk);
+  const size_t head = cz_block_smem_head(T.V);
+  for (int i = threadIdx.x; i < (int)(head / 16); i += 32 * WK_WARPS)
+    reinterpret_cast<uint4*>(bs)[i] = __ldg(reinterpret_cast<const uint4*>(T.blob) + i);
+  const int stage2 = (T.stage_len + 1) >> 1;  // double2 per staging row
+  uint32_t* wwords = reinterpret_cast<uint32_t*>(smem_wk + head) + (size_t)warp * 104;  // cells[64] | skp[8] | scratch[32]
+  double2* stage = reinterpret_cast<double2*>(smem_wk + head + (size_t)WK_WARPS * 104 * 4) + (size_t)warp * NA * stage2;
+  for (int k = lane; k < NA * stage2; k += 32) stage[k] = make_double2(0.0, 0.0);  // never-occupied slots stay zero
+  __syncthreads();
+  if (env >= n_envs) return;
+
+  const SmemTabs* st = &bs->tabs;
+  const double* sxl = bs->xlut + (T.W - 1);
+  const double* syl = bs->ylut + (T.H - 1);
+  const int D = T.D, L2 = T.L >> 1, tab2 = T.tab_len >> 1;
+  const size_t N = (size_t)n_envs;
+  const uint64_t genv = (uint64_t)(env_offset + env);
+
+  WEnv<NA> e;
+  e.st = st;
+  e.lane = lane;
+  e.cells = wwords;
+  e.skp = wwords + 64;
+  uint32_t* scratch = wwords + 72;
+  e.err = 0;
+  // ---- state -> registers: lane s holds slot s; agents and the misc words are broadcast
+  e.rec = lane < D ? __ldg(state + (size_t)lane * N + env) : 0u;
+  e.tf = lane < D ? TAB_TF(lane) : 0u;
+  {
+    const uint32_t w = lane < NA + CZ_NUM_MISC_ROWS ? __ldg(state + (size_t)(D + lane) * N + env) : 0u;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) e.ag[i] = __shfl_sync(WK_FULL, w, i);
+    e.sbits = __shfl_sync(WK_FULL, w, NA + CZ_ROW_SBITS);
+    e.tinfo = __shfl_sync(WK_FULL, w, NA + CZ_ROW_TINFO);
+    e.marks = __shfl_sync(WK_FULL, w, NA + CZ_ROW_MARKS);
+    e.variant = __shfl_sync(WK_FULL, w, NA + CZ_ROW_VARIANT);
+    e.rids = __shfl_sync(WK_FULL, w, NA + CZ_ROW_RECIPES);
+    e.episode = __shfl_sync(WK_FULL, w, NA + CZ_ROW_EPISODE);
+  }
+  wk_variant_consts(T, e, scratch);
+  wk_recipe_consts(T, e);
+
+  // this lane's (observer, slot) pair(s) and table elements: constant over the launch
+  const LaneSlot ls = cz_lane_slot_packed(T, lane);
+  const int num_actions = T.scheme == 1 ? 8 : 5;
+  const bool keep = (flags & CZ_STEP_KEEP_ALL) != 0;
+  const size_t na_stride = keep ? N * NA : 0;  // reward / flags of consecutive steps
+  const int n2 = T.ranges[0][1] >> 1, o2 = T.ranges[0][0] >> 1, s2 = (T.ranges[0][0] - T.stage_lo) >> 1;
+  const double2* tab_lane = reinterpret_cast<const double2*>(T.obs_table) + lane;
+
+  for (int k = 0; k < k_steps; ++k) {
+    // ---- this step's actions: resident [K][n][A] array, or the counter stream of cz_random_actions
+    uint32_t a_mine = 0;
+    if (lane < NA) {
+      if (actions) {
+        a_mine = actions[((size_t)k * N + env) * NA + lane];
+      } else {
+        const double u = cz_uniform(seed ^ CZ_ACTION_STREAM, genv, 0, action_step + (uint64_t)k, (uint64_t)lane);
+        const int a = (int)(u * num_actions);
+        a_mine = (uint32_t)(a < num_actions ? a : num_actions - 1);
+      }
+    }
+    uint32_t act = 0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) act |= __shfl_sync(WK_FULL, a_mine, i) << (8 * i);
+
+    double rw[NA];
+    uint32_t term_mask = 0, trunc_mask = 0;
+    if ((flags & CZ_STEP_AUTO_RESET) && (e.tinfo & TI_DONE)) {
+      // ---- CookingEnvironment.reset (cooking_env.py:178-210): pooled layout -> state, no step (cz_env_kernel)
+      const int layout = (int)(cz_mix(seed, genv, (uint64_t)e.episode) % (uint64_t)T.P);
+      const uint32_t* src = T.pool + (size_t)layout * T.rows;
+      e.rec = lane < D ? __ldg(src + lane) : 0u;
+#pragma unroll
+      for (int i = 0; i < NA; ++i) e.ag[i] = __ldg(src + D + i);
+      e.sbits = __ldg(src + D + NA + CZ_ROW_SBITS);
+      e.tinfo = __ldg(src + D + NA + CZ_ROW_TINFO);
+      e.variant = __ldg(src + D + NA + CZ_ROW_VARIANT);
+      e.episode += 1;
+      wk_variant_consts(T, e, scratch);
+      e.marks = wk_recipe_marks(T, e);
+#pragma unroll
+      for (int i = 0; i < NA; ++i) rw[i] = 0.0;
+    } else {
+      wk_step_env(T, e, act, rw, term_mask, trunc_mask, seed, genv);
+    }
+    if (lane < NA) {
+      double r = rw[0];
+#pragma unroll
+      for (int i = 1; i < NA; ++i)
+        if (lane == i) r = rw[i];
+      const size_t o = (size_t)k * na_stride + (size_t)env * NA + lane;
+      reward[o] = r;
+      term[o] = (uint8_t)(term_mask >> lane & 1u);
+      trunc[o] = (uint8_t)(trunc_mask >> lane & 1u);
+    }
+
+    // ---- get_feature_vector (cooking_env.py:352-373): the A rows of this step
+    if (obs) {
+      double2* g2 = reinterpret_cast<double2*>(obs + ((keep ? (size_t)k * N : 0) + (size_t)env) * NA * T.L);
+      __syncwarp();  // the copy-out of the previous step has read the staging rows
+      wk_pair_store(T, e, ls, sxl, syl, stage, stage2);
+      if (two) wk_pair_store(T, e, cz_lane_slot_packed(T, lane + 32), sxl, syl, stage, stage2);  // 33-64 pairs: second pair of the lane
+      __syncwarp();
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        for (int q = lane; q < n2; q += 32) g2[a * L2 + o2 + q] = stage[a * stage2 + s2 + q];
+      const double2* tab = tab_lane + (size_t)e.variant * 64 * tab2;
+      double2 v0[NA], v1[NA];
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const uint32_t cell = A_XY(e.ag[a]);
+        if (ls.t0 >= 0) v0[a] = __ldg(tab + cell * tab2);
+        if (ls.t1 >= 0) v1[a] = __ldg(tab + cell * tab2 + 32);
+      }
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        if (ls.t0 >= 0) g2[a * L2 + ls.t0] = v0[a];
+        if (ls.t1 >= 0) g2[a * L2 + ls.t1] = v1[a];
+      }
+    }
+  }
+
+  // ---- registers -> state
+  if (lane < D) state[(size_t)lane * N + env] = e.rec;
+  if (lane < NA + CZ_NUM_MISC_ROWS) {
+    uint32_t w = wk_sel(e.ag, lane);
+    const int m = lane - NA;
+    if (m == CZ_ROW_SBITS) w = e.sbits;
+    if (m == CZ_ROW_TINFO) w = e.tinfo;
+    if (m == CZ_ROW_MARKS) w = e.marks;
+    if (m == CZ_ROW_VARIANT) w = e.variant;
+    if (m == CZ_ROW_RECIPES) w = e.rids;
+    if (m == CZ_ROW_EPISODE) w = e.episode;
+    state[(size_t)(D + lane) * N + env] = w;
+  }
+  if (errflags && e.err && lane == 0) errflags[env] |= e.err;
+}

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CZ_ABI_VERSION 1
+#define CZ_ABI_VERSION 2
 
 /* compile-time capacity of the kernels */
 #define CZ_MAX_CELLS 64       /* width<=8, height<=8; device cell index = y*8 + x */
@@ -49,6 +49,7 @@ extern "C" {
 #define CZ_ERR_TRUNC_DESPAWN 16u  /* IndexError at cooking_env.py:348 (truncation with despawned agent) */
 #define CZ_ERR_OBS_OVERFLOW 32u   /* more objects of a type than meta slots (cooking_env.py:371)    */
 #define CZ_ERR_OFFGRID 64u        /* scheme1 interaction with a cell off the grid: get_objects_at(...)[0] IndexError */
+#define CZ_ERR_BAD_ID 128u        /* cz_reset: layout id / recipe id outside the compiled tables (id 0 was used instead) */
 
 /* ---- packed per-environment state --------------------------------------------------
  * `state` is a u32 matrix [cz_state_rows()][n_envs] (structure of arrays: row-major, the
@@ -85,6 +86,10 @@ extern "C" {
 #define CZ_STEP_OBS_F32 2u     /* `obs` points to float32 [n][A][L]: each element is the float64
                                   observation rounded to float32 (the reference's obs.astype(float32));
                                   honoured by cz_step, cz_step_pipelined and cz_step_host */
+#define CZ_STEP_DEVICE_ACTIONS 4u /* cz_step ignores `actions` (may be NULL) and draws step k's actions on the device from the
+                                  counter stream of cz_random_actions at step index action_step + k */
+#define CZ_STEP_KEEP_ALL 8u    /* cz_step with k_steps > 1: obs / reward / terminated / truncated are [k_steps][...] arrays and
+                                  every step's outputs are kept; without it each step overwrites the same [n][A][...] buffers */
 
 /* Host-side description of everything compiled once per (level, meta, recipes, scheme):
  * replaces load_level.load_level / parsing.parse_* (engine/load_level.py:55-71,
@@ -153,19 +158,30 @@ int cz_state_rows(const cz_tables* t);
 /* CookingEnvironment.reset (environment/cooking_env.py:178-210) for every environment whose
  * mask byte is non-zero (mask NULL = all): copy pooled layout layout_ids[e] into the state,
  * evaluate the recipes (cooking_book/recipe.py:77-87), write the first observations
- * (cooking_env.py:352-373).  recipe_ids: [n][R] u8 or NULL (default assignment). */
+ * (cooking_env.py:352-373).  recipe_ids: [n][R] u8 or NULL (default assignment).  An id outside the
+ * compiled tables is replaced by 0 and reported as CZ_ERR_BAD_ID in error_flags (u32 [n], may be NULL). */
 int cz_reset(const cz_tables* t, uint32_t* state, const int32_t* layout_ids, const uint8_t* recipe_ids,
-             const uint8_t* mask, double* obs, int n_envs, void* stream);
+             const uint8_t* mask, double* obs, uint32_t* error_flags, int n_envs, void* stream);
 
-/* CookingEnvironment.accumulated_step + observe (environment/cooking_env.py:243-288):
+/* layout_ids[e] = cz_layout_draw(seed, env_offset + e, episode) % P on the device: the default layout of
+ * every environment's `episode`-th episode, the same draw CZ_STEP_AUTO_RESET makes. */
+int cz_layout_ids(const cz_tables* t, int32_t* layout_ids, int n_envs, uint64_t seed, int64_t env_offset,
+                  uint64_t episode, void* stream);
+
+/* CookingEnvironment.accumulated_step + observe (environment/cooking_env.py:243-288), k_steps times:
  * world_step (cooking_world/cooking_world.py:104-112, action_scheme3.py:4-43), compute_rewards /
  * compute_truncated (:290-350), get_feature_vector (:352-373) for n_envs environments.
- * actions u8 [n][A] (0..4 under scheme3, 0..7 under scheme1); obs f64 [n][A][L]; reward f64 [n][A]; terminated/truncated u8 [n][A];
+ * actions u8 [k_steps][n][A] (0..4 under scheme3, 0..7 under scheme1); obs f64 [n][A][L]; reward f64 [n][A];
+ * terminated/truncated u8 [n][A] (each with a leading [k_steps] axis under CZ_STEP_KEEP_ALL);
  * error_flags u32 [n] (OR-accumulated, may be NULL).  With CZ_STEP_AUTO_RESET the layout of
- * episode k of global environment g = env_offset + e is pool[cz_layout_draw(seed, g, k) % P]. */
+ * episode k of global environment g = env_offset + e is pool[cz_layout_draw(seed, g, k) % P].
+ * k_steps > 1 (and single steps of small batches) run as ONE launch of the warp-per-environment kernel
+ * (csrc/cz_warp.cuh: the environment stays in registers between steps, rows stream out after every step)
+ * when the tables are in the specialised class; otherwise as k_steps launches of the per-step kernels.
+ * The results do not depend on which kernel ran. */
 int cz_step(const cz_tables* t, uint32_t* state, const uint8_t* actions, double* obs, double* reward,
-            uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs,
-            uint32_t flags, uint64_t seed, int64_t env_offset, void* stream);
+            uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, int k_steps,
+            uint32_t flags, uint64_t seed, int64_t env_offset, uint64_t action_step, void* stream);
 
 /* get_feature_vector only (cooking_env.py:352-373): rebuild obs from the current state. */
 int cz_observe(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, void* stream);
@@ -196,9 +212,12 @@ double cz_spawn_uniform(uint64_t seed, uint64_t global_env, uint64_t episode, ui
  * ([2][rows][n]); step k+1's dynamics (cooking_world.world_step + compute_rewards) run on an internal
  * high-priority stream reading one half and writing the other, while the observation writer
  * (get_feature_vector) of step k is still streaming out on a second internal stream.  Every step does
- * the full work of cz_step; only the ordering guarantee changes: outputs are ordered with the
- * caller's stream after cz_pipeline_wait().  cz_pipeline_reset(t, h) declares that half h holds the
- * current state (after cz_reset wrote it) and drains the internal streams. */
+ * the full work of cz_step; only the ordering guarantee changes: the caller's stream is ordered after the
+ * DYNAMICS of the step (state, rewards and flags are final, the action buffer may be overwritten or freed by
+ * later work on that stream); the observation rows are ordered with the caller's stream after
+ * cz_pipeline_wait().  `actions` must not be modified by any OTHER stream until then.
+ * cz_pipeline_reset(t, h) drains the internal streams (host-synchronising) and declares that half h holds
+ * the current state; call it BEFORE cz_reset writes into that half. */
 int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* actions, double* obs, double* reward,
                       uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs,
                       uint32_t flags, uint64_t seed, int64_t env_offset, void* stream);

@@ -49,16 +49,18 @@ def test_step_and_reset_reject_null_and_misaligned_buffers():
     flg = torch.zeros((n, 2), dtype=torch.uint8, device="cuda")
     act = torch.zeros((n, 2), dtype=torch.uint8, device="cuda")
     lid = torch.zeros((n,), dtype=torch.int32, device="cuda")
-    assert lib.cz_reset(h, state.data_ptr(), None, None, None, obs.data_ptr(), n, None) == -1
+    assert lib.cz_reset(h, state.data_ptr(), None, None, None, obs.data_ptr(), None, n, None) == -1
     assert b"layout_ids" in lib.cz_last_error()
-    assert lib.cz_reset(h, state.data_ptr(), lid.data_ptr(), None, None, obs.data_ptr() + 8, n, None) == -1
+    assert lib.cz_reset(h, state.data_ptr(), lid.data_ptr(), None, None, obs.data_ptr() + 8, None, n, None) == -1
     assert b"aligned" in lib.cz_last_error()
     assert lib.cz_step(h, state.data_ptr(), None, obs.data_ptr(), rew.data_ptr(), flg.data_ptr(), flg.data_ptr(), None,
-                       n, 0, 0, 0, None) == -1
+                       n, 1, 0, 0, 0, 0, None) == -1
     assert lib.cz_step(h, None, act.data_ptr(), obs.data_ptr(), rew.data_ptr(), flg.data_ptr(), flg.data_ptr(), None,
-                       n, 0, 0, 0, None) == -1
-    assert lib.cz_reset(h, state.data_ptr(), lid.data_ptr(), None, None, obs.data_ptr(), 0, None) == 0   # empty batch
-    assert lib.cz_reset(h, state.data_ptr(), lid.data_ptr(), None, None, obs.data_ptr(), n, None) == 0
+                       n, 1, 0, 0, 0, 0, None) == -1
+    assert lib.cz_step(h, state.data_ptr(), act.data_ptr(), obs.data_ptr(), rew.data_ptr(), flg.data_ptr(), flg.data_ptr(), None,
+                       n, 0, 0, 0, 0, 0, None) == -1 and b"k_steps" in lib.cz_last_error()
+    assert lib.cz_reset(h, state.data_ptr(), lid.data_ptr(), None, None, obs.data_ptr(), None, 0, None) == 0   # empty batch
+    assert lib.cz_reset(h, state.data_ptr(), lid.data_ptr(), None, None, obs.data_ptr(), None, n, None) == 0
     torch.cuda.synchronize()
     assert lib.cz_launch_count() >= 1
     lib.cz_tables_destroy(h)

@@ -91,7 +91,7 @@ def test_f32_host_step_and_null_obs():
     # obs == NULL: dynamics only, the observation buffer is not touched
     before = b.obs.clone()
     _native.check(b.lib.cz_step(b._handle, b.state.data_ptr(), act.cuda().data_ptr(), None, b.reward.data_ptr(),
-                                b.terminated.data_ptr(), b.truncated.data_ptr(), None, n, 0, 0, 0, stream))
+                                b.terminated.data_ptr(), b.truncated.data_ptr(), None, n, 1, 0, 0, 0, 0, stream))
     a.step(act)
     torch.cuda.synchronize()
     assert torch.equal(b.obs, before) and torch.equal(a.state, b.state)

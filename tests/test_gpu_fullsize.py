@@ -83,7 +83,7 @@ def _check_invariants(env):
 def test_fullsize_sampled_lockstep_invariants_and_idempotence():
     env = _env()
     rid = _recipe_ids(N, 1)
-    lids = env.default_layout_ids()
+    lids = env.default_layout_ids().cpu().numpy()
     obs0 = env.reset(layout_ids=lids, recipe_ids=rid).clone()
     pres0 = _check_invariants(env).clone()
     picks = np.linspace(0, N - 1, 48).astype(int)
@@ -143,7 +143,7 @@ def test_fullsize_exhaustive_lockstep_against_the_compiled_oracle():
     from oracle.cz_oracle_c import CBatch
     env = _env()
     rid = _recipe_ids(N, 21)
-    lids = env.default_layout_ids()
+    lids = env.default_layout_ids().cpu().numpy()
     obs = env.reset(layout_ids=lids, recipe_ids=rid).cpu().numpy()
     ridn = rid.numpy()
     cpu = CBatch([env.tables.layouts[l] for l in lids], [[BOOK[int(r)] for r in row] for row in ridn], 400,
@@ -184,7 +184,7 @@ def test_exhaustive_lockstep_other_paths(name, level, meta, A, recipes, scheme, 
     kw = {} if not spawn else dict(agent_respawn_rate=spawn[0], agent_despawn_rate=spawn[1], grace_period=spawn[2])
     env = BatchedCookingEnv(n, lv, mt, A, 10 ** 5, recipes, end_condition_all_dishes=True, action_scheme=scheme,
                             layout_pool_size=64, layout_seed=9, seed=31, **kw)
-    lids = env.default_layout_ids()
+    lids = env.default_layout_ids().cpu().numpy()
     obs = env.reset(layout_ids=lids).cpu().numpy()
     cpu = CBatch([env.tables.layouts[l] for l in lids], [recipes] * n, 10 ** 5, end_condition_all_dishes=True,
                  action_scheme=scheme, **kw)

@@ -20,10 +20,15 @@ def _make(n, cfg, **kw):
                              reward_scheme=cfg["reward_scheme"], action_scheme=cfg.get("action_scheme", "scheme3"), **kw)
 
 
+@pytest.mark.parametrize("kernel", ["warp", "lane"])
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
-def test_cuda_replays_golden(path):
+def test_cuda_replays_golden(path, kernel, monkeypatch):
     """Lockstep replay of traces recorded from the unmodified reference: bit-exact state,
-    rewards (f64), flags and feature-vector observations (f64)."""
+    rewards (f64), flags and feature-vector observations (f64).  Small batches step on the
+    warp-per-environment kernel (csrc/cz_warp.cuh); "lane" forces the lane-per-environment kernels
+    (CZ_WARP_MAX_ENVS is read when the tables are created)."""
+    if kernel == "lane":
+        monkeypatch.setenv("CZ_WARP_MAX_ENVS", "0")
     g = load_golden(path)
     cfg = g["config"]
     n, A = len(g["layouts"]), cfg["num_agents"]
