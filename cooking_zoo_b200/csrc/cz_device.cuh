@@ -511,7 +511,10 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
       if (ai >= 5u) {          // interact with the cell the agent faces (cooking_world.py:115,139,157)
         const uint32_t o = A_ORI(rec);
         const int fx = (int)(rec & 7u) + (o == 2) - (o == 1), fy = (int)((rec >> 3) & 7u) + (o == 3) - (o == 4);
-        if (fx < 0 || fy < 0 || fx > T.W - 1 || fy > T.H - 1) { e.err |= CZ_ERR_OFFGRID; continue; }
+        if (fx < 0 || fy < 0 || fx > T.W - 1 || fy > T.H - 1) {  // IndexError at cooking_world.py:119 / :160; pick-up-special (:138-154) finds nothing
+          if (ai != 6u) e.err |= CZ_ERR_OFFGRID;
+          continue;
+        }
         const uint32_t cell = (uint32_t)(fx | fy << 3);
         bool stale = false;
         const uint32_t p = cz_interact<FAST>(T, e, i, cell, ai, stale);

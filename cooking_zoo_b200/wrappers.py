@@ -96,10 +96,16 @@ class ParallelCookingEnv:
         obs = self._b.reset(layout_ids=np.array([lid], np.int32)).cpu().numpy()[0]
         self.agents = self.possible_agents[:]
         self._done = False
+        self._termination_info = ""
+        self._was_active = np.ones(len(self.possible_agents), bool)
         return ({a: obs[i].copy() for i, a in enumerate(self.possible_agents)},
                 {a: {} for a in self.possible_agents})
 
     def step(self, actions):
+        """accumulated_step through the dict surface (cooking_env.py:243-269).  Only agents that are active or
+        whose status changed this step appear in the returned dicts, and `self.agents` follows them: a despawned
+        agent leaves (truncated=True on its despawn step, :333-350) and comes back when it respawns, while the
+        episode goes on for the others; the episode ends when the recipes are complete or max_steps is reached."""
         if self._done:
             raise RuntimeError("step() called on a finished episode: call reset() first")
         A = len(self.possible_agents)
@@ -109,18 +115,29 @@ class ParallelCookingEnv:
         obs, rew, term, trunc, info = self._b.step(act)
         obs, rew = obs.cpu().numpy()[0], rew.cpu().numpy()[0]
         term, trunc = term.cpu().numpy()[0].astype(bool), trunc.cpu().numpy()[0].astype(bool)
-        t = int(info["t"][0])
-        done = info["recipe_done"][0].cpu().numpy().astype(bool)
-        tinfo = f"Terminating because {self.max_steps} timesteps passed" if trunc.any() else ""
+        full = self._b.info()
+        t = int(full["t"][0])
+        over = bool(full["done"][0])
+        active = full["active"][0].cpu().numpy().astype(bool)
+        done = full["recipe_done"][0].cpu().numpy().astype(bool)
+        # compute_truncated sets the message only when the clock runs out (cooking_env.py:334-335); it then stays set
+        if t >= self.max_steps:
+            self._termination_info = f"Terminating because {self.max_steps} timesteps passed"
+        relevant = active | trunc          # active, or status changed this step (despawned now / truncated by the clock)
         out_obs, out_r, out_te, out_tr, out_i = {}, {}, {}, {}, {}
         for i, a in enumerate(self.possible_agents):
+            if not relevant[i]:
+                continue
             out_obs[a] = obs[i].copy()
             out_r[a] = np.float64(rew[i])
             out_te[a] = bool(term[i])
             out_tr[a] = bool(trunc[i])
-            out_i[a] = {"goal_vector": self.goal_vectors[a], "t": t, "termination_info": tinfo,
-                        "recipe_done": bool(done[i]), "action": int(act[0, i]), "task": self.recipe_names[i]}
-        if term.any() or trunc.any():
+            out_i[a] = {"goal_vector": self.goal_vectors[a], "t": t, "termination_info": self._termination_info,
+                        "recipe_done": bool(done[i]), "action": int(act[0, i]) if self._was_active[i] else 0,
+                        "task": self.recipe_names[i]}
+        self._was_active = active.copy()
+        self.agents = [a for i, a in enumerate(self.possible_agents) if relevant[i]]     # cooking_env.py:264-266
+        if over:
             self._done = True
             self.agents = []
         return out_obs, out_r, out_te, out_tr, out_i

@@ -48,7 +48,8 @@ extern "C" {
 #define CZ_ERR_SPAWN_LOC 8u       /* generate_location timed out (parsing.py:154-167)               */
 #define CZ_ERR_TRUNC_DESPAWN 16u  /* IndexError at cooking_env.py:348 (truncation with despawned agent) */
 #define CZ_ERR_OBS_OVERFLOW 32u   /* more objects of a type than meta slots (cooking_env.py:371)    */
-#define CZ_ERR_OFFGRID 64u        /* scheme1 interaction with a cell off the grid: get_objects_at(...)[0] IndexError */
+#define CZ_ERR_OFFGRID 64u        /* scheme1 INTERACT_PRIMARY / EXECUTE_ACTION facing a cell off the grid: get_objects_at(...)[0]
+                                     IndexError (cooking_world.py:119, :160); PICK_UP_SPECIAL there is a silent no-op (:138-154) */
 #define CZ_ERR_BAD_ID 128u        /* cz_reset: layout id / recipe id outside the compiled tables (id 0 was used instead) */
 
 /* ---- packed per-environment state --------------------------------------------------

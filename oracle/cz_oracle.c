@@ -205,6 +205,9 @@ static void execute(CzoEnv* e, int x, int y) {
       if (o->type == T_BREAD) { /* Bread.chop spawns a chopped twin appended to content and world */
         int twin = add_object(e, T_BREAD, o->x, o->y);
         e->objs[twin].chopped = 1;
+        /* more Breads than the meta file has slots: the reference's observation silently grows (cooking_env.py:371) */
+        for (int m = 0; m < e->n_meta; ++m)
+          if (e->meta_type[m] == T_BREAD && e->n_by_type[T_BREAD] > e->meta_count[m]) e->error |= 32u;
         st = &e->objs[e->static_at[y][x]];
         st->content[st->n_content++] = (uint8_t)twin;
       }
@@ -338,7 +341,9 @@ static void agent_actions_1(CzoEnv* e, const int* idx, int n, int* acts) {
       if (walkable(e, tx, ty)) walk_to(e, ag, tx, ty);
     } else if (a >= 5 && a <= 7) {
       target(ag, ag->orientation, &tx, &ty);
-      if (!in_grid(e, tx, ty)) { e->error |= 64u; continue; }
+      /* off the grid: get_objects_at(...)[0] raises IndexError (cooking_world.py:119, :160); pick-up-special (:138-154)
+       * never looks the static object up and simply finds nothing */
+      if (!in_grid(e, tx, ty)) { if (a != 6) e->error |= 64u; continue; }
       if (a == 5) primary(e, ag, tx, ty);
       else if (a == 6) pickup_special(e, ag, tx, ty);
       else execute(e, tx, ty);
@@ -530,7 +535,7 @@ void czo_observe(const CzoEnv* e, int agent, double* out) {
         out[p++] = 1.0;
       }
     } else {
-      for (int j = 0; j < e->n_by_type[ty]; ++j, ++n) {
+      for (int j = 0; j < e->n_by_type[ty] && j < e->meta_count[m]; ++j, ++n) {  /* beyond the slots: flagged (error 32) at creation */
         const Obj* o = &e->objs[e->by_type[ty][j]];
         if (!len) continue;
         out[p++] = (o->x - me->x) / W;
@@ -601,6 +606,14 @@ void czo_export(const CzoEnv* e, int16_t* agents, int16_t* objs, int16_t* static
 }
 
 uint32_t czo_error(const CzoEnv* e) { return e->error; }
+
+/* Agent.move_to (world_objects.py:794-797) without the Floor bookkeeping of a walk: test helper for the directed
+ * scenarios of SURVEY.md Appendix E, the counterpart of RefEnv.teleport / OracleEnv.teleport */
+void czo_teleport(CzoEnv* e, int agent, int x, int y) {
+  Agent* ag = &e->agents[agent];
+  ag->x = x; ag->y = y;
+  if (ag->holding >= 0) move_obj(e, ag->holding, x, y);
+}
 int czo_sizeof(void) { return (int)sizeof(CzoEnv); }
 
 /* one step of n independent environments + every agent's observation (the CPU baseline's unit of work) */

@@ -443,7 +443,10 @@ class OracleEnv:
             elif a in (5, 6, 7):                                 # resolve_interaction :33-40
                 cell = self._target(ag, ag.orientation)
                 if cell not in self.static_at:
-                    self.error |= 64                             # get_objects_at(...)[0] -> IndexError off the grid
+                    # get_objects_at(...)[0] -> IndexError off the grid (cooking_world.py:119, :160); the pick-up-special
+                    # path never looks the static object up (:138-154): nothing is there, nothing happens
+                    if a != 6:
+                        self.error |= 64
                     continue
                 st = self.static_at[cell]
                 if a == 5:

@@ -44,6 +44,7 @@ def load():
         lib.czo_export.argtypes = [P, P, P, P, P, P]
         lib.czo_error.argtypes = [P]
         lib.czo_error.restype = C.c_uint32
+        lib.czo_teleport.argtypes = [P, C.c_int, C.c_int, C.c_int]
         lib.czo_batch_step.argtypes = [P, C.c_int, P, P, P, P, P]
         _lib = lib
     return _lib
@@ -140,7 +141,7 @@ class COracleEnv:
         return {"agents": agents, "objs": objs, "statics": statics, "marks": marks, "t": np.int32(t[0])}
 
     def teleport(self, i, x, y):
-        raise NotImplementedError("directed teleports are replayed through the Python oracle")
+        self.lib.czo_teleport(self.h, int(i), int(x), int(y))
 
 
 class CBatch:

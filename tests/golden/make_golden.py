@@ -113,10 +113,13 @@ def record(cfg, seeds, T, policy, teleports=None):
                 tr["policy"][t] = policy.raw
             try:
                 r, te, tu, re_ = env.step(act)
-            except IndexError:
+            except (IndexError, ValueError, AttributeError) as ex:
+                tr["raised_type"] = type(ex).__name__
                 # truncation with a despawned agent raises in the reference
-                # (cooking_env.py:337/348); the trace ends before that step
+                # (cooking_env.py:337/348); the trace ends before that step and remembers it: the action of
+                # step `raised` stays in `actions`, so a replay can take the step and check the error contract
                 length = t
+                tr["raised"] = t
                 break
             rew.append(r); term.append(te); trunc.append(tu); rel.append(re_)
             st = env.export_state()
@@ -154,6 +157,9 @@ def save(name, cfg, traces, T):
         "actions": np.stack([tr["actions"] for tr in traces]),
         "teleport": np.stack([tr["teleport"] for tr in traces]),
         "length": np.array([tr["length"] for tr in traces], np.int32),
+        # step at which the reference itself raised IndexError (Appendix C-9), -1: it did not
+        "raised": np.array([tr.get("raised", -1) for tr in traces], np.int32),
+        "raised_type": np.array(json.dumps([tr.get("raised_type", "") for tr in traces])),
     }
     if "policy" in traces[0]:
         # raw CookingAgent.step outputs on the state BEFORE step t (-1: the reference agent raised)
@@ -270,7 +276,102 @@ def main_custom():
     save("custom_recipes_any", cfg2, record(cfg2, range(1310, 1314), 300, Heuristic(0.15)), 300)
 
 
+def main_errors():
+    """runs that reach max_steps with despawn / respawn enabled.  Where an agent with an
+    index >= len(env.agents) is relevant on the time-up step the reference raises IndexError (cooking_env.py:337
+    sizes active_agents by the LIVE agent count, :348 indexes it by world agent index); the trace stores the step
+    (`raised`).  Traces that time out with every relevant agent below that bound do not raise and are ordinary."""
+    base = {"level": "coop_test", "meta_file": "example", "reward_scheme": None}
+    cfg = dict(base, num_agents=2, recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, max_steps=30,
+               spawn={"respawn": 0.25, "despawn": 0.12, "grace": 2, "seed": 909})
+    save("c9_trunc_despawn", cfg, record(cfg, range(1400, 1424), 30, sticky), 30)
+    cfg4 = dict(base, level="tests/golden/levels/open4.json", meta_file="tests/golden/levels/meta4.json", num_agents=4,
+                recipes=["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"], end_all=True, max_steps=24,
+                spawn={"respawn": 0.2, "despawn": 0.15, "grace": 1, "seed": 910})
+    save("c9_trunc_despawn_open4", cfg4, record(cfg4, range(1430, 1446), 24, uniform), 24)
+
+
+def main_error_bits():
+    """One directed trace per reachable CZ_ERR_* bit whose trigger makes the reference itself raise: the trace ends at the
+    raising step (`raised`, `raised_type`).  tests/test_error_contract.py replays them and takes that step."""
+    lv = "tests/golden/levels/"
+    # CZ_ERR_OFFGRID: scheme1 interaction while facing a cell off the grid: get_objects_at(...)[0] IndexError
+    # (cooking_world.py:119 / :143 / :160).  Agent 0 spawns on (0,0) facing left (orientation 1).
+    cfg = {"level": lv + "edge_floor.json", "meta_file": "example", "max_steps": 50, "reward_scheme": None, "num_agents": 2,
+           "recipes": ["TomatoSalad", "no_recipe"], "end_all": False, "action_scheme": "scheme1"}
+    for name, first in (("err_offgrid_primary", 5), ("err_offgrid_special", 6), ("err_offgrid_execute", 7)):
+        pol, tele = _script([({}, [3, 0]), ({}, [4, 4]), ({}, [1, 0]), ({}, [first, 0])], 2)
+        save(name, cfg, record(cfg, [0], 4, pol, tele), 4)
+    # CZ_ERR_SPAWN_LOC: agent 0 respawns while agent 1 stands on its only spawn cell: generate_location gives up after
+    # 1001 draws (ValueError, parsing.py:154-167).  despawn / respawn rates 1.0, no grace period.
+    cfg = {"level": lv + "one_cell_spawn.json", "meta_file": "example", "max_steps": 50, "reward_scheme": None,
+           "num_agents": 2, "recipes": ["TomatoSalad", "no_recipe"], "end_all": False,
+           "spawn": {"respawn": 1.0, "despawn": 1.0, "grace": 0, "seed": 5}}
+    pol, tele = _script([({}, [3, 1]), ({}, [0, 0]), ({}, [0, 0])], 2)
+    save("err_spawn_loc", cfg, record(cfg, [0], 3, pol, tele), 3)
+    # CZ_ERR_SWITCH_LINK: two Switches in one level link to each other (level ATTRIBUTES are never applied, Appendix
+    # C-6, so every LinkedObject shares group None): pressing one calls switch_state() on the other Switch, which
+    # has no such method (AttributeError, world_objects.py:165-169)
+    cfg = {"level": lv + "two_switch.json", "meta_file": "example", "max_steps": 50, "reward_scheme": None,
+           "num_agents": 1, "recipes": ["TomatoSalad"], "end_all": False}
+    pol, tele = _script([({}, [3]), ({}, [2])], 1)
+    save("err_switch_link", cfg, record(cfg, [0], 2, pol, tele), 2)
+
+
+def _script(steps, A):
+    """steps: list of (teleports {agent: (x, y)}, actions [A]) -> (scripted policy, teleports by step)"""
+    tele = {t: tp for t, (tp, _) in enumerate(steps) if tp}
+    return scripted([list(a) for _, a in steps]), tele
+
+
+def main_kat():
+    """directed known-answer scenarios, recorded from the reference with Agent.move_to teleports
+    (layout of random.seed(0)).  tests/test_kat.py states what each step must show; the usual replays then hold the
+    oracle, the C oracle and the CUDA kernels to every recorded array."""
+    base = {"level": "coop_test", "meta_file": "example", "max_steps": 400, "reward_scheme": None}
+    cfg2 = dict(base, num_agents=2, recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True)
+    steps = [
+        ({0: (1, 2), 1: (1, 4)}, [3, 4]),   # t0  E1: both target (1,3): both cancelled, orientations still change
+        ({0: (1, 2), 1: (1, 3)}, [3, 4]),   # t1  E2: swap
+        ({0: (1, 2), 1: (1, 1)}, [4, 4]),   # t2  E3: a1 bumps the counter, a0 targets a1's cell: cancelled
+        ({0: (2, 2), 1: (5, 1)}, [0, 2]),   # t3  E5: a1 grabs the Banana from counter (6,1)
+        ({1: (4, 5)}, [0, 3]),              # t4  E6: Banana into the Blender (4,6): READY, toggle off, still FRESH
+        ({}, [0, 3]),                       # t5  E7: execute: mashed in the same step, toggle off again, NOT_USABLE
+        ({}, [0, 3]),                       # t6  E8: a1 holds the mashed Banana
+        ({1: (5, 2)}, [0, 2]),              # t7  E9: counter (6,2) holds a Watermelon: nothing happens
+        ({1: (4, 1)}, [0, 4]),              # t8  E10: Banana straight onto the Deliversquare (4,0)
+        ({}, [0, 4]),                       # t9  E11: a Deliversquare never releases
+        ({1: (5, 3)}, [0, 2]),              # t10      a1 grabs the Plate from counter (6,3)
+        ({1: (4, 1)}, [0, 4]),              # t11 E12: the Banana is scooped onto the held Plate
+        ({1: (5, 2)}, [0, 2]),              # t12 E13: Plate[Banana] vs fresh Watermelon: branch 2 rejects, no fall-through
+        ({1: (4, 1)}, [0, 4]),              # t13 E14: Plate placed on the Deliversquare; CarrotBanana not complete
+        ({0: (1, 3)}, [1, 0]),              # t14 E17: a0 grabs the Bread from counter (0,3)
+        ({0: (1, 1)}, [1, 0]),              # t15      onto the Cutboard (0,1): READY
+        ({}, [1, 0]),                       # t16      chop: a second, chopped Bread appears on the board
+        ({}, [1, 0]),                       # t17      grab takes the new Bread (free), the old one stays
+        ({0: (1, 3)}, [1, 0]),              # t18      put it on the empty counter (0,3)
+        ({0: (1, 1)}, [1, 0]),              # t19      grab the first Bread
+    ]
+    pol, tele = _script(steps, 2)
+    save("kat_coop_seed0", cfg2, record(cfg2, [0], len(steps), pol, tele), len(steps))
+    # E4: three agents in the open kitchen: the third ends on the first one's cell
+    cfg3 = dict(base, level="tests/golden/levels/open4.json", meta_file="tests/golden/levels/meta4.json", num_agents=3,
+                recipes=["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad"], end_all=True)
+    pol, tele = _script([({0: (1, 2), 1: (1, 4), 2: (2, 2)}, [3, 4, 1]), ({}, [0, 0, 0])], 3)
+    save("kat_open4_three", cfg3, record(cfg3, [0], 2, pol, tele), 2)
+    # E15: switch_test, one agent steps on the Switch (4,3) and then stands still: it toggles every step
+    cfgs = dict(base, level="switch_test", num_agents=1, recipes=["TomatoLettuceSalad"], end_all=False)
+    pol, tele = _script([({0: (3, 3)}, [2]), ({}, [0]), ({}, [0]), ({}, [1]), ({}, [2])], 1)
+    save("kat_switch", cfgs, record(cfgs, [0], 5, pol, tele), 5)
+
+
 def main():
+    if sys.argv[1:] == ["errors"]:
+        return main_errors()
+    if sys.argv[1:] == ["kat"]:
+        return main_kat()
+    if sys.argv[1:] == ["error_bits"]:
+        return main_error_bits()
     if sys.argv[1:] == ["policy"]:
         return main_policy()
     if sys.argv[1:] == ["custom"]:
@@ -347,6 +448,9 @@ def main():
     save("spawn_open4", cfgsp4, record(cfgsp4, range(810, 816), 200, uniform), 200)
     main_policy()
     main_custom()
+    main_errors()
+    main_kat()
+    main_error_bits()
 
 
 if __name__ == "__main__":

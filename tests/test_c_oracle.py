@@ -21,9 +21,11 @@ def test_c_oracle_replays_golden(path):
         ctx = f"{path} trace {n} reset"
         assert_state_equal({k: g[k][n, 0] for k in STATE_KEYS}, env.export_state(), ctx)
         assert_obs_equal(g["obs"][n, 0], np.stack([env.observe(i) for i in range(A)]), ctx)
-        assert (g["teleport"][n] < 0).all()
         for t in range(int(g["length"][n])):
             ctx = f"{path} trace {n} step {t}"
+            for i in range(A):
+                if g["teleport"][n, t, i, 0] >= 0:
+                    env.teleport(i, *map(int, g["teleport"][n, t, i]))
             rew, term, trunc, rel = env.step(g["actions"][n, t])
             assert np.array_equal(bits(g["reward"][n, t]), bits(rew)), ctx
             assert np.array_equal(g["term"][n, t], term) and np.array_equal(g["trunc"][n, t], trunc), ctx
