@@ -313,7 +313,11 @@ def run_gpu_arm(args):
             torch.cuda.synchronize(dev)
 
     def timed_run(pipelined, sample_clocks, obs_dtype=torch.float64):
-        """W warm-up + K timed steps of one mode; returns (env, ms_total max over ranks, launches, clocks)."""
+        """W warm-up + K timed steps of one mode; returns (env, ms_total max over ranks, launches, clocks, how).
+
+        The K timed steps are enqueued as ONE CUDA graph when K <= 512 (captured after the eager warm-up, replayed once
+        untimed, then timed): the driver's short runs (K = 20) otherwise measure the host's launch jitter, not the GPU.
+        Every step is a full cz_step / cz_step_pipelined with its own resident action tensor; nothing is skipped."""
         env = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
                                 device=str(dev), recipe_pool=BOOK, layout_pool_size=400, layout_seed=0,
                                 auto_reset=True, seed=2026, env_offset=rank * N, pipelined=pipelined, obs_dtype=obs_dtype)
@@ -321,6 +325,31 @@ def run_gpu_arm(args):
         for s in range(args.warmup):
             env.step(actions[s % ring])
         env.wait()
+        sync_all()
+        K = args.steps
+        graph, how = None, "eager launches"
+        if not args.no_graph and K <= 512 and (not pipelined or K % 2 == 0):
+            try:
+                if pipelined:   # no event of the eager warm-up may be waited on inside the capture
+                    _native.check(env.lib.cz_pipeline_reset(env._handle, env.lib.cz_pipeline_current(env._handle)))
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                graph = torch.cuda.CUDAGraph()
+                l0 = env.lib.cz_launch_count()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(graph, stream=side):
+                        for s in range(K):
+                            env.step(actions[s % ring])
+                        env.wait()
+                captured = env.lib.cz_launch_count() - l0
+                torch.cuda.current_stream(dev).wait_stream(side)
+                graph.replay()          # untimed: K more warm-up steps, uploads the graph
+                how = f"one CUDA graph of the {K} steps ({captured} kernel nodes)"
+            except Exception as ex:     # capture not possible on this box: time eager launches
+                sys.stderr.write(f"timed_run: graph capture failed ({ex!r}); timing eager launches\n")
+                graph = None
+                env.close()
+                return timed_run_eager(pipelined, sample_clocks, obs_dtype)
         sync_all()
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
@@ -330,31 +359,42 @@ def run_gpu_arm(args):
         sync_all()
         t_host0 = time.perf_counter()
         ev0.record()
-        for s in range(args.steps):
-            env.step(actions[s % ring])
-        env.wait()      # pipelined mode: order the internal streams before the closing event (no-op otherwise)
+        if graph is not None:
+            graph.replay()
+        else:
+            for s in range(K):
+                env.step(actions[s % ring])
+            env.wait()      # pipelined mode: order the internal streams before the closing event (no-op otherwise)
         ev1.record()
         torch.cuda.synchronize(dev)
         t_host1 = time.perf_counter()
-        launches = env.lib.cz_launch_count() - launches0
+        if graph is not None and pipelined:
+            # the library's events were last recorded inside the capture: forget them before any eager call waits on one
+            _native.check(env.lib.cz_pipeline_reset(env._handle, env.lib.cz_pipeline_current(env._handle)))
+        launches = captured if graph is not None else env.lib.cz_launch_count() - launches0
         clocks = sampler.stop(t_host0, t_host1) if sampler else None
         t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.barrier()
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return env, float(t.item()), launches, clocks
+        env._bench_graph = graph        # keep the graph (and its captured pointers) alive as long as the environment
+        return env, float(t.item()), launches, clocks, how
+
+    def timed_run_eager(pipelined, sample_clocks, obs_dtype):
+        args.no_graph = True
+        return timed_run(pipelined, sample_clocks, obs_dtype)
 
     # in-place step (one fused kernel per step) first, then the pipelined throughput mode (the headline)
-    env_s, ms_sync, launches_sync, _ = timed_run(False, False)
+    env_s, ms_sync, launches_sync, _, how_sync = timed_run(False, False)
     sync_value = world * N * args.steps / (ms_sync / 1e3)
     L = env_s.obs_len
     if args.mode == "sync":
-        env, ms_total_max, launches, clocks = timed_run(False, True)
+        env, ms_total_max, launches, clocks, how_timed = timed_run(False, True)
     else:
         env_s.close()
         del env_s
         torch.cuda.empty_cache()
-        env, ms_total_max, launches, clocks = timed_run(True, True)
+        env, ms_total_max, launches, clocks, how_timed = timed_run(True, True)
     lib = env.lib
     ms_per_step = ms_total_max / args.steps
     value = world * N * args.steps / (ms_total_max / 1e3)
@@ -398,80 +438,138 @@ def run_gpu_arm(args):
     h2d = N * A
     d2h = N * A * L * 8 + N * A * 8 + 2 * N * A
 
-    # ---- BASELINE config 3 (4096 two-agent envs on one GPU): launch-bound, reported beside the headline
+    # ---- BASELINE config 3 (4096 two-agent envs on one GPU): latency-bound; per launch and K steps per launch
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+    def rate(fn, units, reps, warm=5, fin=None):
+        for _ in range(warm):
+            fn()
+        if fin:
+            fin()
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        if fin:
+            fin()       # pipelined groups: order the internal streams before the closing event
+        a1.record()
+        torch.cuda.synchronize(dev)
+        return units * reps / (a0.elapsed_time(a1) / 1e3)
+
     cfg3 = None
     if rank == 0 and world == 1 and not args.no_cfg3:
         try:
-            n3 = 4096
+            n3, K3 = 4096, 64
             env3 = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
                                      device=str(dev), layout_pool_size=400, layout_seed=0, auto_reset=True, seed=7)
             env3.reset()
-            act3 = torch.randint(0, 5, (ring, n3, A), generator=g, dtype=torch.uint8).to(dev)
-            for s in range(20):
-                env3.step(act3[s % ring])
-            torch.cuda.synchronize(dev)
-            k3 = 2000
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            for s in range(k3):
-                env3.step(act3[s % ring])
-            a1.record()
-            torch.cuda.synchronize(dev)
-            per_launch = n3 * k3 / (a0.elapsed_time(a1) / 1e3)
-            # the same launches captured once in a CUDA graph (one graph = `ring` steps) and replayed: with the actions of the
-            # K steps resident, and with the actions generated on the device inside the graph (cz_random_actions)
-            def graphed_rate(next_actions):
-                graph = torch.cuda.CUDAGraph()
-                side = torch.cuda.Stream(dev)
-                side.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(side):
-                    for s in range(ring):
-                        env3.step(next_actions(s))
-                    side.synchronize()
-                    with torch.cuda.graph(graph, stream=side):
-                        for s in range(ring):
-                            env3.step(next_actions(s))
-                torch.cuda.current_stream(dev).wait_stream(side)
-                for _ in range(5):
-                    graph.replay()
-                torch.cuda.synchronize(dev)
-                reps = 200
-                a0.record()
-                for _ in range(reps):
-                    graph.replay()
-                a1.record()
-                torch.cuda.synchronize(dev)
-                return n3 * ring * reps / (a0.elapsed_time(a1) / 1e3)
-            graphed = graphed_rate(lambda s: act3[s])
-            graphed_dev = graphed_rate(lambda s: env3.random_actions(s))
-            # pipelined throughput mode at this size
-            env3p = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
-                                      action_scheme="scheme3", device=str(dev), layout_pool_size=400, layout_seed=0,
-                                      auto_reset=True, seed=7, pipelined=True)
-            env3p.reset()
-            for s in range(20):
-                env3p.step(act3[s % ring])
-            env3p.wait()
-            torch.cuda.synchronize(dev)
-            a0.record()
-            for s in range(k3):
-                env3p.step(act3[s % ring])
-            env3p.wait()
-            a1.record()
-            torch.cuda.synchronize(dev)
-            piped = n3 * k3 / (a0.elapsed_time(a1) / 1e3)
-            env3p.close()
-            cfg3 = {"workload": "cfg3: 4096 two-agent coop_test envs, 1 GPU, random actions, feature_vector obs",
-                    "per_launch_env_steps_per_s": per_launch, "cuda_graph_env_steps_per_s": graphed,
-                    "k_steps_per_launch": {"K": ring, "env_steps_per_s": graphed,
-                                           "how": f"one CUDA graph launch = {ring} consecutive cz_step kernels, actions of the K steps resident",
-                                           "device_actions_env_steps_per_s": graphed_dev,
-                                           "device_actions_how": f"one CUDA graph launch = {ring} x (cz_random_actions + cz_step)"},
-                    "pipelined_env_steps_per_s": piped,
-                    "note": "20 MB per step: launch/latency bound, not HBM bound"}
+            act3 = torch.randint(0, 5, (K3, n3, A), generator=g, dtype=torch.uint8).to(dev)
+            cnt = [0]
+
+            def one_step():
+                env3.step(act3[cnt[0] % K3])
+                cnt[0] += 1
+            per_launch = rate(one_step, n3, 2000, 20)
+            # K steps in ONE launch of the warp-per-environment kernel (cz_step's k_steps): actions of the K steps resident,
+            # or drawn inside the kernel from the counter stream of cz_random_actions
+            k_res = rate(lambda: env3.step_k(K3, actions=act3), n3 * K3, 60)
+            k_dev = rate(lambda: env3.step_k(K3, action_step=cnt[0]), n3 * K3, 60)
+            # the same per-step launches captured in a CUDA graph (what round 1 reported as its K-step figure)
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    for s in range(16):
+                        env3.step(act3[s])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graphed = rate(graph.replay, n3 * 16, 200)
+            b3 = A * env3.obs_len * 8 + A * 8 + 2 * A + A + 2 * env3.tables.rows * 4
+            cfg3 = {"workload": "cfg3: 4096 two-agent coop_test envs, 1 GPU, random actions, feature_vector f64 obs, auto-reset",
+                    "per_launch_env_steps_per_s": per_launch,
+                    "cuda_graph_env_steps_per_s": graphed,
+                    "k_steps_per_launch": {"K": K3, "env_steps_per_s": k_res,
+                                           "how": f"cz_step(k_steps={K3}): one launch of cz_warp_kernel (one warp per environment, "
+                                                  f"state in registers across the K steps, rows written every step), actions "
+                                                  f"[K][n][A] resident",
+                                           "device_actions_env_steps_per_s": k_dev,
+                                           "device_actions_how": "the same launch with CZ_STEP_DEVICE_ACTIONS: actions drawn inside "
+                                                                 "the kernel from the counter stream of cz_random_actions"},
+                    "bytes_per_env_step": b3,
+                    "roofline": {"bound": "latency (19 MB of rows per step stay in the 126 MB L2)", "unit": "GB/s",
+                                 "achieved": k_res * b3 / 1e9, "peak": peak, "frac": k_res * b3 / 1e9 / peak},
+                    "note": "a step writes 19 MB: bounded by the per-step instruction chain, not by HBM"}
             env3.close()
         except Exception as ex:      # a side measurement must never cost the headline line
             cfg3 = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+
+    # ---- BASELINE config 5: 1-4 agents per environment, heuristic cooks on the device, despawn / respawn on
+    cfg5 = None
+    if rank == 0 and world == 1 and not args.no_cfg3:
+        try:
+            from cooking_zoo_b200 import MixedAgentCookingEnv
+            n5 = 65536
+            counts = (np.arange(n5) % 4) + 1
+            lv5 = os.path.join(ROOT, "tests", "golden", "levels", "open4.json")
+            mt5 = os.path.join(ROOT, "tests", "golden", "levels", "meta4.json")
+            r5 = ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "AppleWatermelon"]
+            out5 = {}
+            for mode in ("in_place", "pipelined"):
+                mix = MixedAgentCookingEnv(counts, lv5, mt5, MAX_STEPS, r5, device=str(dev), end_condition_all_dishes=True,
+                                           action_scheme="scheme3", layout_pool_size=256, auto_reset=True, seed=5,
+                                           agent_respawn_rate=0.2, agent_despawn_rate=0.05, grace_period=3,
+                                           pipelined=(mode == "pipelined"))
+                mix.reset()
+
+                def closed_loop():
+                    acts, _ = mix.heuristic_actions()
+                    mix.step(acts)
+                out5[mode] = rate(closed_loop, n5, 100, 10, fin=mix.wait)
+                if mode == "in_place":
+                    b5 = sum(len(mix.index[a]) * (a * grp.obs_len * 8 + a * 11 + 2 * grp.tables.rows * 4)
+                             for a, grp in mix.groups.items()) / n5
+                mix.close()
+            cfg5 = {"workload": f"cfg5: {n5} envs on the open 4-agent kitchen, agent count 1-4 per env (one BatchedCookingEnv group per "
+                                f"count, own CUDA stream each), every action from the device cook (cz_policy_act), despawn 0.05 / "
+                                f"respawn 0.2 / grace 3, per-group recipes, auto-reset",
+                    "closed_loop_env_steps_per_s": out5["in_place"], "closed_loop_pipelined_env_steps_per_s": out5["pipelined"],
+                    "bytes_per_env_step": b5,
+                    "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": out5["pipelined"] * b5 / 1e9, "peak": peak,
+                                 "frac": out5["pipelined"] * b5 / 1e9 / peak,
+                                 "in_place_frac": out5["in_place"] * b5 / 1e9 / peak}}
+        except Exception as ex:
+            cfg5 = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+
+    # ---- generic kernels (tables outside the specialised class; forced here with CZ_GENERIC=1 on the headline workload)
+    generic = None
+    if rank == 0 and world == 1 and not args.no_cfg3:
+        try:
+            os.environ["CZ_GENERIC"] = "1"
+            envg = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
+                                     device=str(dev), recipe_pool=BOOK, layout_pool_size=400, layout_seed=0, auto_reset=True,
+                                     seed=2026)
+            del os.environ["CZ_GENERIC"]
+            envg.reset(recipe_ids=recipe_ids)
+            cg = [0]
+
+            def gen_step():
+                envg.step(actions[cg[0] % ring])
+                cg[0] += 1
+            vg = rate(gen_step, N, 100, 10)
+            bg = A * envg.obs_len * 8 + A * 8 + 2 * A + A + 2 * envg.tables.rows * 4
+            generic = {"workload": "the headline workload on the generic kernels (cz_env_kernel<.,.,0>: tables in global memory, any "
+                                   "observation plan), in-place step",
+                       "env_steps_per_s": vg, "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": vg * bg / 1e9, "peak": peak,
+                                                           "frac": vg * bg / 1e9 / peak}}
+            envg.close()
+        except Exception as ex:
+            os.environ.pop("CZ_GENERIC", None)
+            generic = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
     # ---- closed loop with the device policy: CookingAgent decisions + step, no host in between
     cook = None
@@ -531,9 +629,9 @@ def run_gpu_arm(args):
         try:
             env.wait()
             torch.cuda.synchronize(dev)
-            envf, ms_f, _, _ = timed_run(True, False, torch.float32)
+            envf, ms_f, _, _, _ = timed_run(True, False, torch.float32)
             envf.close()
-            envf, ms_fs, _, _ = timed_run(False, False, torch.float32)
+            envf, ms_fs, _, _, _ = timed_run(False, False, torch.float32)
             h_obs32 = torch.empty((N, A, L), dtype=torch.float32).pin_memory()
 
             def host_step32():
@@ -560,11 +658,6 @@ def run_gpu_arm(args):
             f32 = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
         state_bytes = env.tables.rows * 4
         bytes_per_env_step = A * L * 8 + A * 8 + 2 * A + A + 2 * state_bytes
         achieved = N * bytes_per_env_step / (ms_per_step / 1e3) / 1e9
@@ -617,11 +710,12 @@ def run_gpu_arm(args):
                         "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step)",
                         "host_link_gbs": (h2d + d2h) * e2e_value / N / 1e9 / world,
                         "numa_node_of_rank0": numa_node},
-                "gpu_launches": int(launches), "clocks": clocks, "cfg3": cfg3, "device_policy": cook, "f32_obs": f32,
+                "gpu_launches": int(launches), "timed_region": how_timed, "clocks": clocks, "cfg3": cfg3, "cfg5": cfg5,
+                "generic_tables": generic, "device_policy": cook, "f32_obs": f32,
                 "mode": args.mode,
                 "sync_step": {"value": sync_value, "ms_per_step": ms_sync / args.steps,
                               "frac": N * bytes_per_env_step / (ms_sync / args.steps / 1e3) / 1e9 / peak,
-                              "gpu_launches": int(launches_sync),
+                              "gpu_launches": int(launches_sync), "timed_region": how_sync,
                               "note": "in-place cz_step, outputs ordered on the caller's stream: dynamics kernel + row-writer kernel at this batch size (one fused kernel below 49152 environments)"},
                 "stats": {"episodes_started": float(stats[0]), "recipes_done_now": float(stats[1]),
                           "last_step_return": float(stats[2])}}
@@ -641,6 +735,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6000, help="oracle env-steps per host process for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph of the K steps")
     ap.add_argument("--mode", default="pipelined", choices=["pipelined", "sync"],
                     help="pipelined (default): throughput mode, the dynamics of step k+1 overlap the observation "
                          "writes of step k (two kernels, two streams, ping-pong state); sync: one fused kernel per step")

@@ -1127,7 +1127,7 @@ static int cz_launch_warp(const cz_tables* t, uint32_t* state, const uint8_t* ac
   if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
   const CzDev& T = t->dev;
   const int blocks = (n_envs + WK_WARPS - 1) / WK_WARPS;
-  const size_t smem = cz_block_smem_head(T.V) + (size_t)WK_WARPS * 104 * 4 + (size_t)WK_WARPS * T.A * ((T.stage_len + 1) / 2) * 16;
+  const size_t smem = cz_block_smem_head(T.V) + (size_t)WK_WARPS * WK_WORDS * 4 + (size_t)WK_WARPS * T.A * ((T.stage_len + 1) / 2) * 16;
   cudaStream_t s = (cudaStream_t)stream;
 #define CZ_WARP_GO(NA)                                                                                                     \
   cz_warp_kernel<NA><<<blocks, 32 * WK_WARPS, smem, s>>>(t->dev, state, actions, obs, reward, terminated, truncated, error_flags, \

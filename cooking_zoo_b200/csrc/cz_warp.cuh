@@ -18,6 +18,7 @@
 #define WK_WARPS 4  // environments (warps) per block
 #endif
 #define WK_FULL 0xffffffffu
+#define WK_WORDS 136  // per-warp scratch words: cells[64] | skp[8] | plist[32] (uint2)
 #define CZ_ACTION_STREAM 0xA5A5A5A5A5A5A5A5ull  // keeps the action stream apart from the spawn stream of the same seed
 
 template <int NA>
@@ -28,11 +29,14 @@ struct WEnv {
   uint32_t m_none, m_chop, m_mash;  // (recipe, node) pairs this slot's type can satisfy: always / when chopped / when mashed
   uint32_t ag[NA];                  // agent records (warp-uniform)
   uint32_t sbits, tinfo, marks, variant, rids, episode, err;  // warp-uniform
-  uint32_t pairs_static, pairs_static_only;  // warp-uniform masks over (recipe, node) pairs
+  uint32_t pairs_static_only, static_marks;  // pairs whose whole subtree is static, and which of them hold in this variant
+  uint32_t n_vote;                           // entries of `plist`
+  double v_idle;                             // a recipe's reward on a step that changes none of its marks
   uint64_t walk64, block64;  // cells whose static object is always walkable / is a Block (walkable by state)
   const SmemTabs* st;
   uint32_t* cells;   // [64] per-warp scratch: pairs satisfied per cell
   uint32_t* skp;     // [8]  pairs satisfied by a static kind
+  uint2* plist;      // [32] {subtree mask, own bit} of every pair that is decided by looking at the objects
   int lane;
 };
 
@@ -63,28 +67,54 @@ __device__ __forceinline__ bool wk_walkable(const CzDev& T, const WEnv<NA>& e, u
   return false;
 }
 
+// Subtree mask of pair p = 8 r + k in pair space (0 when the environment has no such node)
+template <int NA>
+__device__ __forceinline__ uint32_t wk_pair_desc(const CzDev& T, const WEnv<NA>& e, int p) {
+  constexpr bool FAST = true;
+  const SmemTabs* st = e.st;
+  const int r = p >> 3, k = p & 7;
+  if (r >= T.R) return 0u;
+  const uint32_t rid = (e.rids >> (8 * r)) & 255u;
+  return k < (int)TAB_RLEN(rid) ? (uint32_t)st->recipe_desc[rid][k] << (8 * r) : 0u;
+}
+
 // everything that depends on the static variant of the current layout (changes only on reset)
 template <int NA>
-__device__ __forceinline__ void wk_variant_consts(const CzDev& T, WEnv<NA>& e, uint32_t* scratch) {
+__device__ __forceinline__ void wk_variant_consts(const CzDev& T, WEnv<NA>& e) {
   constexpr bool FAST = true;
   const SmemTabs* st = e.st;
   e.walk64 = TAB_SMASK(e.variant, ST_FLOOR) | TAB_SMASK(e.variant, ST_SWITCH);
   e.block64 = TAB_SMASK(e.variant, ST_BLOCK);
+  uint32_t* scratch = e.cells;  // rewritten by every step anyway
   if (e.lane < T.D) scratch[TAB_SCAN(e.variant, e.lane)] = (uint32_t)e.lane;
   __syncwarp();
   e.rank = e.lane < T.D ? scratch[e.lane] : 0u;
   __syncwarp();
+  // a node whose whole subtree is static is decided by the variant's static masks alone: lane p decides pair p
+  bool holds = false;
+  if (e.pairs_static_only >> e.lane & 1u) {
+    const int r = e.lane >> 3;
+    const uint32_t rid = (e.rids >> (8 * r)) & 255u;
+    const uint32_t d = wk_pair_desc(T, e, e.lane) >> (8 * r);
+    uint64_t m = ~0ull;
+    for (int j = 0; j < CZ_MAX_NODES; ++j)
+      if (d >> j & 1u) m &= TAB_SMASK(e.variant, TAB_RNODE(rid, j) & 7u);
+    holds = m != 0;
+  }
+  e.static_marks = __ballot_sync(WK_FULL, holds);
 }
 
 // (recipe, node) pair p = 8 r + k, the bit layout of the MARKS word.  Per lane: the pairs an object in this slot
-// satisfies on its own (type + condition, recipe.py:96-98); per warp: the pairs a static kind satisfies.
+// satisfies on its own (type + condition, recipe.py:96-98); per warp: the pairs a static kind satisfies, and the
+// compact list of pairs that have to be looked for among the objects.  The recipes of an environment never change
+// inside a launch, so this runs once.
 template <int NA>
 __device__ __forceinline__ void wk_recipe_consts(const CzDev& T, WEnv<NA>& e) {
   constexpr bool FAST = true;
   const SmemTabs* st = e.st;
   const uint32_t my_type = e.lane < T.D ? TAB_STYPE(e.lane) : 0xFEu;
   e.m_none = e.m_chop = e.m_mash = 0;
-  e.pairs_static = 0;
+  uint32_t pairs_static = 0;
   if (e.lane < 8) e.skp[e.lane] = 0;
   __syncwarp();
   for (int r = 0; r < T.R; ++r) {
@@ -93,7 +123,7 @@ __device__ __forceinline__ void wk_recipe_consts(const CzDev& T, WEnv<NA>& e) {
     for (int k = 0; k < n; ++k) {
       const uint32_t node = TAB_RNODE(rid, k), bit = 1u << (8 * r + k);
       if (node & 256u) {
-        e.pairs_static |= bit;
+        pairs_static |= bit;
         if (e.lane == 0) e.skp[node & 7u] |= bit;
       } else if ((node & 255u) == my_type) {
         const uint32_t cond = (node >> 9) & 3u;
@@ -103,23 +133,27 @@ __device__ __forceinline__ void wk_recipe_consts(const CzDev& T, WEnv<NA>& e) {
       }
     }
   }
+  const uint32_t d = wk_pair_desc(T, e, e.lane);
+  const bool static_only = d != 0 && (d & ~pairs_static) == 0;
+  const bool vote = d != 0 && !static_only;
+  e.pairs_static_only = __ballot_sync(WK_FULL, static_only);
+  const uint32_t m_vote = __ballot_sync(WK_FULL, vote);
+  if (vote) e.plist[__popc(m_vote & ((1u << e.lane) - 1u))] = make_uint2(d, 1u << e.lane);
+  e.n_vote = __popc(m_vote);
   __syncwarp();
-  // a node whose whole subtree is static is decided by the static masks alone
-  e.pairs_static_only = 0;
-  for (int r = 0; r < T.R; ++r) {
-    const uint32_t rid = (e.rids >> (8 * r)) & 255u;
-    const int n = TAB_RLEN(rid);
-    for (int k = 0; k < n; ++k) {
-      const uint32_t d = (uint32_t)st->recipe_desc[rid][k] << (8 * r);
-      if ((d & ~e.pairs_static) == 0) e.pairs_static_only |= 1u << (8 * r + k);
-    }
-  }
+  // reward of a recipe none of whose marks changed: the reference's sum with every term but the time penalty at zero
+  double v = 0.0;
+  v = __dadd_rn(v, __dmul_rn(0.0, T.r_node));
+  v = __dadd_rn(v, 0.0);
+  v = __dadd_rn(v, 0.0);
+  e.v_idle = __dadd_rn(v, T.r_time);
 }
 
 // Recipe.update_recipe_state for every recipe of the environment at once (recipe.py:77-104).  A node is marked iff
 // some cell holds, for the node and every descendant, an object that satisfies that node on its own (the AND of the
 // children's cell masks in cz_recipe_marks, unrolled over the subtree).  Lanes OR their slot's pairs into a per-cell
-// word, read back everything satisfied at their own cell, and one vote per node decides it.
+// word, read back everything satisfied at their own cell, test every listed pair against it, and one OR-reduction
+// collects the marks.
 template <int NA>
 __device__ __forceinline__ uint32_t wk_recipe_marks(const CzDev& T, WEnv<NA>& e) {
   constexpr bool FAST = true;
@@ -134,27 +168,13 @@ __device__ __forceinline__ uint32_t wk_recipe_marks(const CzDev& T, WEnv<NA>& e)
   __syncwarp();
   uint32_t here = 0;
   if (present) here = e.cells[O_XY(rec)] | e.skp[TAB_GRID(e.variant, O_XY(rec)) & 7u];
-  __syncwarp();
-  uint32_t marks = 0;
-  for (int r = 0; r < T.R; ++r) {
-    const uint32_t rid = (e.rids >> (8 * r)) & 255u;
-    const int n = TAB_RLEN(rid);
-    for (int k = 0; k < n; ++k) {
-      const uint32_t bit = 1u << (8 * r + k);
-      const uint32_t d = (uint32_t)st->recipe_desc[rid][k] << (8 * r);
-      bool ok;
-      if (e.pairs_static_only & bit) {
-        uint64_t m = ~0ull;
-        for (int j = 0; j < n; ++j)
-          if (d >> (8 * r + j) & 1u) m &= TAB_SMASK(e.variant, TAB_RNODE(rid, j) & 7u);
-        ok = m != 0;
-      } else {
-        ok = __any_sync(WK_FULL, (here & d) == d);
-      }
-      if (ok) marks |= bit;
-    }
+  uint32_t full = 0;
+  for (uint32_t j = 0; j < e.n_vote; ++j) {
+    const uint2 pd = e.plist[j];
+    if ((here & pd.x) == pd.x) full |= pd.y;
   }
-  return marks;
+  __syncwarp();
+  return __reduce_or_sync(WK_FULL, full) | e.static_marks;
 }
 
 // Object.move_to / Plate.move_to (abstract_classes.py:21-22, world_objects.py:393-396): slot s and, for a Plate that
@@ -518,25 +538,36 @@ __device__ __forceinline__ void wk_step_env(const CzDev& T, WEnv<NA>& e, const u
   bool all_done = true, any_done = false;
 #pragma unroll
   for (int i = 0; i < A; ++i) rw[i] = 0.0;
-  for (int r = 0; r < T.R; ++r) {
-    const uint32_t before = (e.marks >> (8 * r)) & 255u;
-    const uint32_t after = (new_marks >> (8 * r)) & 255u;
-    const bool was = before & 1u, now = after & 1u;
-    const int delta = __popc(after) - __popc(before);
-    double v = 0.0;
-    v = __dadd_rn(v, __dmul_rn((double)delta, T.r_node));
-    v = __dadd_rn(v, (now && !was) ? T.r_recipe : 0.0);
-    v = __dadd_rn(v, (!now && was) ? T.r_penalty : 0.0);
-    v = __dadd_rn(v, T.r_time);
-    all_done = all_done && now;
-    any_done = any_done || now;
-    uint32_t m = relevant;  // the r-th relevant agent receives entry r of the recipe lists (cooking_env.py:250-262)
-    for (int q = 0; q < r; ++q) m &= m - 1;
-    if (m) {
-      const int who = __ffs(m) - 1;
+  if (new_marks == e.marks) {
+    // the common step: no node changed, so every recipe's reward is the idle value (bit-identical to the sum below
+    // with delta = bonus = malus = 0) and completion is read off the root bits
+    const uint32_t roots = 0x01010101u & (T.R >= 4 ? 0xFFFFFFFFu : ((1u << (8 * T.R)) - 1u));
+    all_done = (new_marks & roots) == roots;
+    any_done = (new_marks & roots) != 0;
 #pragma unroll
-      for (int i = 0; i < A; ++i)
-        if (i == who) rw[i] = v;
+    for (int i = 0; i < A; ++i)
+      if (relevant >> i & 1u) rw[i] = e.v_idle;  // entries beyond the recipe list are cleared below
+  } else {
+    for (int r = 0; r < T.R; ++r) {
+      const uint32_t before = (e.marks >> (8 * r)) & 255u;
+      const uint32_t after = (new_marks >> (8 * r)) & 255u;
+      const bool was = before & 1u, now = after & 1u;
+      const int delta = __popc(after) - __popc(before);
+      double v = 0.0;
+      v = __dadd_rn(v, __dmul_rn((double)delta, T.r_node));
+      v = __dadd_rn(v, (now && !was) ? T.r_recipe : 0.0);
+      v = __dadd_rn(v, (!now && was) ? T.r_penalty : 0.0);
+      v = __dadd_rn(v, T.r_time);
+      all_done = all_done && now;
+      any_done = any_done || now;
+      uint32_t m = relevant;  // the r-th relevant agent receives entry r of the recipe lists (cooking_env.py:250-262)
+      for (int q = 0; q < r; ++q) m &= m - 1;
+      if (m) {
+        const int who = __ffs(m) - 1;
+#pragma unroll
+        for (int i = 0; i < A; ++i)
+          if (i == who) rw[i] = v;
+      }
     }
   }
   e.marks = new_marks;
@@ -608,8 +639,8 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
   for (int i = threadIdx.x; i < (int)(head / 16); i += 32 * WK_WARPS)
     reinterpret_cast<uint4*>(bs)[i] = __ldg(reinterpret_cast<const uint4*>(T.blob) + i);
   const int stage2 = (T.stage_len + 1) >> 1;  // double2 per staging row
-  uint32_t* wwords = reinterpret_cast<uint32_t*>(smem_wk + head) + (size_t)warp * 104;  // cells[64] | skp[8] | scratch[32]
-  double2* stage = reinterpret_cast<double2*>(smem_wk + head + (size_t)WK_WARPS * 104 * 4) + (size_t)warp * NA * stage2;
+  uint32_t* wwords = reinterpret_cast<uint32_t*>(smem_wk + head) + (size_t)warp * WK_WORDS;  // cells[64] | skp[8] | plist[32] uint2
+  double2* stage = reinterpret_cast<double2*>(smem_wk + head + (size_t)WK_WARPS * WK_WORDS * 4) + (size_t)warp * NA * stage2;
   for (int k = lane; k < NA * stage2; k += 32) stage[k] = make_double2(0.0, 0.0);  // never-occupied slots stay zero
   __syncthreads();
   if (env >= n_envs) return;
@@ -626,7 +657,7 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
   e.lane = lane;
   e.cells = wwords;
   e.skp = wwords + 64;
-  uint32_t* scratch = wwords + 72;
+  e.plist = reinterpret_cast<uint2*>(wwords + 72);
   e.err = 0;
   // ---- state -> registers: lane s holds slot s; agents and the misc words are broadcast
   e.rec = lane < D ? __ldg(state + (size_t)lane * N + env) : 0u;
@@ -642,8 +673,8 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
     e.rids = __shfl_sync(WK_FULL, w, NA + CZ_ROW_RECIPES);
     e.episode = __shfl_sync(WK_FULL, w, NA + CZ_ROW_EPISODE);
   }
-  wk_variant_consts(T, e, scratch);
   wk_recipe_consts(T, e);
+  wk_variant_consts(T, e);
 
   // this lane's (observer, slot) pair(s) and table elements: constant over the launch
   const LaneSlot ls = cz_lane_slot_packed(T, lane);
@@ -682,7 +713,7 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
       e.tinfo = __ldg(src + D + NA + CZ_ROW_TINFO);
       e.variant = __ldg(src + D + NA + CZ_ROW_VARIANT);
       e.episode += 1;
-      wk_variant_consts(T, e, scratch);
+      wk_variant_consts(T, e);
       e.marks = wk_recipe_marks(T, e);
 #pragma unroll
       for (int i = 0; i < NA; ++i) rw[i] = 0.0;

@@ -88,6 +88,11 @@ class MixedAgentCookingEnv:
         obs = self._fan_out(go)
         return obs, self.reward, self.terminated, self.truncated
 
+    def wait(self):
+        """pipelined groups: order every group's observation rows before later work on the caller's stream (rewards and
+        flags are ordered by step() itself: cz_step_pipelined makes the stepping stream trail the dynamics)"""
+        self._fan_out(lambda a, g: g.wait())
+
     def heuristic_actions(self, cook_recipes=None):
         """device policy of every group -> actions u8 [N, max_agents] (padded columns 0), crashed u8 [N]"""
         crashed = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
