@@ -174,6 +174,7 @@ __host__ __device__ __forceinline__ double cz_uniform(uint64_t seed, uint64_t en
 __device__ __forceinline__ bool cz_agent_on(const CzDev& T, const EnvRegs& e, uint32_t cell) {
   // `any(agent.location == interaction_location for agent in self.agents)` (cooking_world.py:116,158)
   bool on = false;
+#pragma unroll 1
   for (int j = 0; j < T.A; ++j)
     if (A_XY(e.ag[j * OSTRIDE]) == cell) on = true;
   return on;
@@ -187,6 +188,7 @@ __device__ __forceinline__ void cz_move_obj(const CzDev& T, EnvRegs& e, uint32_t
   e.o[s * OSTRIDE] = O_WITH_XY(rec, xy);
   const SmemTabs* st = e.st;
   if ((TAB_TF(s) & TF_PLATE) && O_PCOUNT(rec)) {  // an empty plate (the common case) has nothing to carry along
+    #pragma unroll 1
     for (int k = 0; k < T.D; ++k) {
       uint32_t r = e.o[k * OSTRIDE];
       if (O_ON_PLATE(r, s)) e.o[k * OSTRIDE] = O_WITH_XY(r, xy);
@@ -196,6 +198,7 @@ __device__ __forceinline__ void cz_move_obj(const CzDev& T, EnvRegs& e, uint32_t
 
 // list.remove(obj) on the content of the static object at `cell`: later items shift down.
 __device__ __forceinline__ void cz_remove_from_static(const CzDev& T, EnvRegs& e, uint32_t cell, uint32_t pos) {
+  #pragma unroll 1
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
     if (O_IN_STATIC_AT(r, cell) && O_POS(r) > pos) e.o[k * OSTRIDE] = r - (1u << 17);
@@ -205,6 +208,7 @@ __device__ __forceinline__ void cz_remove_from_static(const CzDev& T, EnvRegs& e
 // add_content's `for c in content: c.free = False; content[-1].free = True` for a plate
 // (world_objects.py:398-406): clear the flag of everything already on plate `p`.
 __device__ __forceinline__ void cz_plate_clear_free(const CzDev& T, EnvRegs& e, uint32_t p) {
+  #pragma unroll 1
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
     if (O_ON_PLATE(r, p)) e.o[k * OSTRIDE] = r & ~O_FREE;
@@ -248,6 +252,7 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
     // ---- resolve_interaction_pick_up_special (cooking_world.py:138-154): take the last item off the one plate
     if (blocked || A_HAS(agent_rec) || n_dyn == 0 || n_plates != 1) return 0xFFu;
     int top = -1, ts = -1;
+    #pragma unroll 1
     for (int k = 0; k < T.D; ++k) {
       uint32_t r = e.o[k * OSTRIDE];
       if (O_ON_PLATE(r, plate) && (int)O_POS(r) > top) { top = O_POS(r); ts = k; }
@@ -266,6 +271,7 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
       if (!(e.sbits & SB_CUT_READY(sp))) return 0xFFu;
       for (int p = 0; p < n_content; ++p) {
         int s = -1;
+        #pragma unroll 1
         for (int k = 0; k < T.D; ++k) {
           uint32_t r = e.o[k * OSTRIDE];
           if (O_IN_STATIC_AT(r, cell) && O_POS(r) == (uint32_t)p) s = k;
@@ -281,6 +287,7 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
         if (tf & TF_SPAWN) {  // Bread.chop spawns a chopped twin (world_objects.py:738-745)
           int base = TAB_TBASE(tid), cnt = TAB_TCOUNT(tid);
           int slot = -1;
+          #pragma unroll 1
           for (int k = base; k < base + cnt; ++k)
             if (slot < 0 && !(e.o[k * OSTRIDE] & O_PRESENT)) slot = k;
           if (slot < 0) {
@@ -382,10 +389,12 @@ __device__ __forceinline__ uint32_t cz_interact(const CzDev& T, EnvRegs& e, int 
 // only containers that lost an item or gained a spawned Bread this step can be stale.
 __device__ __forceinline__ void cz_refresh_static_free(const CzDev& T, EnvRegs& e, uint32_t cell) {
   int top = -1;
+  #pragma unroll 1
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
     if (O_IN_STATIC_AT(r, cell) && (int)O_POS(r) > top) top = O_POS(r);
   }
+  #pragma unroll 1
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
     if (O_IN_STATIC_AT(r, cell))
@@ -396,10 +405,12 @@ __device__ __forceinline__ void cz_refresh_static_free(const CzDev& T, EnvRegs& 
 // The same for a plate that lost its top item (scheme1's pick-up-special).
 __device__ __forceinline__ void cz_refresh_plate_free(const CzDev& T, EnvRegs& e, uint32_t p) {
   int top = -1;
+  #pragma unroll 1
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
     if (O_ON_PLATE(r, p) && (int)O_POS(r) > top) top = O_POS(r);
   }
+  #pragma unroll 1
   for (int k = 0; k < T.D; ++k) {
     uint32_t r = e.o[k * OSTRIDE];
     if (O_ON_PLATE(r, p))
@@ -425,9 +436,12 @@ __device__ __noinline__ uint64_t cz_node_mask(const uint32_t* o, uint32_t span) 
 // Recipe.update_recipe_state as cell bitmasks (recipe.py:77-104): node mask = cells holding an
 // object of the node's type that meets its condition, ANDed with every child's mask (children
 // come later in node_list, so the list is walked back to front).
+// Out of line and by value (the environment view stays in registers): one copy of the unrolled node walk serves the
+// step, the auto-reset and the reset kernels; the dynamics are instruction-fetch bound, code size is the budget.
 template <bool FAST>
-__device__ __forceinline__ uint32_t cz_recipe_marks(const CzDev& T, const EnvRegs& e, uint32_t rid) {
-  const SmemTabs* st = e.st;
+__device__ __noinline__ uint32_t cz_recipe_marks_of(const CzDev& T, const uint32_t* eo, const SmemTabs* st, uint32_t variant,
+                                                    uint32_t rid) {
+  struct { const uint32_t* o; uint32_t variant; } e = {eo, variant};
   uint64_t m[CZ_MAX_NODES];
   const int n = TAB_RLEN(rid);
   uint32_t marks = 0;
@@ -449,6 +463,10 @@ __device__ __forceinline__ uint32_t cz_recipe_marks(const CzDev& T, const EnvReg
   }
   return marks;
 }
+template <bool FAST>
+__device__ __forceinline__ uint32_t cz_recipe_marks(const CzDev& T, const EnvRegs& e, uint32_t rid) {
+  return cz_recipe_marks_of<FAST>(T, e.o, e.st, e.variant, rid);
+}
 
 // CookingEnvironment.accumulated_step (cooking_env.py:243-269) for one environment.
 // Writes reward f64[A], terminated u8[A], truncated u8[A] of this environment.
@@ -468,6 +486,7 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
   // ---- action_scheme3.perform_agent_actions (action_scheme3.py:4-16)
   // per agent, 8 bits each: apack = action after checks, fpack = faced cell, epack = end cell | 0x40 walkable
   uint32_t apack = 0, fpack = 0, epack = 0x80808080u;
+#pragma unroll 1
   for (int i = 0; i < A; ++i) {
     if (!(active >> i & 1u)) continue;
     uint32_t ai = (act_packed >> (8 * i)) & 255u;
@@ -500,12 +519,16 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
       if (j != i && !(ej & 0x80u) && (ej & 63u) == (ei & 63u)) cancel |= 1u << i;
     }
   }
-  // sequential resolution in agent order (action_scheme3.py:15-34)
+  // sequential resolution in agent order (action_scheme3.py:15-34).  The loop stays rolled and cz_interact has ONE
+  // call site: the dynamics are bound by instruction fetch (profiles/r02_notes.md), so code size is the budget.
   uint32_t pressed = 0, dirty = 0xFFFFFFFFu, dirty_plate = 0xFFFFFFFFu;
+#pragma unroll 1
   for (int i = 0; i < A; ++i) {
     if (!(active >> i & 1u)) continue;
     uint32_t rec = e.ag[i * OSTRIDE];
-    uint32_t ai = (cancel >> i & 1u) ? 0u : ((apack >> (8 * i)) & 255u);
+    const uint32_t ai = (cancel >> i & 1u) ? 0u : ((apack >> (8 * i)) & 255u);
+    uint32_t cell = 0, mode = 0;
+    bool interact = false;
     if (scheme1) {
       if (ai == 0u) continue;  // scheme1: only walk actions walk (action_scheme1.py:16-19), a no-op does nothing
       if (ai >= 5u) {          // interact with the cell the agent faces (cooking_world.py:115,139,157)
@@ -515,28 +538,32 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
           if (ai != 6u) e.err |= CZ_ERR_OFFGRID;
           continue;
         }
-        const uint32_t cell = (uint32_t)(fx | fy << 3);
-        bool stale = false;
-        const uint32_t p = cz_interact<FAST>(T, e, i, cell, ai, stale);
-        if (stale) dirty = (dirty & ~(0xFFu << (8 * i))) | (cell << (8 * i));
-        dirty_plate = (dirty_plate & ~(0xFFu << (8 * i))) | (p << (8 * i));
-        continue;
+        cell = (uint32_t)(fx | fy << 3);
+        mode = ai;
+        interact = true;
       }
     }
-    uint32_t tgt = ai ? ((fpack >> (8 * i)) & 63u) : A_XY(rec);
-    if (cz_walkable<FAST>(T, e, tgt)) {  // resolve_walking_action (:26-34)
-      rec = (rec & ~63u) | tgt;
-      e.ag[i * OSTRIDE] = rec;
-      if (A_HAS(rec)) cz_move_obj<FAST>(T, e, A_HOLD(rec), tgt);  // Agent.move_to (world_objects.py:793-796)
-      uint32_t g = TAB_GRID(e.variant, tgt);
-      if ((g & 15u) == ST_SWITCH) {  // Switch.add_content (:159-163)
-        e.sbits ^= SB_SW_ACTIVE(g >> 4);
-        pressed |= 1u << (g >> 4);
+    if (!interact) {
+      const uint32_t tgt = ai ? ((fpack >> (8 * i)) & 63u) : A_XY(rec);
+      if (cz_walkable<FAST>(T, e, tgt)) {  // resolve_walking_action (:26-34)
+        rec = (rec & ~63u) | tgt;
+        e.ag[i * OSTRIDE] = rec;
+        if (A_HAS(rec)) cz_move_obj<FAST>(T, e, A_HOLD(rec), tgt);  // Agent.move_to (world_objects.py:793-796)
+        uint32_t g = TAB_GRID(e.variant, tgt);
+        if ((g & 15u) == ST_SWITCH) {  // Switch.add_content (:159-163)
+          e.sbits ^= SB_SW_ACTIVE(g >> 4);
+          pressed |= 1u << (g >> 4);
+        }
+      } else if (ai && !scheme1) {
+        cell = tgt;
+        interact = true;
       }
-    } else if (ai && !scheme1) {
+    }
+    if (interact) {
       bool stale = false;
-      cz_interact<FAST>(T, e, i, tgt, 0u, stale);
-      if (stale) dirty = (dirty & ~(0xFFu << (8 * i))) | (tgt << (8 * i));
+      const uint32_t p = cz_interact<FAST>(T, e, i, cell, mode, stale);  // p != 0xFF only for scheme1's pick-up-special
+      if (stale) dirty = (dirty & ~(0xFFu << (8 * i))) | (cell << (8 * i));
+      dirty_plate = (dirty_plate & ~(0xFFu << (8 * i))) | (p << (8 * i));
     }
   }
 
@@ -548,6 +575,7 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
       if (cell == 0xFFu) continue;
       int n = 0;
       bool all_mashed = true;
+      #pragma unroll 1
       for (int s = 0; s < T.D; ++s) {
         uint32_t r = e.o[s * OSTRIDE];
         if (!O_IN_STATIC_AT(r, cell)) continue;
@@ -641,6 +669,7 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
   // agent i is the k-th relevant agent and receives entry k of the recipe lists (:250-262)
   uint32_t new_marks = 0;
   bool all_done = true, any_done = false;
+#pragma unroll 1
   for (int r = 0; r < T.R; ++r) {
     uint32_t rid = (e.rids >> (8 * r)) & 255u;
     uint32_t before = (e.marks >> (8 * r)) & 255u;
@@ -657,6 +686,7 @@ __device__ __forceinline__ void cz_step_env(const CzDev& T, EnvRegs& e, const ui
     any_done = any_done || now;
     // which agent is the r-th relevant one?
     uint32_t m = relevant;
+#pragma unroll 1
     for (int q = 0; q < r; ++q) m &= m - 1;
     if (m) reward[__ffs(m) - 1] = v;
   }

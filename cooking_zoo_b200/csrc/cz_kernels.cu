@@ -416,6 +416,7 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
         e.variant = __ldg(src + D + A + CZ_ROW_VARIANT);
         e.episode += 1;
         uint32_t marks = 0;
+#pragma unroll 1
         for (int r = 0; r < T.R; ++r) marks |= cz_recipe_marks<FAST>(T, e, (e.rids >> (8 * r)) & 255u) << (8 * r);
         e.marks = marks;
         if (MODE == MODE_STEP) {
@@ -700,6 +701,7 @@ struct cz_tables {
   int two_kernel_min_envs;  // in-place step of at least this many environments: dynamics kernel, then the row-writer kernel
   int warp_max_envs;        // single in-place step of at most this many environments: warp-per-environment kernel (cz_warp.cuh)
   int warp_k_max_envs;      // k_steps > 1 with at most this many environments: one persistent launch of that kernel
+  int warp_group;           // lanes per environment in that kernel: 16 (two environments per warp) or 32
   uint8_t* d_rand;          // scratch for device-generated actions outside the warp kernel
   int rand_envs;
   int num_sms;
@@ -927,6 +929,9 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     t->warp_max_envs = w ? atoi(w) : 8192;
     const char* wk = getenv("CZ_WARP_K_MAX_ENVS");
     t->warp_k_max_envs = wk ? atoi(wk) : 32768;
+    const char* wg = getenv("CZ_WARP_GROUP");  // 16 or 32 lanes per environment in the warp kernel (default: 16 when D <= 16)
+    t->warp_group = T.D <= 16 ? 16 : 32;
+    if (wg && atoi(wg) == 32) t->warp_group = 32;
   }
 #define SET_SMEM(K) CZ_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin))
 #define SET_MODE(M)                                                                                    \
@@ -940,7 +945,8 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   SET_SMEM((cz_env_kernel<M, OBS_NONE, 3>)); SET_SMEM((cz_env_kernel<M, OBS_NONE, 4>))
   SET_MODE(MODE_STEP); SET_MODE(MODE_RESET); SET_MODE(MODE_OBSERVE);
   SET_SMEM(cz_obs32_kernel);
-  SET_SMEM(cz_warp_kernel<1>); SET_SMEM(cz_warp_kernel<2>); SET_SMEM(cz_warp_kernel<3>); SET_SMEM(cz_warp_kernel<4>);
+  SET_SMEM((cz_warp_kernel<1, 16>)); SET_SMEM((cz_warp_kernel<2, 16>)); SET_SMEM((cz_warp_kernel<3, 16>)); SET_SMEM((cz_warp_kernel<4, 16>));
+  SET_SMEM((cz_warp_kernel<1, 32>)); SET_SMEM((cz_warp_kernel<2, 32>)); SET_SMEM((cz_warp_kernel<3, 32>)); SET_SMEM((cz_warp_kernel<4, 32>));
 #undef SET_MODE
 #undef SET_SMEM
   *out = t;
@@ -1126,12 +1132,19 @@ static int cz_launch_warp(const cz_tables* t, uint32_t* state, const uint8_t* ac
                           uint64_t seed, int64_t env_offset, uint64_t action_step, void* stream) {
   if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
   const CzDev& T = t->dev;
-  const int blocks = (n_envs + WK_WARPS - 1) / WK_WARPS;
-  const size_t smem = cz_block_smem_head(T.V) + (size_t)WK_WARPS * WK_WORDS * 4 + (size_t)WK_WARPS * T.A * ((T.stage_len + 1) / 2) * 16;
+  // two environments per warp (16-lane groups) when every dynamic slot finds a lane in half a warp
+  const int G = t->warp_group;
+  const int groups = WK_WARPS * 32 / G;
+  const int blocks = (n_envs + groups - 1) / groups;
+  const size_t smem = wk_smem_bytes(T.V, T.A, T.stage_len, G);
   cudaStream_t s = (cudaStream_t)stream;
-#define CZ_WARP_GO(NA)                                                                                                     \
-  cz_warp_kernel<NA><<<blocks, 32 * WK_WARPS, smem, s>>>(t->dev, state, actions, obs, reward, terminated, truncated, error_flags, \
-                                                         n_envs, k_steps, flags, seed, env_offset, action_step, t->simple2)
+#define CZ_WARP_GO(NA)                                                                                                          \
+  if (G == 16)                                                                                                                 \
+    cz_warp_kernel<NA, 16><<<blocks, 32 * WK_WARPS, smem, s>>>(t->dev, state, actions, obs, reward, terminated, truncated,      \
+                                                               error_flags, n_envs, k_steps, flags, seed, env_offset, action_step); \
+  else                                                                                                                         \
+    cz_warp_kernel<NA, 32><<<blocks, 32 * WK_WARPS, smem, s>>>(t->dev, state, actions, obs, reward, terminated, truncated,      \
+                                                               error_flags, n_envs, k_steps, flags, seed, env_offset, action_step)
   switch (T.A) {
     case 1: CZ_WARP_GO(1); break;
     case 2: CZ_WARP_GO(2); break;

@@ -1,6 +1,7 @@
 """The reference's env wrappers re-exposed over the batched CUDA backend.
 
 Same constructor arguments and return shapes as
+  cooking_env.env                     (environment/cooking_env.py:26-43; the PettingZoo AEC surface; id cookingZooEnv-v0),
   cooking_env.parallel_env            (environment/cooking_env.py:26-46; dicts keyed "player_i"),
   environment.GymCookingEnvironment   (environment/environment.py:10-31; id cookingEnv-v1),
   multi_agent_gym.GymCookingEnvironment (environment/multi_agent_gym.py:10-34; id cookingEnvMA-v1),
@@ -94,6 +95,7 @@ class ParallelCookingEnv:
             lid = self._b.lib.cz_layout_draw(self._b.seed, self._b.env_offset, self._episode) % self._b.tables.num_layouts
         self._episode += 1
         obs = self._b.reset(layout_ids=np.array([lid], np.int32)).cpu().numpy()[0]
+        self._obs_all = obs
         self.agents = self.possible_agents[:]
         self._done = False
         self._termination_info = ""
@@ -114,6 +116,7 @@ class ParallelCookingEnv:
             act[0, i] = int(actions.get(a, 0))
         obs, rew, term, trunc, info = self._b.step(act)
         obs, rew = obs.cpu().numpy()[0], rew.cpu().numpy()[0]
+        self._obs_all = obs
         term, trunc = term.cpu().numpy()[0].astype(bool), trunc.cpu().numpy()[0].astype(bool)
         full = self._b.info()
         t = int(full["t"][0])
@@ -152,6 +155,130 @@ class ParallelCookingEnv:
 def parallel_env(**kwargs):
     """cooking_env.parallel_env (cooking_env.py:46)."""
     return ParallelCookingEnv(**kwargs)
+
+
+class _Selector:
+    """pettingzoo's agent_selector as the reference uses it (cooking_env.py:135-136, 189-190, 268): next() hands out the
+    agents round-robin, is_last() says whether the agent handed out last closes the round."""
+
+    def __init__(self, order):
+        self.order, self.pos, self.selected = list(order), 0, None
+
+    def next(self):
+        self.selected = self.order[self.pos]
+        self.pos = (self.pos + 1) % len(self.order)
+        return self.selected
+
+    def is_last(self):
+        return self.selected == self.order[-1]
+
+
+class AECCookingEnv:
+    """The PettingZoo AEC surface of the reference (`cooking_env.env(...)`, cooking_env.py:26-43; AEC step :215-241):
+    `agent_selection`, `last()`, one `step(action)` per selected agent; the world advances when the last agent of the
+    round has stepped.  Same constructor arguments as the reference's factory.  Backed by one environment of the batched
+    CUDA path; the batched entry point is the fast path, this surface is for drop-in compatibility.
+
+    Reference behaviour kept on purpose (pinned by tests/golden/aec/aec_cfg2.npz, recorded from the reference):
+    * the stepping agent's cumulative reward is NOT what gets cleared after a call: the loop variable of :228 shadows it,
+      so the LAST agent of the round is cleared on every call and the others keep accumulating over the episode;
+    * after an episode ends the dead-agent round cannot make progress: step() on a finished
+      agent raises like pettingzoo's `_was_dead_step`; call reset()."""
+
+    metadata = {"render_modes": [], "name": "cookingzoo_v1", "is_parallelizable": True}
+
+    def __init__(self, level, meta_file, num_agents, max_steps, recipes, agent_visualization=None, obs_spaces=None,
+                 end_condition_all_dishes=False, action_scheme="scheme1", render=False, reward_scheme=None,
+                 agent_respawn_rate=0.0, grace_period=20, agent_despawn_rate=0.0, **backend_kwargs):
+        self._par = ParallelCookingEnv(level, meta_file, num_agents, max_steps, recipes, agent_visualization, obs_spaces,
+                                       end_condition_all_dishes, action_scheme, render, reward_scheme, agent_respawn_rate,
+                                       grace_period, agent_despawn_rate, **backend_kwargs)
+        self.possible_agents = list(self._par.possible_agents)
+        self.observation_spaces, self.action_spaces = self._par.observation_spaces, self._par.action_spaces
+        self.agents = []
+
+    def observation_space(self, agent):
+        return self.observation_spaces[agent]
+
+    def action_space(self, agent):
+        return self.action_spaces[agent]
+
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def num_agents(self):
+        return len(self.agents)
+
+    @property
+    def backend(self):
+        return self._par.backend
+
+    def reset(self, seed=None, return_info=False, options=None):
+        self._par.reset(seed=seed, options=options)
+        self.agents = self.possible_agents[:]
+        self._selector = _Selector(self.agents)
+        self.agent_selection = self._selector.next()
+        self.rewards = {a: 0 for a in self.agents}
+        self._cumulative_rewards = {a: 0 for a in self.agents}
+        self.terminations = {a: False for a in self.agents}
+        self.truncations = {a: False for a in self.agents}
+        self.infos = {a: {} for a in self.agents}
+        self._pending = []
+
+    def observe(self, agent):
+        return self._par._obs_all[self.possible_agents.index(agent)].copy()
+
+    def last(self, observe=True):
+        a = self.agent_selection
+        return (self.observe(a) if observe else None, self._cumulative_rewards[a], self.terminations[a],
+                self.truncations[a], self.infos[a])
+
+    def agent_iter(self, max_iter=2 ** 63):
+        it = 0
+        while self.agents and it < max_iter:
+            it += 1
+            yield self.agent_selection
+
+    def step(self, action):
+        if action is None:
+            return          # :216-224: only meaningful right after a despawn / respawn; nothing to do otherwise (C-8)
+        sel = self.agent_selection
+        if self.terminations[sel] or self.truncations[sel]:
+            raise ValueError("when an agent is dead, the only valid action is None")
+        self._pending.append(int(action))
+        for a in self.agents:
+            self.rewards[a] = 0
+        closing = self.agents[-1]      # what the reference's shadowed loop variable holds from here on (:228)
+        if self._selector.is_last():
+            acts = dict(zip(self.agents, self._pending))
+            self._pending = []
+            obs, rew, term, trunc, infos = self._par.step(acts)
+            self.rewards, self.terminations, self.truncations, self.infos = {}, {}, {}, {}
+            for a in self.possible_agents:
+                if a not in rew:
+                    continue
+                self.rewards[a] = rew[a]
+                self.terminations[a], self.truncations[a], self.infos[a] = term[a], trunc[a], infos[a]
+                self._cumulative_rewards[a] = self._cumulative_rewards.get(a, 0) + rew[a]
+            self.agents = [a for a in self.possible_agents if a in rew]
+            self._selector = _Selector(self.agents)
+            for a in self.agents:
+                if self.terminations[a] or self.truncations[a]:
+                    self.agent_selection = a
+                    self._cumulative_rewards[closing] = 0
+                    return
+        self.agent_selection = self._selector.next()
+        self._cumulative_rewards[closing] = 0
+
+    def close(self):
+        self._par.close()
+
+
+def env(**kwargs):
+    """cooking_env.env (cooking_env.py:26-43)."""
+    return AECCookingEnv(**kwargs)
 
 
 class GymCookingEnvironment:
@@ -213,9 +340,13 @@ class GymCookingEnvironmentMA:
         self.zoo_env.close()
 
 
-if _gym is not None:  # pragma: no cover - ids of cooking_zoo/__init__.py:3-8
-    for _id, _ep in (("cookingEnv-v1", "cooking_zoo_b200.wrappers:GymCookingEnvironment"),
-                     ("cookingEnvMA-v1", "cooking_zoo_b200.wrappers:GymCookingEnvironmentMA")):
+# ids of cooking_zoo/__init__.py:3-8 -> entry points here (registered with gymnasium when it is installed)
+ENV_IDS = {"cookingEnv-v1": "cooking_zoo_b200.wrappers:GymCookingEnvironment",
+           "cookingEnvMA-v1": "cooking_zoo_b200.wrappers:GymCookingEnvironmentMA",
+           "cookingZooEnv-v0": "cooking_zoo_b200.wrappers:AECCookingEnv"}
+
+if _gym is not None:  # pragma: no cover
+    for _id, _ep in ENV_IDS.items():
         try:
             _gym.envs.registration.register(id=_id, entry_point=_ep)
         except Exception:

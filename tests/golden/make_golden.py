@@ -318,6 +318,74 @@ def main_error_bits():
     save("err_switch_link", cfg, record(cfg, [0], 2, pol, tele), 2)
 
 
+def main_aec():
+    """The PettingZoo AEC surface of the reference (cooking_env.py:26-43, 215-241: agent_selection, last(), per-agent
+    step) recorded call by call: for every step() call the selected agent, what last() returned before it (observation,
+    cumulative reward, terminated, truncated, info scalars) and the action passed.  Quirks this pins: the loop variable
+    of :228 shadows `agent`, so the LAST agent's cumulative reward is zeroed on every call and the others' are never
+    reset.  One file, two traces (uniform actions; the reference's own cooks, which finish a recipe)."""
+    import random as _random
+    from oracle.ref_harness import load_reference
+    from oracle import ref_dump
+    ce = load_reference()
+    cfg = {"level": "coop_test", "meta_file": "example", "max_steps": 60, "reward_scheme": None, "num_agents": 2,
+           "recipes": ["TomatoLettuceSalad", "CarrotBanana"], "end_all": False, "action_scheme": "scheme3"}
+    traces = []
+    for seed, pol in ((1500, uniform), (1501, Heuristic(0.05))):
+        _random.seed(seed)
+        np.random.seed(seed)
+        env = ce.CookingEnvironment(level=cfg["level"], meta_file=cfg["meta_file"], num_agents=2, max_steps=cfg["max_steps"],
+                                    recipes=cfg["recipes"], obs_spaces=["feature_vector"] * 2,
+                                    end_condition_all_dishes=False, action_scheme="scheme3")
+        env.reset()
+
+        class _Shim:          # Heuristic.bind expects the RefEnv wrapper
+            pass
+        shim = _Shim()
+        shim.env = env
+        if hasattr(pol, "bind"):
+            pol.bind(shim, cfg)
+        rng = np.random.default_rng(seed)
+        layout = ref_dump.describe_layout(env)
+        calls = {"agent": [], "obs": [], "cum": [], "term": [], "trunc": [], "info_t": [], "info_done": [], "action": []}
+        prev = np.zeros(2, np.int64)
+        t = 0
+        while True:
+            act = pol(rng, t, 2, prev)
+            prev = act
+            t += 1
+            finished = False
+            for _ in range(len(env.agents)):
+                name = env.agent_selection
+                i = env.possible_agents.index(name)
+                obs, cum, term, trunc, info = env.last()
+                calls["agent"].append(i); calls["obs"].append(np.asarray(obs, np.float64)); calls["cum"].append(float(cum))
+                calls["term"].append(int(term)); calls["trunc"].append(int(trunc))
+                calls["info_t"].append(int(info.get("t", -1))); calls["info_done"].append(int(info.get("recipe_done", -1)))
+                if term or trunc:
+                    finished = True      # quirk C-8: the dead-agent loop cannot make progress; the trace ends here
+                    calls["action"].append(-1)
+                    break
+                calls["action"].append(int(act[i]))
+                env.step(int(act[i]))
+            if finished:
+                break
+        traces.append((layout, {k: np.asarray(v) for k, v in calls.items()}))
+    n = max(len(c["agent"]) for _, c in traces)
+    out = {"config": np.array(json.dumps(cfg)), "layouts": np.array(json.dumps([l for l, _ in traces])),
+           "n_calls": np.array([len(c["agent"]) for _, c in traces], np.int32)}
+    for k in traces[0][1]:
+        first = traces[0][1][k]
+        arr = np.zeros((len(traces), n) + first.shape[1:], first.dtype)
+        for j, (_, c) in enumerate(traces):
+            arr[j, :len(c[k])] = c[k]
+        out[k] = arr
+    path = os.path.join(OUT, "aec", "aec_cfg2.npz")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    np.savez_compressed(path, **out)
+    print("aec_cfg2:", out["n_calls"].tolist(), "calls", os.path.getsize(path) // 1024, "KiB")
+
+
 def _script(steps, A):
     """steps: list of (teleports {agent: (x, y)}, actions [A]) -> (scripted policy, teleports by step)"""
     tele = {t: tp for t, (tp, _) in enumerate(steps) if tp}
@@ -372,6 +440,8 @@ def main():
         return main_kat()
     if sys.argv[1:] == ["error_bits"]:
         return main_error_bits()
+    if sys.argv[1:] == ["aec"]:
+        return main_aec()
     if sys.argv[1:] == ["policy"]:
         return main_policy()
     if sys.argv[1:] == ["custom"]:
@@ -451,6 +521,7 @@ def main():
     main_errors()
     main_kat()
     main_error_bits()
+    main_aec()
 
 
 if __name__ == "__main__":

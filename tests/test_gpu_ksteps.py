@@ -59,12 +59,19 @@ def _sticky_actions(K, n, A, n_act, seed):
     return torch.from_numpy(out).cuda()
 
 
+@pytest.mark.parametrize("group", ["auto", "32"])
 @pytest.mark.parametrize("case", list(CASES))
-def test_k_steps_in_one_launch_equal_k_single_steps(case, monkeypatch):
+def test_k_steps_in_one_launch_equal_k_single_steps(case, group, monkeypatch):
+    """group: lanes per environment in the warp kernel — auto = 16 (two environments per warp) when the tables have at
+    most 16 dynamic slots, 32 otherwise; "32" forces one environment per warp"""
     K, rounds = 16, 5           # 80 steps: several auto-resets at these max_steps
     monkeypatch.setenv("CZ_WARP_MAX_ENVS", "0")          # reference arm of this test: the lane-per-environment kernels
     lane = _make(case)
     monkeypatch.delenv("CZ_WARP_MAX_ENVS")
+    if group == "32":
+        if lane.tables.num_dyn_slots > 16:
+            pytest.skip("already one environment per warp")
+        monkeypatch.setenv("CZ_WARP_GROUP", "32")
     warp = _make(case)
     assert torch.equal(lane.state, warp.state) and torch.equal(lane.obs.view(torch.int64), warp.obs.view(torch.int64))
     n, A = lane.num_envs, lane.num_agents

@@ -58,7 +58,10 @@ def test_cuda_replays_golden(path, kernel, monkeypatch):
             assert np.array_equal(g["trunc"][k, t], trunc[k]), ctx
             assert_state_equal({key: g[key][k, t + 1] for key in STATE_KEYS}, states[k], ctx)
             assert_obs_equal(g["obs"][k, t + 1], obs[k], ctx)
-    assert int(env.error_flags.abs().sum()) == 0
+    # traces that end where the reference itself raised (Appendix C-9 fixtures) keep stepping past that point here and
+    # are flagged, as they must be (tests/test_error_contract.py); every other trace stays clean
+    clean = torch.from_numpy(np.asarray(g.get("raised", -np.ones(n)), np.int64) < 0).cuda()
+    assert int(env.error_flags[clean].abs().sum()) == 0
 
 
 def _oracle_lockstep(n_envs, check, steps, A, recipes, seed, max_steps=400, end_all=True, level="coop_test", meta="example"):

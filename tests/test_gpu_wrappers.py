@@ -111,3 +111,60 @@ def test_symbolic_observation_rebuilt_from_device_state_matches_the_oracle_world
                 assert (r.holding is None) == (ag.holding is None)
                 if ag.holding is not None:
                     assert (r.holding.name, r.holding.location) == (ag.holding.type, (ag.holding.x, ag.holding.y))
+
+
+def test_aec_surface_replays_the_reference_trace_call_by_call():
+    """cooking_env.env(...): agent_selection / last() / per-agent step against tests/golden/aec/aec_cfg2.npz, recorded
+    from the unmodified reference (make_golden.py aec), including the cumulative-reward quirk of cooking_env.py:228"""
+    import json
+    from cooking_zoo_b200.wrappers import env as make_env, ENV_IDS
+    z = np.load(os.path.join(ROOT, "tests", "golden", "aec", "aec_cfg2.npz"))
+    cfg, layouts = json.loads(str(z["config"])), json.loads(str(z["layouts"]))
+    assert ENV_IDS["cookingZooEnv-v0"].endswith("AECCookingEnv")
+    for k in range(len(layouts)):
+        aec = make_env(level=cfg["level"], meta_file=cfg["meta_file"], num_agents=2, max_steps=cfg["max_steps"],
+                       recipes=cfg["recipes"], obs_spaces=["feature_vector"] * 2, end_condition_all_dishes=cfg["end_all"],
+                       action_scheme=cfg["action_scheme"], layouts=[layouts[k]])
+        aec.reset(options={"layout_id": 0})
+        n = int(z["n_calls"][k])
+        for c in range(n):
+            assert aec.agent_selection == f"player_{int(z['agent'][k, c])}", (k, c)
+            obs, cum, term, trunc, info = aec.last()
+            assert np.array_equal(bits(z["obs"][k, c]), bits(obs)), (k, c)
+            assert bits(float(cum)) == bits(z["cum"][k, c]), (k, c, cum)
+            assert (int(term), int(trunc)) == (int(z["term"][k, c]), int(z["trunc"][k, c])), (k, c)
+            assert info.get("t", -1) == z["info_t"][k, c] and int(info.get("recipe_done", -1)) == z["info_done"][k, c]
+            if z["action"][k, c] < 0:
+                with pytest.raises(ValueError):
+                    aec.step(0)
+                aec.step(None)                      # C-8: a no-op, the round cannot make progress
+                assert c == n - 1
+            else:
+                aec.step(int(z["action"][k, c]))
+        aec.close()
+
+
+def test_parallel_env_with_despawn_and_respawn_follows_the_reference_agents_list():
+    """an agent that despawns leaves `agents` (truncated on that step) and the episode goes on for the others
+    (cooking_env.py:262-266); replayed against spawn_cfg2.npz (rel = the agents present in the reference's dicts)"""
+    from cooking_zoo_b200.wrappers import parallel_env
+    g = load_golden(os.path.join(ROOT, "tests", "golden", "spawn_cfg2.npz"))
+    cfg, sp = g["config"], g["config"]["spawn"]
+    seen_partial = False
+    for n in range(4):
+        env = parallel_env(num_agents=2, agent_respawn_rate=sp["respawn"], agent_despawn_rate=sp["despawn"],
+                           grace_period=sp["grace"], seed=sp["seed"], env_offset=n, **_kw(cfg, [g["layouts"][n]]))
+        env.reset(options={"layout_id": 0})
+        for t in range(int(g["length"][n])):
+            obs, rew, term, trunc, infos = env.step({f"player_{i}": int(g["actions"][n, t, i]) for i in range(2)})
+            rel = [f"player_{i}" for i in range(2) if g["rel"][n, t, i]]
+            assert sorted(obs) == rel and sorted(rew) == rel and env.agents == rel, (n, t)
+            seen_partial |= len(rel) == 1
+            for i in range(2):
+                a = f"player_{i}"
+                if a in rel:
+                    assert np.array_equal(bits(g["obs"][n, t + 1, i]), bits(obs[a])) and bits(rew[a]) == bits(g["reward"][n, t, i])
+                    assert term[a] == bool(g["term"][n, t, i]) and trunc[a] == bool(g["trunc"][n, t, i])
+                    assert infos[a]["termination_info"] == ""
+        env.close()
+    assert seen_partial
