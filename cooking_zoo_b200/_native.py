@@ -36,7 +36,7 @@ class TableDesc(C.Structure):
                 + [(n, _P) for n in ("xlut", "ylut", "grid", "static_cells", "scan_order", "special_cells",
                                      "static_masks", "slot_type", "type_flags", "type_base", "type_count",
                                      "comp_slots", "obs_table", "recipe_nodes", "recipe_len", "pool", "default_recipes",
-                                     "spawn_x", "spawn_y", "spawn_n")])
+                                     "spawn_x", "spawn_y", "spawn_n", "layout_cum")])
 
 
 class PolicyDesc(C.Structure):
@@ -50,6 +50,7 @@ SIGNATURES = {
     "cz_last_error": (C.c_char_p, []),
     "cz_launch_count": (C.c_uint64, []),
     "cz_layout_draw": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint64]),
+    "cz_layout_index": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64]),
     "cz_spawn_uniform": (C.c_double, [C.c_uint64] * 5),
     "cz_tables_create": (C.c_int, [C.POINTER(TableDesc), C.c_int, C.POINTER(_P)]),
     "cz_tables_destroy": (C.c_int, [_P]),
@@ -135,6 +136,11 @@ def make_desc(t):
         arr = np.ascontiguousarray(getattr(t, name), dtype=dtype)
         keep.append(arr)
         setattr(d, name, arr.ctypes.data)
+    d.layout_cum = None
+    if getattr(t, "layout_cum", None) is not None:
+        arr = np.ascontiguousarray(t.layout_cum, dtype=np.uint64)
+        keep.append(arr)
+        d.layout_cum = arr.ctypes.data
     return d, keep
 
 

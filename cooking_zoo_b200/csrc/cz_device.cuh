@@ -44,6 +44,7 @@ struct CzDev {
   const float* xlut32;       // the same tables rounded to float32 once on the host (float32 observation rows)
   const float* ylut32;
   const float* obs_table32;
+  const uint64_t* layout_cum;  // weighted layout pool: cumulative probabilities * 2^64, or nullptr (uniform pool)
   const void* blob;  // BlockSmem image (LUTs + SmemTabs), built by cz_tables_create
 };
 
@@ -148,6 +149,23 @@ __device__ __forceinline__ uint64_t cz_mix(uint64_t seed, uint64_t env, uint64_t
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
+}
+
+// Pool index selected by a 64-bit draw: first layout whose cumulative threshold exceeds it (weighted pool: the exact
+// distribution of the reference's level parser), or draw % P (uniform pool).  Host twin: cz_layout_index.
+__host__ __device__ __forceinline__ int cz_pick_layout(const uint64_t* cum, int P, uint64_t u) {
+  if (!cum) return (int)(u % (uint64_t)P);
+  int lo = 0, hi = P - 1;  // cum[P - 1] = 2^64 - 1 >= u: the answer exists
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+#ifdef __CUDA_ARCH__
+    const uint64_t c = __ldg(cum + mid);
+#else
+    const uint64_t c = cum[mid];
+#endif
+    if (c > u) hi = mid; else lo = mid + 1;
+  }
+  return lo;
 }
 
 template <bool FAST>

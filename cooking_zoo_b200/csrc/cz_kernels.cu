@@ -402,7 +402,7 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
       } else if (MODE == MODE_STEP) {
         if ((flags & CZ_STEP_AUTO_RESET) && (e.tinfo & TI_DONE)) {
           do_reset = true;
-          layout = (int)(cz_mix(seed, (uint64_t)(env_offset + env), (uint64_t)e.episode) % (uint64_t)T.P);
+          layout = cz_pick_layout(T.layout_cum, T.P, cz_mix(seed, (uint64_t)(env_offset + env), (uint64_t)e.episode));
         }
       }
 
@@ -702,6 +702,7 @@ struct cz_tables {
   int warp_max_envs;        // single in-place step of at most this many environments: warp-per-environment kernel (cz_warp.cuh)
   int warp_k_max_envs;      // k_steps > 1 with at most this many environments: one persistent launch of that kernel
   int warp_group;           // lanes per environment in that kernel: 16 (two environments per warp) or 32
+  uint64_t* h_layout_cum;   // host copy of the weighted pool's thresholds (cz_layout_index), or nullptr
   uint8_t* d_rand;          // scratch for device-generated actions outside the warp kernel
   int rand_envs;
   int num_sms;
@@ -749,6 +750,11 @@ extern "C" uint64_t cz_layout_draw(uint64_t seed, uint64_t env, uint64_t episode
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
+}
+
+extern "C" int cz_layout_index(const cz_tables* t, uint64_t seed, uint64_t env, uint64_t episode) {
+  if (!t) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  return cz_pick_layout(t->h_layout_cum, t->dev.P, cz_layout_draw(seed, env, episode));
 }
 
 extern "C" double cz_spawn_uniform(uint64_t seed, uint64_t env, uint64_t episode, uint64_t t, uint64_t c) {
@@ -853,6 +859,16 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     }
   UP(recipe_spans, spans, (size_t)T.B * CZ_MAX_NODES);
   UP(pool, d->pool, (size_t)T.P * T.rows);
+  T.layout_cum = nullptr;
+  if (d->layout_cum && rc == CZ_OK) {
+    if (d->layout_cum[T.P - 1] != ~0ull) { cz_tables_destroy(t); return cz_fail(CZ_EINVAL, "%s", "layout_cum must end at 2^64 - 1"); }
+    for (int i = 1; i < T.P; ++i)
+      if (d->layout_cum[i] < d->layout_cum[i - 1]) { cz_tables_destroy(t); return cz_fail(CZ_EINVAL, "%s", "layout_cum must not decrease"); }
+    UP(layout_cum, d->layout_cum, T.P);
+    t->h_layout_cum = new (std::nothrow) uint64_t[T.P];
+    if (!t->h_layout_cum) { cz_tables_destroy(t); return cz_fail(CZ_EINVAL, "%s", "out of host memory"); }
+    memcpy(t->h_layout_cum, d->layout_cum, (size_t)T.P * sizeof(uint64_t));
+  }
   UP(default_recipes, d->default_recipes, T.R);
   UP(spawn_x, d->spawn_x, (size_t)T.A * 8);
   UP(spawn_y, d->spawn_y, (size_t)T.A * 8);
@@ -963,6 +979,7 @@ extern "C" int cz_tables_destroy(cz_tables* t) {
   if (t->d_term) cudaFree(t->d_term);
   if (t->d_trunc) cudaFree(t->d_trunc);
   if (t->d_rand) cudaFree(t->d_rand);
+  delete[] t->h_layout_cum;
   if (t->pipe_ready) {
     cudaStreamDestroy(t->pipe_dyn); cudaStreamDestroy(t->pipe_obs);
     cudaEventDestroy(t->ev_user); cudaEventDestroy(t->ev_dyn); cudaEventDestroy(t->ev_obs[0]); cudaEventDestroy(t->ev_obs[1]);
@@ -1085,16 +1102,18 @@ extern "C" int cz_reset(const cz_tables* t, uint32_t* state, const int32_t* layo
 }
 
 // default layout ids of an episode: cz_layout_draw(seed, env_offset + e, episode) % P for every environment
-__global__ void cz_layout_ids_kernel(int32_t* __restrict__ out, int n_envs, int P, uint64_t seed, int64_t env_offset, uint64_t episode) {
+__global__ void cz_layout_ids_kernel(int32_t* __restrict__ out, int n_envs, const uint64_t* __restrict__ cum, int P, uint64_t seed,
+                                     int64_t env_offset, uint64_t episode) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < n_envs) out[e] = (int32_t)(cz_mix(seed, (uint64_t)(env_offset + e), episode) % (uint64_t)P);
+  if (e < n_envs) out[e] = (int32_t)cz_pick_layout(cum, P, cz_mix(seed, (uint64_t)(env_offset + e), episode));
 }
 
 extern "C" int cz_layout_ids(const cz_tables* t, int32_t* layout_ids, int n_envs, uint64_t seed, int64_t env_offset, uint64_t episode,
                              void* stream) {
   if (!t || !layout_ids) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (n_envs <= 0) return CZ_OK;
-  cz_layout_ids_kernel<<<(n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(layout_ids, n_envs, t->dev.P, seed, env_offset, episode);
+  cz_layout_ids_kernel<<<(n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(layout_ids, n_envs, t->dev.layout_cum, t->dev.P, seed, env_offset,
+                                                                               episode);
   g_launches.fetch_add(1);
   CZ_CUDA(cudaGetLastError());
   return CZ_OK;

@@ -802,7 +802,7 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
     const bool fresh = (flags & CZ_STEP_AUTO_RESET) && (e.tinfo & TI_DONE);
     if (fresh) {
       // ---- CookingEnvironment.reset (cooking_env.py:178-210): pooled layout -> state, no step (cz_env_kernel)
-      const int layout = (int)(cz_mix(seed, genv, (uint64_t)e.episode) % (uint64_t)T.P);
+      const int layout = cz_pick_layout(T.layout_cum, T.P, cz_mix(seed, genv, (uint64_t)e.episode));
       const uint32_t* src = T.pool + (size_t)layout * T.rows;
       e.rec = g < D ? __ldg(src + g) : 0u;
 #pragma unroll

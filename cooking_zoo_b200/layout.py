@@ -10,11 +10,17 @@ Reference: cooking_zoo/cooking_world/engine/parsing.py:5-151 draws placements fr
      "objects": [[type, [[x, y]...]]...]   # world_objects insertion order, list order
      "agents": [[x, y]...], "agent_spawn": [[xs, ys]...]}
 """
+from fractions import Fraction
+
 from .entities import entity
 
 
 class LayoutError(ValueError):
     pass
+
+
+class TooManyLayouts(Exception):
+    """enumerate_layouts gave up: the level has more distinct initial layouts than the caller wants to pool"""
 
 
 def sample_layout(level_object, meta, num_agents, rng):
@@ -127,3 +133,139 @@ def sample_layout(level_object, meta, num_agents, rng):
         "agents": [list(p) for p in agents],
         "agent_spawn": spawn,
     }
+
+
+def enumerate_layouts(level_object, meta, num_agents, max_layouts=4096):
+    """The EXACT distribution of the reference's level parser: every layout `sample_layout` can return, with its
+    probability as a Fraction -> [(layout, probability)], probabilities summing to 1.
+
+    Each placement of parsing.py is a rejection loop whose iterations are independent given the world built so far
+    (:25-76, :86-115, :127-151): with probability 1 - OPTIONAL the object is skipped, otherwise a cell is drawn as
+    (uniform pick from X_POSITION, uniform pick from Y_POSITION) and rejected cells repeat the whole iteration.  The
+    accepted outcome is therefore distributed as one iteration conditioned on not being rejected, which makes the
+    parser a finite tree of independent choices (the time-outs after 10001 / 1001 straight rejections are unreachable
+    unless no cell is valid at all, which raises here like there).  Layouts reached along several paths are merged.
+    Raises TooManyLayouts when the tree has more than `max_layouts` leaves."""
+    meta_count = dict(meta)
+    lines = level_object["LEVEL_LAYOUT"].splitlines()
+    width, height = len(lines[-1]), len(lines)
+    for y, line in enumerate(lines):          # the reference takes the width from the last row (parsing.py:17)
+        width = len(line)
+    base_static = {}
+    base_types = {}
+    for y, line in enumerate(lines):
+        for x, ch in enumerate(line):
+            typ = "Counter" if ch == "-" else "Floor"
+            base_types.setdefault(typ, []).append((x, y))
+            base_static[(x, y)] = typ
+
+    tasks = []
+    for entry in level_object["STATIC_OBJECTS"]:
+        name = next(iter(entry))
+        tasks += [("static", name, entry[name])] * entry[name]["COUNT"]
+    for entry in level_object["DYNAMIC_OBJECTS"]:
+        name = next(iter(entry))
+        tasks += [("dynamic", name, entry[name])] * entry[name]["COUNT"]
+    placed = 0
+    for spec in level_object["AGENTS"]:
+        for _ in range(spec["MAX_COUNT"]):
+            placed += 1
+            if placed <= num_agents:
+                tasks.append(("agent", "Agent", spec))
+    excluded = {tuple(p) for p in level_object["DYNAMIC_EXCLUDED_POSITIONS"]}
+
+    def cells_with_weight(spec, what):
+        xs, ys = spec["X_POSITION"], spec["Y_POSITION"]
+        out = {}
+        for px in xs:
+            for py in ys:
+                if px < 0 or py < 0 or px > width or py > height:
+                    raise LayoutError(f"Position {px} {py} of {what} is out of bounds set by the level layout!")
+                out[(px, py)] = out.get((px, py), 0) + Fraction(1, len(xs) * len(ys))
+        return out
+
+    leaves = {}
+    n_leaves = [0]
+
+    def finish(world, prob):
+        by_type, agents, spawn = world["by_type"], world["agents"], world["spawn"]
+        layout = {"width": width, "height": height, "meta": [[k, int(v)] for k, v in meta],
+                  "objects": [[t, [list(p) for p in locs]] for t, locs in by_type if locs],
+                  "agents": [list(p) for p in agents], "agent_spawn": spawn}
+        key = repr(layout)
+        if key in leaves:
+            leaves[key][1] += prob
+        else:
+            n_leaves[0] += 1
+            if n_leaves[0] > max_layouts:
+                raise TooManyLayouts(f"more than {max_layouts} distinct initial layouts")
+            leaves[key] = [layout, prob]
+
+    def walk(k, world, prob):
+        if k == len(tasks):
+            return finish(world, prob)
+        kind, name, spec = tasks[k]
+        p_opt = Fraction(spec["OPTIONAL"]).limit_denominator(1 << 53) if "OPTIONAL" in spec and kind != "agent" else Fraction(1)
+        if "OPTIONAL" in spec and kind != "agent":
+            # `OPTIONAL <= random.random()` skips: random() is k / 2**53, so P(skip) = 1 - ceil(OPTIONAL * 2**53) / 2**53
+            import math
+            p_opt = Fraction(min(max(math.ceil(Fraction(spec["OPTIONAL"]) * (1 << 53)), 0), 1 << 53), 1 << 53)
+        static_at, dynamic_at, agents = world["static_at"], world["dynamic_at"], world["agents"]
+        valid = {}
+        for cell, w in cells_with_weight(spec, f"object {name}" if kind != "agent" else "agent").items():
+            under = static_at.get(cell)
+            if kind == "static":
+                ok = under in ("Counter", "Floor")
+            elif kind == "dynamic":
+                ok = under == "Counter" and cell not in dynamic_at and cell not in excluded
+            else:
+                ok = cell not in agents and under == "Floor"
+            if ok:
+                valid[cell] = w
+        p_valid = p_opt * sum(valid.values(), Fraction(0))
+        p_skip = 1 - p_opt
+        norm = p_valid + p_skip
+        if norm == 0:
+            raise LayoutError(f"Can't find valid position for {kind}: {spec}")
+        if valid:          # the count check fires only when a cell is accepted (parsing.py:43, :57, :102, :137)
+            if name not in meta_count:
+                raise KeyError(name)
+            if meta_count[name] <= world["loaded"].get(name, 0):
+                raise LayoutError(f"Too many {name} objects loaded")
+            if kind != "agent" and entity(name).kind != kind:
+                raise LayoutError(f"{name} is not a {kind} object")
+        if p_skip:
+            walk(k + 1, world, prob * p_skip / norm)
+        for cell, w in valid.items():
+            nw = {"static_at": static_at, "dynamic_at": dynamic_at, "agents": agents, "spawn": world["spawn"],
+                  "loaded": dict(world["loaded"]), "by_type": [(t, list(l)) for t, l in world["by_type"]]}
+            nw["loaded"][name] = nw["loaded"].get(name, 0) + 1
+            types = dict(nw["by_type"])
+
+            def add(typ, loc):
+                if typ in types:
+                    types[typ].append(loc)
+                else:
+                    lst = [loc]
+                    types[typ] = lst
+                    nw["by_type"].append((typ, lst))
+            if kind == "static":
+                under = static_at[cell]
+                types[under].remove(cell)
+                add(name, cell)
+                nw["static_at"] = dict(static_at)
+                nw["static_at"][cell] = name
+            elif kind == "dynamic":
+                add(name, cell)
+                nw["dynamic_at"] = dynamic_at | {cell}
+            else:
+                nw["agents"] = agents + [(int(cell[0]), int(cell[1]))]
+                nw["spawn"] = world["spawn"] + [[list(spec["X_POSITION"]), list(spec["Y_POSITION"])]]
+            walk(k + 1, nw, prob * p_opt * w / norm)
+
+    world0 = {"static_at": base_static, "dynamic_at": frozenset(), "agents": [], "spawn": [], "loaded": {},
+              "by_type": [(t, list(l)) for t, l in base_types.items()]}
+    walk(0, world0, Fraction(1))
+    out = [(lay, p) for lay, p in leaves.values()]
+    assert sum(p for _, p in out) == 1
+    return out

@@ -12,7 +12,7 @@ import random
 import numpy as np
 
 from . import entities as E
-from .layout import sample_layout
+from .layout import sample_layout, enumerate_layouts, TooManyLayouts
 from .levels import load_level_object, load_meta
 from .recipes import active_book
 
@@ -41,11 +41,18 @@ class CompiledTables:
 
 def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_scheme=None,
                    end_condition_all_dishes=False, grace_period=20, agent_respawn_rate=0.0,
-                   agent_despawn_rate=0.0, recipe_pool=None, layout_pool_size=256, layout_seed=0,
-                   layouts=None, action_scheme="scheme3"):
+                   agent_despawn_rate=0.0, recipe_pool=None, layout_pool_size="auto", layout_seed=0,
+                   layouts=None, action_scheme="scheme3", layout_weights=None, exact_layout_cap=4096):
     """`recipes`: the per-agent recipe names of the reference constructor (default per-env
     assignment).  `recipe_pool`: every recipe name environments may be assigned (defaults to
-    `recipes`).  `layouts`: explicit list of layout dicts (overrides sampling)."""
+    `recipes`).  `layouts`: explicit list of layout dicts (overrides sampling; `layout_weights`: their
+    probabilities, default uniform).
+
+    The layout pool is what reset / auto-reset draw from.  layout_pool_size="auto" (default): the EXACT distribution of
+    the reference's level parser (layout.enumerate_layouts: every reachable layout with its probability; coop_test has
+    400, switch_test 648) when the level has at most `exact_layout_cap` layouts, so that episode starts follow the
+    reference's reset (cooking_env.py:190-195); levels with a larger support fall back to 256 i.i.d. draws of that
+    parser.  An integer asks for that many i.i.d. draws (uniform pool, draw index = cz_layout_draw % P)."""
     t = CompiledTables()
     if action_scheme not in ("scheme1", "scheme3"):
         # scheme2 raises AttributeError on its first step in the reference (action_scheme2.py:15)
@@ -98,9 +105,33 @@ def compile_tables(level, meta_file, num_agents, max_steps, recipes, reward_sche
     rows = D + num_agents + NUM_MISC
 
     # ---- layout pool -----------------------------------------------------------------
+    t.layout_exact = False
     if layouts is None:
-        rng = random.Random(layout_seed)
-        layouts = [sample_layout(level_object, meta, num_agents, rng) for _ in range(layout_pool_size)]
+        if layout_pool_size == "auto":
+            try:
+                support = enumerate_layouts(level_object, meta, num_agents, exact_layout_cap)
+                layouts, layout_weights = [lay for lay, _ in support], [p for _, p in support]
+                t.layout_exact = True
+            except TooManyLayouts:
+                layout_pool_size = 256
+        if layouts is None:
+            rng = random.Random(layout_seed)
+            layouts = [sample_layout(level_object, meta, num_agents, rng) for _ in range(int(layout_pool_size))]
+    # cumulative thresholds of a weighted pool, scaled to 2**64 (exact integer arithmetic): layout = first index whose
+    # threshold exceeds the 64-bit draw; None = uniform pool, layout = draw % P
+    t.layout_cum = None
+    if layout_weights is not None:
+        from fractions import Fraction
+        w = [Fraction(x) for x in layout_weights]
+        if len(w) != len(layouts) or any(x < 0 for x in w) or sum(w) <= 0:
+            raise ValueError("layout_weights must be one non-negative weight per layout")
+        total, acc, cum = sum(w), Fraction(0), []
+        for x in w:
+            acc += x
+            cum.append(min(int(acc * (1 << 64) / total), (1 << 64) - 1))
+        cum[-1] = (1 << 64) - 1
+        t.layout_cum = np.array(cum, np.uint64)
+        t.layout_prob = np.array([float(x / total) for x in w])
     W, H = layouts[0]["width"], layouts[0]["height"]
     if W > 8 or H > 8 or W * H > MAX_CELLS:
         raise ValueError("levels larger than 8x8 are not supported by the kernels")

@@ -85,14 +85,15 @@ class ParallelCookingEnv:
 
     def reset(self, seed=None, options=None):
         """The reference re-samples the layout from the global `random` stream and ignores `seed`
-        (cooking_env.py:178); here episode k takes pool layout cz_layout_draw(seed, 0, k) % P, or
+        (cooking_env.py:178); here episode k takes pool layout cz_layout_index(tables, seed, env_offset, k) — for levels
+        with at most 4096 initial layouts a draw from the exact distribution of the reference's parser — or
         options["layout_id"]."""
         options = options or {}
         if seed is not None:
             self._b.seed = int(seed)
         lid = options.get("layout_id")
         if lid is None:
-            lid = self._b.lib.cz_layout_draw(self._b.seed, self._b.env_offset, self._episode) % self._b.tables.num_layouts
+            lid = self._b.lib.cz_layout_index(self._b._handle, self._b.seed, self._b.env_offset, self._episode)
         self._episode += 1
         obs = self._b.reset(layout_ids=np.array([lid], np.int32)).cpu().numpy()[0]
         self._obs_all = obs

@@ -144,6 +144,9 @@ typedef struct cz_table_desc {
   const uint8_t* spawn_x;     /* [A][8] X_POSITION list of the agent's spawn entry (parsing.py:147)  */
   const uint8_t* spawn_y;     /* [A][8] Y_POSITION list                                      */
   const uint8_t* spawn_n;     /* [A][2] lengths of the two lists                             */
+  const uint64_t* layout_cum; /* [P] or NULL.  Weighted pool (the exact layout distribution of the reference's level
+                                 parser, engine/parsing.py:21-151): cumulative probabilities scaled to 2^64; a 64-bit
+                                 draw u selects the first layout with layout_cum[i] > u.  NULL: uniform pool, u % P. */
 } cz_table_desc;
 
 typedef struct cz_tables cz_tables;
@@ -164,7 +167,7 @@ int cz_state_rows(const cz_tables* t);
 int cz_reset(const cz_tables* t, uint32_t* state, const int32_t* layout_ids, const uint8_t* recipe_ids,
              const uint8_t* mask, double* obs, uint32_t* error_flags, int n_envs, void* stream);
 
-/* layout_ids[e] = cz_layout_draw(seed, env_offset + e, episode) % P on the device: the default layout of
+/* layout_ids[e] = cz_layout_index(t, seed, env_offset + e, episode) on the device: the default layout of
  * every environment's `episode`-th episode, the same draw CZ_STEP_AUTO_RESET makes. */
 int cz_layout_ids(const cz_tables* t, int32_t* layout_ids, int n_envs, uint64_t seed, int64_t env_offset,
                   uint64_t episode, void* stream);
@@ -175,7 +178,7 @@ int cz_layout_ids(const cz_tables* t, int32_t* layout_ids, int n_envs, uint64_t 
  * actions u8 [k_steps][n][A] (0..4 under scheme3, 0..7 under scheme1); obs f64 [n][A][L]; reward f64 [n][A];
  * terminated/truncated u8 [n][A] (each with a leading [k_steps] axis under CZ_STEP_KEEP_ALL);
  * error_flags u32 [n] (OR-accumulated, may be NULL).  With CZ_STEP_AUTO_RESET the layout of
- * episode k of global environment g = env_offset + e is pool[cz_layout_draw(seed, g, k) % P].
+ * episode k of global environment g = env_offset + e is pool[cz_layout_index(t, seed, g, k)].
  * k_steps > 1 (and single steps of small batches) run as ONE launch of the warp-per-environment kernel
  * (csrc/cz_warp.cuh: the environment stays in registers between steps, rows stream out after every step)
  * when the tables are in the specialised class; otherwise as k_steps launches of the per-step kernels.
@@ -201,6 +204,10 @@ int cz_step_host(cz_tables* t, uint32_t* state_dev, const uint8_t* actions_host,
 
 /* The counter-based draw used by auto-reset (splitmix64 finaliser over seed, env, episode). */
 uint64_t cz_layout_draw(uint64_t seed, uint64_t global_env, uint64_t episode);
+
+/* Pool index that draw selects under these tables: the first i with layout_cum[i] > draw for a weighted pool,
+ * draw % P for a uniform one.  What CZ_STEP_AUTO_RESET and cz_layout_ids compute on the device. */
+int cz_layout_index(const cz_tables* t, uint64_t seed, uint64_t global_env, uint64_t episode);
 
 /* Randomness of handle_agent_spawn (cooking_world/cooking_world.py:267-290).  The reference draws
  * np.random.random() for despawn/respawn and random.sample(list, 1) for the respawn cell from

@@ -130,3 +130,46 @@ def test_scan_order_is_shared_only_when_every_layout_agrees_with_the_level_file(
     finally:
         os.unlink(f.name)
     assert len({s.tobytes() for s in t2.scan_order}) > 1
+
+
+def _chi2_ok(counts, probs, n):
+    """Pearson chi-square of observed counts against exact probabilities: within 5 sigma of its mean"""
+    import numpy as np
+    exp = np.asarray(probs, np.float64) * n
+    chi2 = float(((np.asarray(counts) - exp) ** 2 / exp).sum())
+    dof = len(probs) - 1
+    return abs(chi2 - dof) < 5 * (2 * dof) ** 0.5, chi2, dof
+
+
+def test_exact_layout_distribution_matches_the_parser():
+    """layout.enumerate_layouts: the support and the probabilities of the reference's level parser, against the
+    frequencies of sample_layout (which reproduces the reference's worlds seed by seed, see above)"""
+    from fractions import Fraction
+    from cooking_zoo_b200.layout import enumerate_layouts
+    for level, meta, A, n_support in (("coop_test", "example", 2, 400), ("switch_test", "example", 2, 648),
+                                      (os.path.join(ROOT, "tests/golden/levels/weighted_layouts.json"), "example", 1, None)):
+        lo, mt = levels.load_level_object(level), levels.load_meta(meta)
+        support = enumerate_layouts(lo, mt, A)
+        assert sum(p for _, p in support) == 1
+        if n_support:
+            assert len(support) == n_support and all(p == Fraction(1, n_support) for _, p in support)   # SURVEY §8c: 400
+        else:
+            assert len({p for _, p in support}) > 3          # OPTIONAL objects, duplicate list entries, competing objects
+        index = {repr(lay): k for k, (lay, _) in enumerate(support)}
+        n = 60 * len(support)
+        counts = [0] * len(support)
+        rng = random.Random(99)
+        for _ in range(n):
+            counts[index[repr(sample_layout(lo, mt, A, rng))]] += 1       # KeyError = a layout outside the support
+        ok, chi2, dof = _chi2_ok(counts, [float(p) for _, p in support], n)
+        assert ok, (level, chi2, dof)
+
+
+def test_auto_pool_is_the_exact_support_and_large_levels_fall_back():
+    t = compile_tables("coop_test", "example", 2, 400, ["TomatoLettuceSalad", "CarrotBanana"])
+    assert t.layout_exact and t.num_layouts == 400 and t.layout_cum is not None
+    assert int(t.layout_cum[-1]) == 2 ** 64 - 1 and (np.diff(t.layout_cum.astype(object)) > 0).all()
+    t = compile_tables("coexistence_test", "example", 2, 400, ["TomatoLettuceSalad", "CarrotBanana"])
+    assert not t.layout_exact and t.num_layouts == 256 and t.layout_cum is None      # > 4096 layouts: i.i.d. pool
+    t = compile_tables("coop_test", "example", 2, 400, ["TomatoLettuceSalad", "CarrotBanana"], layout_pool_size=32)
+    assert not t.layout_exact and t.num_layouts == 32 and t.layout_cum is None
