@@ -64,7 +64,8 @@ def bind_to_gpu_numa_node(local):
 def workload_config(n_gpus, envs_per_gpu):
     return {"workload": f"cfg4 shard: {envs_per_gpu} envs/GPU x {n_gpus} GPU, coop_test/example, 2 agents, "
                         f"per-env recipe pairs from the 8-recipe book, scheme3 uniform random actions, "
-                        f"max_steps {MAX_STEPS}, auto-reset, feature_vector f64 obs",
+                        f"max_steps {MAX_STEPS}, auto-reset from the exact 400-layout distribution of the level parser, "
+                        f"feature_vector f64 obs",
             "envs_per_gpu": envs_per_gpu, "num_agents": NUM_AGENTS, "obs_len": 278,
             "l2": "per-step working set (>600 MB) exceeds the 126 MB L2; no flush needed",
             "parallelism": f"env-sharded x{n_gpus}, no per-step collective"}
@@ -319,7 +320,7 @@ def run_gpu_arm(args):
         untimed, then timed): the driver's short runs (K = 20) otherwise measure the host's launch jitter, not the GPU.
         Every step is a full cz_step / cz_step_pipelined with its own resident action tensor; nothing is skipped."""
         env = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
-                                device=str(dev), recipe_pool=BOOK, layout_pool_size=400, layout_seed=0,
+                                device=str(dev), recipe_pool=BOOK, layout_pool_size="auto", layout_seed=0,
                                 auto_reset=True, seed=2026, env_offset=rank * N, pipelined=pipelined, obs_dtype=obs_dtype)
         env.reset(recipe_ids=recipe_ids)
         for s in range(args.warmup):
@@ -466,7 +467,7 @@ def run_gpu_arm(args):
         try:
             n3, K3 = 4096, 64
             env3 = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
-                                     device=str(dev), layout_pool_size=400, layout_seed=0, auto_reset=True, seed=7)
+                                     device=str(dev), layout_pool_size="auto", layout_seed=0, auto_reset=True, seed=7)
             env3.reset()
             act3 = torch.randint(0, 5, (K3, n3, A), generator=g, dtype=torch.uint8).to(dev)
             cnt = [0]
@@ -526,10 +527,30 @@ def run_gpu_arm(args):
                                            pipelined=(mode == "pipelined"))
                 mix.reset()
 
-                def closed_loop():
-                    acts, _ = mix.heuristic_actions()
-                    mix.step(acts)
-                out5[mode] = rate(closed_loop, n5, 100, 10, fin=mix.wait)
+                for _ in range(5):
+                    mix.cook_step()
+                mix.wait()
+                torch.cuda.synchronize(dev)
+                # 10 closed-loop steps (per group: cz_policy_act + step on the group's stream) as one CUDA graph: the
+                # eager loop is bound by the host's per-group launch work, not by the GPU
+                graph5 = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                if mode == "pipelined":
+                    for grp in mix.groups.values():
+                        _native.check(grp.lib.cz_pipeline_reset(grp._handle, grp.lib.cz_pipeline_current(grp._handle)))
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(graph5, stream=side):
+                        for _ in range(10):
+                            mix.cook_step()
+                        mix.wait()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                out5[mode] = rate(graph5.replay, n5 * 10, 20, 3)
+                out5[mode + "_eager"] = None
+                if mode == "pipelined":
+                    for grp in mix.groups.values():
+                        _native.check(grp.lib.cz_pipeline_reset(grp._handle, grp.lib.cz_pipeline_current(grp._handle)))
+                out5[mode + "_eager"] = rate(mix.cook_step, n5, 100, 10, fin=mix.wait)
                 if mode == "in_place":
                     b5 = sum(len(mix.index[a]) * (a * grp.obs_len * 8 + a * 11 + 2 * grp.tables.rows * 4)
                              for a, grp in mix.groups.items()) / n5
@@ -538,6 +559,9 @@ def run_gpu_arm(args):
                                 f"count, own CUDA stream each), every action from the device cook (cz_policy_act), despawn 0.05 / "
                                 f"respawn 0.2 / grace 3, per-group recipes, auto-reset",
                     "closed_loop_env_steps_per_s": out5["in_place"], "closed_loop_pipelined_env_steps_per_s": out5["pipelined"],
+                    "how": "10 closed-loop steps of every group captured as one CUDA graph (4 streams, 2-3 kernels per group and step)",
+                    "eager_env_steps_per_s": {"in_place": out5["in_place_eager"], "pipelined": out5["pipelined_eager"],
+                                              "note": "host-bound: ~8 library calls and 8 stream joins per population step"},
                     "bytes_per_env_step": b5,
                     "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": out5["pipelined"] * b5 / 1e9, "peak": peak,
                                  "frac": out5["pipelined"] * b5 / 1e9 / peak,
@@ -551,7 +575,7 @@ def run_gpu_arm(args):
         try:
             os.environ["CZ_GENERIC"] = "1"
             envg = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
-                                     device=str(dev), recipe_pool=BOOK, layout_pool_size=400, layout_seed=0, auto_reset=True,
+                                     device=str(dev), recipe_pool=BOOK, layout_pool_size="auto", layout_seed=0, auto_reset=True,
                                      seed=2026)
             del os.environ["CZ_GENERIC"]
             envg.reset(recipe_ids=recipe_ids)
@@ -578,7 +602,7 @@ def run_gpu_arm(args):
             env.wait()
             torch.cuda.synchronize(dev)
             envc = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
-                                     action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size=400,
+                                     action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size="auto",
                                      layout_seed=0, auto_reset=True, seed=2026)
             envc.reset(recipe_ids=recipe_ids)
             for _ in range(5):
@@ -600,7 +624,7 @@ def run_gpu_arm(args):
             pol_ms = c0.elapsed_time(c1) / kc
             envc.close()
             envc = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
-                                     action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size=400,
+                                     action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size="auto",
                                      layout_seed=0, auto_reset=True, seed=2026, pipelined=True)
             envc.reset(recipe_ids=recipe_ids)
             for _ in range(5):

@@ -39,8 +39,8 @@ class BatchedCookingEnv:
     def __init__(self, num_envs, level, meta_file, num_agents, max_steps, recipes, agent_visualization=None,
                  obs_spaces=None, end_condition_all_dishes=False, action_scheme="scheme1", render=False,
                  reward_scheme=None, agent_respawn_rate=0.0, grace_period=20, agent_despawn_rate=0.0, *,
-                 device="cuda:0", recipe_pool=None, layout_pool_size=256, layout_seed=0, layouts=None,
-                 auto_reset=False, seed=0, env_offset=0, pipelined=False, obs_dtype=torch.float64):
+                 device="cuda:0", recipe_pool=None, layout_pool_size="auto", layout_seed=0, layouts=None,
+                 auto_reset=False, seed=0, env_offset=0, pipelined=False, obs_dtype=torch.float64, stream=None):
         obs_spaces = obs_spaces or ["feature_vector"] * num_agents
         if any(o != "feature_vector" for o in obs_spaces):
             raise NotImplementedError("the batched entry point builds feature_vector observations only "
@@ -50,6 +50,7 @@ class BatchedCookingEnv:
                                       "in the reference itself, action_scheme2.py:15)")
         if render:
             raise NotImplementedError("rendering is out of scope")
+        self.stream = stream                    # a torch.cuda.Stream every call is enqueued on (default: torch's current stream)
         self.lib = _native.load_library()       # raises when the CUDA library is missing
         if not torch.cuda.is_available():
             raise _native.NativeError("BatchedCookingEnv needs a CUDA device (there is no CPU fallback)")
@@ -90,6 +91,8 @@ class BatchedCookingEnv:
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
+        if self.stream is not None:
+            return C.c_void_p(self.stream.cuda_stream)
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def close(self):

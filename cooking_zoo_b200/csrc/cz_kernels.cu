@@ -61,6 +61,21 @@ __device__ __forceinline__ void cz_bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
+// Row stores of the warp-per-environment writer.  CZ_OBS_ST selects the cache operator (A/B builds through
+// CZ_NVCC_EXTRA=-DCZ_OBS_ST=1|2): 0 default (write-back), 1 st.global.cs (streaming, evict first), 2 st.global.wt.
+#ifndef CZ_OBS_ST
+#define CZ_OBS_ST 0
+#endif
+__device__ __forceinline__ void cz_row_store(double2* p, const double2 v) {
+#if CZ_OBS_ST == 1
+  __stcs(p, v);
+#elif CZ_OBS_ST == 2
+  __stwt(p, v);
+#else
+  *p = v;
+#endif
+}
+
 // ---- observation rows (get_feature_vector, cooking_env.py:352-373) -----------------------------
 // A row = table segments (static slots: a function of layout variant and observer cell only, copied
 // from the L2-resident obs_table with 128-bit loads/stores) + computed slots (dynamic objects,
@@ -307,7 +322,9 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
               const int32_t* __restrict__ layout_ids, const uint8_t* __restrict__ recipe_ids,
               const uint8_t* __restrict__ mask, double* __restrict__ obs, double* __restrict__ reward,
               uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint32_t* __restrict__ errflags,
-              int n_envs, uint32_t flags, uint64_t seed, int64_t env_offset) {
+              int n_envs, uint32_t flags, uint64_t seed, int64_t env_offset, int ld) {
+  // `ld`: columns of the state matrix (>= n_envs: a launch may cover a column range of a larger batch, with `state`,
+  // the outputs and env_offset already advanced to its first environment)
   // NA = 0: generic kernel (run-time agent count, tables in global memory, any observation plan)
   // NA > 0: specialised kernel for NA agents (tables in shared memory, packed observation lanes)
   constexpr bool FAST = NA != 0;
@@ -347,7 +364,7 @@ cz_env_kernel(const __grid_constant__ CzDev T, const uint32_t* state, uint32_t* 
   const int ts = (int)((flags >> CZ_FLAG_TILE_SHIFT) & 7u), TS = 1 << ts;
   const int n_tiles = (n_envs + TS - 1) >> ts;
   const int warps_total = gridDim.x * CZ_WARPS_PER_BLOCK;
-  const size_t N = (size_t)n_envs;
+  const size_t N = (size_t)ld;
   const uint32_t* misc = state + (size_t)(D + A) * N;
   uint32_t* misc_out = state_out + (size_t)(D + A) * N;  // == misc unless the step is pipelined (ping-pong state)
 
@@ -624,13 +641,13 @@ __device__ __forceinline__ void cz_pair_store(const CzDev& T, const LaneSlot& ls
 // a lane owns pairs `lane` and `lane + 32`.
 template <int NA, bool TWO>
 __global__ void __launch_bounds__(32 * ENVS_WARPS, (TWO || NA >= 3) ? 5 : CZ_ENVS_MIN_BLOCKS)
-cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, double* __restrict__ obs, int n_envs) {
+cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, double* __restrict__ obs, int n_envs, int ld) {
   extern __shared__ __align__(16) unsigned char smem_rows[];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int env = blockIdx.x * ENVS_WARPS + warp;
   if (env >= n_envs) return;
   const int D = T.D, tab2 = T.tab_len >> 1, L2 = T.L >> 1;
-  const size_t N = (size_t)n_envs;
+  const size_t N = (size_t)ld;  // columns of the state matrix (the launch may cover a column range of a larger batch)
   const int stage2 = (T.stage_len + 1) >> 1;  // double2 per staging row
   double2* stage = reinterpret_cast<double2*>(smem_rows) + (size_t)warp * NA * stage2;
 
@@ -656,7 +673,7 @@ cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__
     const int n2 = T.ranges[0][1] >> 1, o2 = T.ranges[0][0] >> 1, s2 = (T.ranges[0][0] - T.stage_lo) >> 1;
 #pragma unroll
     for (int a = 0; a < NA; ++a)
-      for (int k = lane; k < n2; k += 32) g2[a * L2 + o2 + k] = stage[a * stage2 + s2 + k];
+      for (int k = lane; k < n2; k += 32) cz_row_store(g2 + a * L2 + o2 + k, stage[a * stage2 + s2 + k]);
   }
   {  // table segments: all rows' loads first, then the stores
     double2 v0[NA], v1[NA];
@@ -670,8 +687,8 @@ cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__
     }
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
-      if (ls.t0 >= 0) g2[a * L2 + ls.t0] = v0[a];
-      if (ls.t1 >= 0) g2[a * L2 + ls.t1] = v1[a];
+      if (ls.t0 >= 0) cz_row_store(g2 + a * L2 + ls.t0, v0[a]);
+      if (ls.t1 >= 0) cz_row_store(g2 + a * L2 + ls.t1, v1[a]);
     }
   }
 }
@@ -713,7 +730,8 @@ struct cz_tables {
   int scratch_envs;
   // pipelined step: dynamics on a high-priority stream, observations on a second one, ping-pong state
   cudaStream_t pipe_dyn, pipe_obs;
-  cudaEvent_t ev_user, ev_dyn, ev_obs[2];
+  cudaEvent_t ev_user, ev_dyn, ev_obs[2], ev_chunk[8];
+  int split;                // in-place step of a large batch: column ranges whose dynamics run under the previous range's rows
   int pipe_ready, pipe_cur, pipe_obs_pending[2];
   int pipe_dyn_blocks;   // resident dynamics blocks per SM in the pipelined step (0 = no cap)
   size_t smem_optin;
@@ -941,6 +959,9 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     if (g && g[0] == '1') t->simple = t->simple2 = 0;
     const char* k = getenv("CZ_TWO_KERNEL_MIN_ENVS");
     t->two_kernel_min_envs = k ? atoi(k) : 49152;  // measured crossover between 32768 and 65536 (profiles/r01_two_kernel_sweep.txt)
+    const char* sp = getenv("CZ_SPLIT");
+    t->split = sp ? atoi(sp) : 2;
+    if (t->split > 8) t->split = 8;
     const char* w = getenv("CZ_WARP_MAX_ENVS");
     t->warp_max_envs = w ? atoi(w) : 8192;
     const char* wk = getenv("CZ_WARP_K_MAX_ENVS");
@@ -983,6 +1004,7 @@ extern "C" int cz_tables_destroy(cz_tables* t) {
   if (t->pipe_ready) {
     cudaStreamDestroy(t->pipe_dyn); cudaStreamDestroy(t->pipe_obs);
     cudaEventDestroy(t->ev_user); cudaEventDestroy(t->ev_dyn); cudaEventDestroy(t->ev_obs[0]); cudaEventDestroy(t->ev_obs[1]);
+    for (int c = 0; c < 8; ++c) cudaEventDestroy(t->ev_chunk[c]);
   }
   delete t;
   return CZ_OK;
@@ -1012,7 +1034,8 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
                      const int32_t* layout_ids,
                      const uint8_t* recipe_ids, const uint8_t* mask, double* obs, double* reward, uint8_t* term,
                      uint8_t* trunc, uint32_t* err, int n_envs, uint32_t flags, uint64_t seed, int64_t env_offset,
-                     void* stream) {
+                     void* stream, int ld = 0) {
+  if (ld <= 0) ld = n_envs;
   if (!t || !state || !state_out) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (MODE == MODE_OBSERVE && !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (n_envs <= 0) return CZ_OK;
@@ -1031,7 +1054,7 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
   cudaStream_t s = (cudaStream_t)stream;
 #define CZ_GO(O, NA)                                                                                                  \
   cz_env_kernel<MODE, O, NA><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, state_out, actions, layout_ids, recipe_ids, mask, obs, \
-                                                           reward, term, trunc, err, n_envs, flags, seed, env_offset)
+                                                           reward, term, trunc, err, n_envs, flags, seed, env_offset, ld)
   if (dyn_only && (t->simple || t->simple2)) {
     switch (t->dev.A) {
       case 1: CZ_GO(OBS_NONE, 1); break;
@@ -1067,15 +1090,16 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
 }
 
 // The warp-per-environment float64 row writer (packed plans) on `s`.
-static int cz_launch_obs64(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, cudaStream_t s) {
+static int cz_launch_obs64(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, cudaStream_t s, int ld = 0) {
+  if (ld <= 0) ld = n_envs;
   if (!state || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
   if (n_envs <= 0) return CZ_OK;
   const int blocks = (n_envs + ENVS_WARPS - 1) / ENVS_WARPS;
   const size_t smem = (size_t)ENVS_WARPS * t->dev.A * ((t->dev.stage_len + 1) / 2) * 16;
 #define CZ_OBS_GO(NA)                                                                                               \
-  if (t->simple2) cz_obs_envs_kernel<NA, true><<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs);    \
-  else cz_obs_envs_kernel<NA, false><<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs)
+  if (t->simple2) cz_obs_envs_kernel<NA, true><<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs, ld); \
+  else cz_obs_envs_kernel<NA, false><<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs, ld)
   switch (t->dev.A) {
     case 1: CZ_OBS_GO(1); break;
     case 2: CZ_OBS_GO(2); break;
@@ -1122,6 +1146,43 @@ extern "C" int cz_layout_ids(const cz_tables* t, int32_t* layout_ids, int n_envs
 extern "C" int cz_random_actions(const cz_tables* t, uint8_t* actions, int n_envs, uint64_t seed, uint64_t step,
                                  int64_t env_offset, void* stream);
 
+static int cz_pipe_init(cz_tables* t);
+
+// In-place step of a large batch as `split` column ranges: the dynamics of range c + 1 (internal high-priority stream)
+// run under the row writer of range c (second internal stream), so only the first range's dynamics are exposed.  The
+// caller's stream forks into both and joins them again: every output is ordered on it when the call's work is done,
+// exactly like the two launches it replaces.
+static int cz_step_split(cz_tables* t, uint32_t* state, const uint8_t* actions, double* obs, double* reward,
+                         uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, uint32_t flags,
+                         uint64_t seed, int64_t env_offset, void* stream) {
+  int rc = cz_pipe_init(t);
+  if (rc != CZ_OK) return rc;
+  const int A = t->dev.A, L = t->dev.L;
+  const int chunk = (((n_envs + t->split - 1) / t->split) + 255) & ~255;  // whole tiles and whole writer blocks
+  cudaStream_t user = (cudaStream_t)stream;
+  CZ_CUDA(cudaEventRecord(t->ev_user, user));
+  CZ_CUDA(cudaStreamWaitEvent(t->pipe_dyn, t->ev_user, 0));
+  CZ_CUDA(cudaStreamWaitEvent(t->pipe_obs, t->ev_user, 0));
+  int c = 0;
+  for (int e0 = 0; e0 < n_envs; e0 += chunk, ++c) {
+    const int n = n_envs - e0 < chunk ? n_envs - e0 : chunk;
+    const size_t na = (size_t)e0 * A;
+    rc = cz_launch<MODE_STEP>(t, state + e0, state + e0, true, actions + na, nullptr, nullptr, nullptr, nullptr, reward + na,
+                              terminated + na, truncated + na, error_flags ? error_flags + e0 : nullptr, n, flags, seed,
+                              env_offset + e0, t->pipe_dyn, n_envs);
+    if (rc != CZ_OK) return rc;
+    CZ_CUDA(cudaEventRecord(t->ev_chunk[c], t->pipe_dyn));
+    CZ_CUDA(cudaStreamWaitEvent(t->pipe_obs, t->ev_chunk[c], 0));
+    rc = cz_launch_obs64(t, state + e0, obs + na * L, n, t->pipe_obs, n_envs);
+    if (rc != CZ_OK) return rc;
+  }
+  CZ_CUDA(cudaEventRecord(t->ev_dyn, t->pipe_dyn));
+  CZ_CUDA(cudaEventRecord(t->ev_obs[0], t->pipe_obs));
+  CZ_CUDA(cudaStreamWaitEvent(user, t->ev_dyn, 0));
+  CZ_CUDA(cudaStreamWaitEvent(user, t->ev_obs[0], 0));
+  return CZ_OK;
+}
+
 // one in-place step with resident actions on the lane-per-environment kernels
 static int cz_step_one(const cz_tables* t, uint32_t* state, const uint8_t* actions, double* obs, double* reward,
                        uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs, uint32_t flags,
@@ -1130,6 +1191,9 @@ static int cz_step_one(const cz_tables* t, uint32_t* state, const uint8_t* actio
   // observation phase of the fused kernel; small batches keep the single launch): dynamics, then the row writer
   if (t && obs && !(flags & CZ_STEP_OBS_F32) &&
       (t->simple2 || (t->simple && t->two_kernel_min_envs > 0 && n_envs >= t->two_kernel_min_envs))) {
+    if (t->split > 1 && n_envs >= 2 * t->two_kernel_min_envs && t->two_kernel_min_envs > 0)
+      return cz_step_split(const_cast<cz_tables*>(t), state, actions, obs, reward, terminated, truncated, error_flags, n_envs, flags,
+                           seed, env_offset, stream);
     int rc = cz_launch<MODE_STEP>(t, state, state, true, actions, nullptr, nullptr, nullptr, nullptr, reward, terminated, truncated,
                                   error_flags, n_envs, flags, seed, env_offset, stream);
     if (rc != CZ_OK) return rc;
@@ -1236,6 +1300,7 @@ static int cz_pipe_init(cz_tables* t) {
   CZ_CUDA(cudaEventCreateWithFlags(&t->ev_dyn, cudaEventDisableTiming));
   CZ_CUDA(cudaEventCreateWithFlags(&t->ev_obs[0], cudaEventDisableTiming));
   CZ_CUDA(cudaEventCreateWithFlags(&t->ev_obs[1], cudaEventDisableTiming));
+  for (int c = 0; c < 8; ++c) CZ_CUDA(cudaEventCreateWithFlags(&t->ev_chunk[c], cudaEventDisableTiming));
   t->pipe_ready = 1;
   return CZ_OK;
 }

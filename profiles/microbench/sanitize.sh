@@ -1,7 +1,7 @@
 # compute-sanitizer over every kernel family (run on the GPU box from the repo root):
 #   bash profiles/microbench/sanitize.sh "fused two pipe policy f32 generic open4 spawn warp" "memcheck racecheck"
 # One log per (tool, path) under gpurun_out/sanitize/; the summary line of each goes to gpurun_out/sanitize/SUMMARY.txt.
-PATHS=${1:-"fused two pipe policy f32 generic open4 spawn"}
+PATHS=${1:-"fused two pipe policy f32 generic open4 spawn warp"}
 TOOLS=${2:-"memcheck racecheck"}
 mkdir -p gpurun_out/sanitize
 : > gpurun_out/sanitize/SUMMARY.txt

@@ -41,6 +41,7 @@ def drive(env, steps, n, A, k_steps=1):
 
 def main(which):
     if which == "fused":
+        os.environ["CZ_WARP_MAX_ENVS"] = "0"      # the lane-per-environment fused TMA kernel (small batches default to the warp kernel)
         drive(make(4096), 16, 4096, 2)
     elif which == "two":
         drive(make(50001), 4, 50001, 2)
@@ -62,9 +63,16 @@ def main(which):
         drive(make(5003), 4, 5003, 2)
         drive(make(3001, obs_dtype=torch.float32), 3, 3001, 2)
     elif which == "warp":
-        env = make(4099)
+        env = make(4099)                          # 16-lane groups: two environments per warp, ragged last warp
         drive(env, 3, 4099, 2, k_steps=8)
         env.step_k(8)          # device-generated actions
+        drive(env, 6, 4099, 2)                    # single steps of a small batch
+        os.environ["CZ_WARP_GROUP"] = "32"
+        drive(make(1001, agent_respawn_rate=0.3, agent_despawn_rate=0.2, grace_period=2), 2, 1001, 2, k_steps=5)
+        del os.environ["CZ_WARP_GROUP"]
+        R4 = ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"]
+        drive(make(777, level="tests/golden/levels/open4.json", meta="tests/golden/levels/meta4.json", A=4, recipes=R4),
+              2, 777, 4, k_steps=5)
         torch.cuda.synchronize()
     elif which == "open4":
         R4 = ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"]

@@ -251,6 +251,32 @@ def test_large_batch_two_kernel_step_equals_the_fused_kernel_on_a_ragged_batch(m
     assert torch.equal(a.state, b.state)
 
 
+@pytest.mark.parametrize("split", ["2", "3", "8"])
+def test_split_in_place_step_equals_the_unsplit_step(split, monkeypatch):
+    """in-place steps of >= 98304 environments run as column ranges (dynamics of range c+1 under the rows of range c,
+    csrc cz_step_split); CZ_SPLIT=1 is the plain two-launch step.  100001 environments: ragged last range."""
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=30,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    n = 100001
+    monkeypatch.setenv("CZ_SPLIT", "1")
+    a = _make(n, cfg, auto_reset=True, seed=8, layout_pool_size=64)
+    monkeypatch.setenv("CZ_SPLIT", split)
+    b = _make(n, cfg, auto_reset=True, seed=8, layout_pool_size=64)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(2)
+    for t in range(35):
+        act = torch.from_numpy(rng.integers(0, 5, size=(n, 2)).astype(np.uint8)).cuda()
+        l0 = a.lib.cz_launch_count()
+        oa, ra, ta, ua, _ = a.step(act)
+        l1 = a.lib.cz_launch_count()
+        ob, rb, tb, ub, _ = b.step(act)
+        l2 = a.lib.cz_launch_count()
+        assert l1 - l0 == 2 and l2 - l1 == 2 * min(int(split), -(-n // (((-(-n // int(split))) + 255) & ~255)))
+        assert torch.equal(oa.view(torch.int64), ob.view(torch.int64)), t
+        assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(ta, tb) and torch.equal(ua, ub)
+    assert torch.equal(a.state, b.state) and torch.equal(a.error_flags, b.error_flags)
+
+
 def test_device_action_stream_matches_its_definition_and_is_shard_independent():
     """cz_random_actions: floor(cz_spawn_uniform(seed ^ 0xA5.., env, 0, step, agent) * len(ACTIONS)); scheme1 draws from 8
     actions, scheme3 from 5; the stream of an environment does not depend on the shard it lives in"""
