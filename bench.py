@@ -462,8 +462,13 @@ def run_gpu_arm(args):
         torch.cuda.synchronize(dev)
         return units * reps / (a0.elapsed_time(a1) / 1e3)
 
+    only = set(filter(None, os.environ.get("CZ_BENCH_ONLY", "").split(",")))      # e.g. CZ_BENCH_ONLY=cfg5 while tuning
+
+    def want(name):
+        return rank == 0 and world == 1 and not args.no_cfg3 and (not only or name in only)
+
     cfg3 = None
-    if rank == 0 and world == 1 and not args.no_cfg3:
+    if want("cfg3"):
         try:
             n3, K3 = 4096, 64
             env3 = BatchedCookingEnv(n3, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
@@ -511,7 +516,7 @@ def run_gpu_arm(args):
 
     # ---- BASELINE config 5: 1-4 agents per environment, heuristic cooks on the device, despawn / respawn on
     cfg5 = None
-    if rank == 0 and world == 1 and not args.no_cfg3:
+    if want("cfg5"):
         try:
             from cooking_zoo_b200 import MixedAgentCookingEnv
             n5 = 65536
@@ -519,59 +524,62 @@ def run_gpu_arm(args):
             lv5 = os.path.join(ROOT, "tests", "golden", "levels", "open4.json")
             mt5 = os.path.join(ROOT, "tests", "golden", "levels", "meta4.json")
             r5 = ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "AppleWatermelon"]
-            out5 = {}
+            out5, b5 = {}, 0.0
             for mode in ("in_place", "pipelined"):
-                mix = MixedAgentCookingEnv(counts, lv5, mt5, MAX_STEPS, r5, device=str(dev), end_condition_all_dishes=True,
-                                           action_scheme="scheme3", layout_pool_size=256, auto_reset=True, seed=5,
-                                           agent_respawn_rate=0.2, agent_despawn_rate=0.05, grace_period=3,
-                                           pipelined=(mode == "pipelined"))
-                mix.reset()
-
-                for _ in range(5):
-                    mix.cook_step()
-                mix.wait()
-                torch.cuda.synchronize(dev)
-                # 10 closed-loop steps (per group: cz_policy_act + step on the group's stream) as one CUDA graph: the
-                # eager loop is bound by the host's per-group launch work, not by the GPU
-                graph5 = torch.cuda.CUDAGraph()
-                side = torch.cuda.Stream(dev)
-                side.wait_stream(torch.cuda.current_stream(dev))
-                if mode == "pipelined":
-                    for grp in mix.groups.values():
-                        _native.check(grp.lib.cz_pipeline_reset(grp._handle, grp.lib.cz_pipeline_current(grp._handle)))
-                with torch.cuda.stream(side):
-                    with torch.cuda.graph(graph5, stream=side):
-                        for _ in range(10):
-                            mix.cook_step()
-                        mix.wait()
-                torch.cuda.current_stream(dev).wait_stream(side)
-                out5[mode] = rate(graph5.replay, n5 * 10, 20, 3)
-                out5[mode + "_eager"] = None
-                if mode == "pipelined":
-                    for grp in mix.groups.values():
-                        _native.check(grp.lib.cz_pipeline_reset(grp._handle, grp.lib.cz_pipeline_current(grp._handle)))
-                out5[mode + "_eager"] = rate(mix.cook_step, n5, 100, 10, fin=mix.wait)
-                if mode == "in_place":
+                try:
+                    mix = MixedAgentCookingEnv(counts, lv5, mt5, MAX_STEPS, r5, device=str(dev), end_condition_all_dishes=True,
+                                               action_scheme="scheme3", layout_pool_size=256, auto_reset=True, seed=5,
+                                               agent_respawn_rate=0.2, agent_despawn_rate=0.05, grace_period=3,
+                                               pipelined=(mode == "pipelined"))
+                    mix.reset()
                     b5 = sum(len(mix.index[a]) * (a * grp.obs_len * 8 + a * 11 + 2 * grp.tables.rows * 4)
                              for a, grp in mix.groups.items()) / n5
-                mix.close()
+                    for _ in range(5):
+                        mix.cook_step()
+                    mix.wait()
+                    torch.cuda.synchronize(dev)
+                    # 10 closed-loop steps (per group: cz_policy_act + step on the group's stream) as one CUDA graph: the
+                    # eager loop is bound by the host's per-group launch work, not by the GPU
+                    graph5 = torch.cuda.CUDAGraph()
+                    side = torch.cuda.Stream(dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    if mode == "pipelined":
+                        for grp in mix.groups.values():
+                            _native.check(grp.lib.cz_pipeline_reset(grp._handle, grp.lib.cz_pipeline_current(grp._handle)))
+                    with torch.cuda.stream(side):
+                        with torch.cuda.graph(graph5, stream=side):
+                            for _ in range(10):
+                                mix.cook_step()
+                            mix.wait()
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    out5[mode] = rate(graph5.replay, n5 * 10, 20, 3)
+                    out5[mode + "_eager"] = None
+                    if mode == "pipelined":
+                        for grp in mix.groups.values():
+                            _native.check(grp.lib.cz_pipeline_reset(grp._handle, grp.lib.cz_pipeline_current(grp._handle)))
+                    out5[mode + "_eager"] = rate(mix.cook_step, n5, 100, 10, fin=mix.wait)
+                    mix.close()
+                except Exception as ex:      # one mode failing must not cost the other
+                    out5[mode] = out5.get(mode)
+                    out5[mode + "_error"] = f"{type(ex).__name__}: {str(ex)[:160]}"
             cfg5 = {"workload": f"cfg5: {n5} envs on the open 4-agent kitchen, agent count 1-4 per env (one BatchedCookingEnv group per "
                                 f"count, own CUDA stream each), every action from the device cook (cz_policy_act), despawn 0.05 / "
                                 f"respawn 0.2 / grace 3, per-group recipes, auto-reset",
-                    "closed_loop_env_steps_per_s": out5["in_place"], "closed_loop_pipelined_env_steps_per_s": out5["pipelined"],
+                    "closed_loop_env_steps_per_s": out5.get("in_place"), "closed_loop_pipelined_env_steps_per_s": out5.get("pipelined"),
+                    "errors": {k: v for k, v in out5.items() if k.endswith("_error")},
                     "how": "10 closed-loop steps of every group captured as one CUDA graph (4 streams, 2-3 kernels per group and step)",
-                    "eager_env_steps_per_s": {"in_place": out5["in_place_eager"], "pipelined": out5["pipelined_eager"],
+                    "eager_env_steps_per_s": {"in_place": out5.get("in_place_eager"), "pipelined": out5.get("pipelined_eager"),
                                               "note": "host-bound: ~8 library calls and 8 stream joins per population step"},
                     "bytes_per_env_step": b5,
-                    "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": out5["pipelined"] * b5 / 1e9, "peak": peak,
-                                 "frac": out5["pipelined"] * b5 / 1e9 / peak,
-                                 "in_place_frac": out5["in_place"] * b5 / 1e9 / peak}}
+                    "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": (out5.get("pipelined") or 0) * b5 / 1e9, "peak": peak,
+                                 "frac": (out5.get("pipelined") or 0) * b5 / 1e9 / peak,
+                                 "in_place_frac": (out5.get("in_place") or 0) * b5 / 1e9 / peak}}
         except Exception as ex:
             cfg5 = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
     # ---- generic kernels (tables outside the specialised class; forced here with CZ_GENERIC=1 on the headline workload)
     generic = None
-    if rank == 0 and world == 1 and not args.no_cfg3:
+    if want("generic"):
         try:
             os.environ["CZ_GENERIC"] = "1"
             envg = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
@@ -597,7 +605,7 @@ def run_gpu_arm(args):
 
     # ---- closed loop with the device policy: CookingAgent decisions + step, no host in between
     cook = None
-    if rank == 0 and world == 1 and not args.no_cfg3:
+    if want("cook"):
         try:
             env.wait()
             torch.cuda.synchronize(dev)
@@ -649,7 +657,7 @@ def run_gpu_arm(args):
 
     # ---- float32 observation mode (reported separately; rows = the f64 rows rounded element-wise)
     f32 = None
-    if world == 1 and not args.no_cfg3:
+    if want("f32"):
         try:
             env.wait()
             torch.cuda.synchronize(dev)

@@ -733,6 +733,7 @@ struct cz_tables {
   cudaEvent_t ev_user, ev_dyn, ev_obs[2], ev_chunk[8];
   int split;                // in-place step of a large batch: column ranges whose dynamics run under the previous range's rows
   int pipe_ready, pipe_cur, pipe_obs_pending[2];
+  int pipe_steps;           // pipelined steps enqueued since the last cz_pipeline_reset (0: the internal streams hold nothing to wait for)
   int pipe_dyn_blocks;   // resident dynamics blocks per SM in the pipelined step (0 = no cap)
   size_t smem_optin;
 };
@@ -960,10 +961,10 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     const char* k = getenv("CZ_TWO_KERNEL_MIN_ENVS");
     t->two_kernel_min_envs = k ? atoi(k) : 49152;  // measured crossover between 32768 and 65536 (profiles/r01_two_kernel_sweep.txt)
     const char* sp = getenv("CZ_SPLIT");
-    t->split = sp ? atoi(sp) : 2;
+    t->split = sp ? atoi(sp) : 1;  // measured: every split is slower than the two plain launches (profiles/r02_notes.md)
     if (t->split > 8) t->split = 8;
     const char* w = getenv("CZ_WARP_MAX_ENVS");
-    t->warp_max_envs = w ? atoi(w) : 8192;
+    t->warp_max_envs = w ? atoi(w) : 6144;  // measured crossover of the per-launch times (profiles/r02_notes.md)
     const char* wk = getenv("CZ_WARP_K_MAX_ENVS");
     t->warp_k_max_envs = wk ? atoi(wk) : 32768;
     const char* wg = getenv("CZ_WARP_GROUP");  // 16 or 32 lanes per environment in the warp kernel (default: 16 when D <= 16)
@@ -1313,6 +1314,7 @@ extern "C" int cz_pipeline_reset(cz_tables* t, int current_half) {
   CZ_CUDA(cudaStreamSynchronize(t->pipe_obs));
   t->pipe_cur = current_half;
   t->pipe_obs_pending[0] = t->pipe_obs_pending[1] = 0;
+  t->pipe_steps = 0;
   return CZ_OK;
 }
 
@@ -1354,12 +1356,13 @@ extern "C" int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* 
   CZ_CUDA(cudaEventRecord(t->ev_obs[nxt], t->pipe_obs));
   t->pipe_obs_pending[nxt] = 1;
   t->pipe_cur = nxt;
+  t->pipe_steps += 1;
   return CZ_OK;
 }
 
 extern "C" int cz_pipeline_wait(cz_tables* t, void* stream) {
   if (!t) return cz_fail(CZ_EINVAL, "%s", "null argument");
-  if (!t->pipe_ready) return CZ_OK;
+  if (!t->pipe_ready || t->pipe_steps == 0) return CZ_OK;  // nothing enqueued since the reset (also keeps a stream capture legal)
   cudaStream_t user = (cudaStream_t)stream;
   CZ_CUDA(cudaEventRecord(t->ev_dyn, t->pipe_dyn));
   CZ_CUDA(cudaStreamWaitEvent(user, t->ev_dyn, 0));
@@ -1369,7 +1372,7 @@ extern "C" int cz_pipeline_wait(cz_tables* t, void* stream) {
 
 extern "C" int cz_pipeline_wait_state(cz_tables* t, void* stream) {
   if (!t) return cz_fail(CZ_EINVAL, "%s", "null argument");
-  if (!t->pipe_ready) return CZ_OK;
+  if (!t->pipe_ready || t->pipe_steps == 0) return CZ_OK;
   CZ_CUDA(cudaEventRecord(t->ev_dyn, t->pipe_dyn));
   CZ_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, t->ev_dyn, 0));
   return CZ_OK;
