@@ -338,7 +338,7 @@ def run_gpu_arm(args):
                 graph = torch.cuda.CUDAGraph()
                 l0 = env.lib.cz_launch_count()
                 with torch.cuda.stream(side):
-                    with torch.cuda.graph(graph, stream=side):
+                    with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
                         for s in range(K):
                             env.step(actions[s % ring])
                         env.wait()
@@ -490,7 +490,7 @@ def run_gpu_arm(args):
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                with torch.cuda.graph(graph, stream=side):
+                with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
                     for s in range(16):
                         env3.step(act3[s])
             torch.cuda.current_stream(dev).wait_stream(side)
@@ -547,7 +547,7 @@ def run_gpu_arm(args):
                         for grp in mix.groups.values():
                             _native.check(grp.lib.cz_pipeline_reset(grp._handle, grp.lib.cz_pipeline_current(grp._handle)))
                     with torch.cuda.stream(side):
-                        with torch.cuda.graph(graph5, stream=side):
+                        with torch.cuda.graph(graph5, stream=side, capture_error_mode="thread_local"):
                             for _ in range(10):
                                 mix.cook_step()
                             mix.wait()
