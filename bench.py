@@ -741,7 +741,16 @@ def run_gpu_arm(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step)",
                         "host_link_gbs": (h2d + d2h) * e2e_value / N / 1e9 / world,
+                        "limiter": "the host link: the device->host copy of the rows is > 99 % of the call (kernels: 0.11 ms of "
+                                   "~11 ms), so overlapping or chunking the call can recover < 1 %; with several GPUs the copies "
+                                   "share the host's PCIe root / memory system (host_link_gbs is per GPU)",
                         "numa_node_of_rank0": numa_node},
+                "e2e_f32": None if not f32 or "error" in f32 else {
+                    "value": f32["e2e_env_steps_per_s"], "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": f32["d2h_bytes_per_step"],
+                    "note": "the same call with float32 rows (CZ_STEP_OBS_F32: the float64 rows rounded element-wise, what a "
+                            "float32 learner does with the reference's rows): half the bytes over the host link; the "
+                            "headline e2e stays float64, the reference's dtype"},
                 "gpu_launches": int(launches), "timed_region": how_timed, "clocks": clocks, "cfg3": cfg3, "cfg5": cfg5,
                 "generic_tables": generic, "device_policy": cook, "f32_obs": f32,
                 "mode": args.mode,

@@ -6,7 +6,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "cz_kernels.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "cz_device.cuh"), os.path.join(HERE, "csrc", "cz_policy.cuh"), os.path.join(os.path.dirname(HERE), "include", "cz_b200.h")]
+def _deps():
+    """every file of csrc/ plus the public header: editing any of them triggers a rebuild"""
+    import glob
+    return sorted(glob.glob(os.path.join(HERE, "csrc", "*"))) + [os.path.join(os.path.dirname(HERE), "include", "cz_b200.h")]
+
+
+DEPS = _deps()
 LIB = os.path.join(HERE, "libcz_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

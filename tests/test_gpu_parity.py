@@ -251,6 +251,49 @@ def test_large_batch_two_kernel_step_equals_the_fused_kernel_on_a_ragged_batch(m
     assert torch.equal(a.state, b.state)
 
 
+def test_pipelined_masked_reset_after_an_odd_number_of_steps_and_staged_actions():
+    """a masked reset in pipelined mode must land in the ping-pong half that holds the current state and must
+    not race the internal streams; host-side (numpy) actions go through the staging buffer, which a running dynamics kernel
+    may still be reading unless the caller's stream trails it.  Compared step by step with the in-place environment."""
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=50,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    n = 20011
+    a = _make(n, cfg, seed=3, layout_pool_size=64)
+    b = _make(n, cfg, seed=3, layout_pool_size=64, pipelined=True)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(5)
+
+    def both(act):
+        oa, ra, ta, ua, _ = a.step(act)
+        ob, rb, tb, ub, _ = b.step(act)
+        b.wait()
+        assert torch.equal(oa.view(torch.int64), ob.view(torch.int64))
+        assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(ta, tb) and torch.equal(ua, ub)
+        assert torch.equal(a.state, b.state)
+
+    for t in range(3):                                    # odd: the current state sits in the second half
+        both(rng.integers(0, 5, size=(n, 2)).astype(np.uint8))            # numpy actions -> staging buffer
+    mask = torch.from_numpy(rng.random(n) < 0.3)
+    lids = a.default_layout_ids(1)
+    oa = a.reset(layout_ids=lids, mask=mask)
+    ob = b.reset(layout_ids=lids, mask=mask)
+    assert torch.equal(oa.view(torch.int64), ob.view(torch.int64)) and torch.equal(a.state, b.state)
+    for t in range(4):
+        both(rng.integers(0, 5, size=(n, 2)).astype(np.uint8))
+    a.reset(); b.reset()                                  # full reset after an even + odd mix
+    for t in range(3):
+        both(torch.from_numpy(rng.integers(0, 5, size=(n, 2)).astype(np.uint8)).cuda())
+    # back-to-back pipelined steps from host arrays with no wait in between: the staging copy of step k+1 is ordered after
+    # the dynamics of step k (cz_step_pipelined makes the caller's stream trail them)
+    acts = [rng.integers(0, 5, size=(n, 2)).astype(np.uint8) for _ in range(6)]
+    for act in acts:
+        b.step(act)
+    b.wait()
+    for act in acts:
+        a.step(act)
+    assert torch.equal(a.state, b.state) and torch.equal(a.obs.view(torch.int64), b.obs.view(torch.int64))
+
+
 @pytest.mark.parametrize("split", ["2", "3", "8"])
 def test_split_in_place_step_equals_the_unsplit_step(split, monkeypatch):
     """in-place steps of >= 98304 environments run as column ranges (dynamics of range c+1 under the rows of range c,
