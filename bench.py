@@ -35,6 +35,7 @@ BOOK = ["TomatoSalad", "TomatoLettuceSalad", "CarrotBanana", "MashedCarrotBanana
         "AppleWatermelon", "TomatoLettuceOnionSalad", "no_recipe"]
 METRIC = "env-steps/sec (batched step+feature_vector obs)"
 UNIT = "env-steps/s"
+BACKGROUND_DYN_BLOCKS = 3     # pipelined headline: the dynamics kernel of step k+1 runs as 3 blocks per SM behind the rows of step k
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
@@ -321,7 +322,8 @@ def run_gpu_arm(args):
         Every step is a full cz_step / cz_step_pipelined with its own resident action tensor; nothing is skipped."""
         env = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
                                 device=str(dev), recipe_pool=BOOK, layout_pool_size="auto", layout_seed=0,
-                                auto_reset=True, seed=2026, env_offset=rank * N, pipelined=pipelined, obs_dtype=obs_dtype)
+                                auto_reset=True, seed=2026, env_offset=rank * N, pipelined=pipelined, obs_dtype=obs_dtype,
+                                background_dynamics=BACKGROUND_DYN_BLOCKS if pipelined else 0)
         env.reset(recipe_ids=recipe_ids)
         for s in range(args.warmup):
             env.step(actions[s % ring])
@@ -735,7 +737,8 @@ def run_gpu_arm(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "bytes_per_env_step": bytes_per_env_step,
-                             "kernel": ("cz_obs_envs_kernel (+ cz_env_kernel<STEP,dynamics-only> overlapped)"
+                             "kernel": (f"cz_obs_envs_kernel (+ cz_env_kernel<STEP,dynamics-only> of the next step in the background, "
+                                        f"{BACKGROUND_DYN_BLOCKS} blocks per SM)"
                                         if args.mode == "pipelined" else "cz_obs_envs_kernel (after cz_env_kernel<STEP,dynamics-only> on the same stream)")},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -778,8 +781,9 @@ def main():
     ap.add_argument("--no-cfg3", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph of the K steps")
     ap.add_argument("--mode", default="pipelined", choices=["pipelined", "sync"],
-                    help="pipelined (default): throughput mode, the dynamics of step k+1 overlap the observation "
-                         "writes of step k (two kernels, two streams, ping-pong state); sync: one fused kernel per step")
+                    help="pipelined (default): throughput mode for open-loop action streams, the dynamics of step k+1 run in "
+                         "the background of the observation writes of step k (two kernels, two streams, ping-pong state, "
+                         "cz_pipeline_config); sync: the in-place step (dynamics kernel, then the row writer)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 6000

@@ -40,7 +40,8 @@ class BatchedCookingEnv:
                  obs_spaces=None, end_condition_all_dishes=False, action_scheme="scheme1", render=False,
                  reward_scheme=None, agent_respawn_rate=0.0, grace_period=20, agent_despawn_rate=0.0, *,
                  device="cuda:0", recipe_pool=None, layout_pool_size="auto", layout_seed=0, layouts=None,
-                 auto_reset=False, seed=0, env_offset=0, pipelined=False, obs_dtype=torch.float64, stream=None):
+                 auto_reset=False, seed=0, env_offset=0, pipelined=False, obs_dtype=torch.float64, stream=None,
+                 pipeline_buffers=2, background_dynamics=0):
         obs_spaces = obs_spaces or ["feature_vector"] * num_agents
         if any(o != "feature_vector" for o in obs_spaces):
             raise NotImplementedError("the batched entry point builds feature_vector observations only "
@@ -72,8 +73,13 @@ class BatchedCookingEnv:
         dev = self.device
         # pipelined throughput mode: two state matrices (ping-pong), see cz_step_pipelined in cz_b200.h
         self.pipelined = bool(pipelined)
-        self._state2 = torch.zeros((2 if self.pipelined else 1, t.rows, N), dtype=torch.int32, device=dev)
+        # pipeline_buffers (2..4) state matrices; background_dynamics = blocks per SM of the dynamics kernel (0: full grid).
+        # With a small grid the dynamics run behind the row writer of the previous steps (cz_pipeline_config): the
+        # throughput setting for open-loop action streams, not for policies that need this step's state at once.
+        self._state2 = torch.zeros((int(pipeline_buffers) if self.pipelined else 1, t.rows, N), dtype=torch.int32, device=dev)
         self.state = self._state2[0]
+        if self.pipelined and (int(pipeline_buffers) != 2 or int(background_dynamics) != 0):
+            _native.check(self.lib.cz_pipeline_config(self._handle, int(pipeline_buffers), int(background_dynamics)))
         # float32 observations: the float64 rows rounded element-wise (reference obs.astype(np.float32)), written
         # directly by their own kernel — half the bytes of the default
         if obs_dtype not in (torch.float64, torch.float32):

@@ -730,11 +730,13 @@ struct cz_tables {
   int scratch_envs;
   // pipelined step: dynamics on a high-priority stream, observations on a second one, ping-pong state
   cudaStream_t pipe_dyn, pipe_obs;
-  cudaEvent_t ev_user, ev_dyn, ev_obs[2], ev_chunk[8];
+  cudaEvent_t ev_user, ev_dyn, ev_obs[4], ev_chunk[8];
   int split;                // in-place step of a large batch: column ranges whose dynamics run under the previous range's rows
-  int pipe_ready, pipe_cur, pipe_obs_pending[2];
+  int pipe_ready, pipe_cur, pipe_obs_pending[4];
+  int pipe_buffers;         // state matrices of the pipelined step's ring (2..4, cz_pipeline_config)
   int pipe_steps;           // pipelined steps enqueued since the last cz_pipeline_reset (0: the internal streams hold nothing to wait for)
-  int pipe_dyn_blocks;   // resident dynamics blocks per SM in the pipelined step (0 = no cap)
+  int pipe_dyn_blocks;   // blocks per SM the dynamics kernel of the pipelined step is launched with (0 = no cap): a small grid that
+                         // loops over its tiles runs in the background of the row writer instead of displacing it
   size_t smem_optin;
 };
 
@@ -807,6 +809,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   {
     const char* pb = getenv("CZ_PIPE_DYN_BLOCKS");
     t->pipe_dyn_blocks = pb ? atoi(pb) : 0;
+    t->pipe_buffers = 2;
   }
   const char* p = getenv("CZ_OBS_PATH");
   t->obs_path = (p && !strcmp(p, "stg")) ? OBS_STG : OBS_TMA;
@@ -1004,7 +1007,8 @@ extern "C" int cz_tables_destroy(cz_tables* t) {
   delete[] t->h_layout_cum;
   if (t->pipe_ready) {
     cudaStreamDestroy(t->pipe_dyn); cudaStreamDestroy(t->pipe_obs);
-    cudaEventDestroy(t->ev_user); cudaEventDestroy(t->ev_dyn); cudaEventDestroy(t->ev_obs[0]); cudaEventDestroy(t->ev_obs[1]);
+    cudaEventDestroy(t->ev_user); cudaEventDestroy(t->ev_dyn);
+    for (int c = 0; c < 4; ++c) cudaEventDestroy(t->ev_obs[c]);
     for (int c = 0; c < 8; ++c) cudaEventDestroy(t->ev_chunk[c]);
   }
   delete t;
@@ -1035,7 +1039,7 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
                      const int32_t* layout_ids,
                      const uint8_t* recipe_ids, const uint8_t* mask, double* obs, double* reward, uint8_t* term,
                      uint8_t* trunc, uint32_t* err, int n_envs, uint32_t flags, uint64_t seed, int64_t env_offset,
-                     void* stream, int ld = 0) {
+                     void* stream, int ld = 0, int blocks_per_sm = 0) {
   if (ld <= 0) ld = n_envs;
   if (!t || !state || !state_out) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (MODE == MODE_OBSERVE && !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
@@ -1043,14 +1047,11 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
   if (!obs) dyn_only = true;  // no observation buffer: dynamics / reset only
   if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
   size_t smem = cz_smem_bytes(t->dev);
-  if (dyn_only && t->pipe_dyn_blocks > 0) {
-    // pipelined step: pad the dynamics kernel's shared memory so that only `pipe_dyn_blocks` of its
-    // blocks fit on an SM and the observation kernel of the previous step keeps the rest of the SM
-    size_t want = (size_t)(227 * 1024) / t->pipe_dyn_blocks - 1024;
-    if (want > smem && want <= t->smem_optin) smem = want;
-  }
   const int ts = cz_tile_shift(t, n_envs);
   int grid = cz_grid(t, n_envs, ts);
+  // background dynamics of the pipelined step: a grid of `blocks_per_sm` blocks per SM walks the tiles in its
+  // persistent loop, so the kernel keeps a few warp slots for a long time instead of half of every SM for a short one
+  if (blocks_per_sm > 0 && grid > t->num_sms * blocks_per_sm) grid = t->num_sms * blocks_per_sm;
   flags = (flags & ~(7u << CZ_FLAG_TILE_SHIFT)) | ((uint32_t)ts << CZ_FLAG_TILE_SHIFT);
   cudaStream_t s = (cudaStream_t)stream;
 #define CZ_GO(O, NA)                                                                                                  \
@@ -1295,25 +1296,36 @@ static int cz_pipe_init(cz_tables* t) {
   if (t->pipe_ready) return CZ_OK;
   int lo = 0, hi = 0;
   CZ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  CZ_CUDA(cudaStreamCreateWithPriority(&t->pipe_dyn, cudaStreamNonBlocking, hi));  // highest priority: slips in between observe blocks
-  CZ_CUDA(cudaStreamCreateWithPriority(&t->pipe_obs, cudaStreamNonBlocking, lo));
+  const char* sw = getenv("CZ_PIPE_PRIO");  // "swap": row writer above the dynamics, "equal": same priority (A/B only)
+  const int p_dyn = (sw && !strcmp(sw, "swap")) ? lo : hi, p_obs = (sw && !strcmp(sw, "swap")) ? hi : ((sw && !strcmp(sw, "equal")) ? hi : lo);
+  CZ_CUDA(cudaStreamCreateWithPriority(&t->pipe_dyn, cudaStreamNonBlocking, p_dyn));  // highest priority: slips in between observe blocks
+  CZ_CUDA(cudaStreamCreateWithPriority(&t->pipe_obs, cudaStreamNonBlocking, p_obs));
   CZ_CUDA(cudaEventCreateWithFlags(&t->ev_user, cudaEventDisableTiming));
   CZ_CUDA(cudaEventCreateWithFlags(&t->ev_dyn, cudaEventDisableTiming));
-  CZ_CUDA(cudaEventCreateWithFlags(&t->ev_obs[0], cudaEventDisableTiming));
-  CZ_CUDA(cudaEventCreateWithFlags(&t->ev_obs[1], cudaEventDisableTiming));
+  for (int c = 0; c < 4; ++c) CZ_CUDA(cudaEventCreateWithFlags(&t->ev_obs[c], cudaEventDisableTiming));
   for (int c = 0; c < 8; ++c) CZ_CUDA(cudaEventCreateWithFlags(&t->ev_chunk[c], cudaEventDisableTiming));
   t->pipe_ready = 1;
   return CZ_OK;
 }
 
+extern "C" int cz_pipeline_config(cz_tables* t, int n_buffers, int dyn_blocks_per_sm) {
+  if (!t || n_buffers < 2 || n_buffers > 4 || dyn_blocks_per_sm < 0 || dyn_blocks_per_sm > 8)
+    return cz_fail(CZ_EINVAL, "%s", "cz_pipeline_config: 2..4 buffers, 0..8 dynamics blocks per SM");
+  int rc = cz_pipeline_reset(t, 0);  // drains the internal streams
+  if (rc != CZ_OK) return rc;
+  t->pipe_buffers = n_buffers;
+  t->pipe_dyn_blocks = dyn_blocks_per_sm;
+  return CZ_OK;
+}
+
 extern "C" int cz_pipeline_reset(cz_tables* t, int current_half) {
-  if (!t || (current_half != 0 && current_half != 1)) return cz_fail(CZ_EINVAL, "%s", "bad argument");
+  if (!t || current_half < 0 || current_half >= (t->pipe_buffers ? t->pipe_buffers : 2)) return cz_fail(CZ_EINVAL, "%s", "bad argument");
   int rc = cz_pipe_init(t);
   if (rc != CZ_OK) return rc;
   CZ_CUDA(cudaStreamSynchronize(t->pipe_dyn));
   CZ_CUDA(cudaStreamSynchronize(t->pipe_obs));
   t->pipe_cur = current_half;
-  t->pipe_obs_pending[0] = t->pipe_obs_pending[1] = 0;
+  for (int c = 0; c < 4; ++c) t->pipe_obs_pending[c] = 0;
   t->pipe_steps = 0;
   return CZ_OK;
 }
@@ -1328,7 +1340,7 @@ extern "C" int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* 
   int rc = cz_pipe_init(t);
   if (rc != CZ_OK) return rc;
   const size_t half = (size_t)t->dev.rows * n_envs;
-  const int cur = t->pipe_cur, nxt = cur ^ 1;
+  const int cur = t->pipe_cur, nxt = (cur + 1) % t->pipe_buffers;
   uint32_t* in = state2 + (size_t)cur * half;
   uint32_t* out = state2 + (size_t)nxt * half;
   cudaStream_t user = (cudaStream_t)stream;
@@ -1338,7 +1350,7 @@ extern "C" int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* 
   // the observe kernel that read the half we are about to overwrite must be done
   if (t->pipe_obs_pending[nxt]) CZ_CUDA(cudaStreamWaitEvent(t->pipe_dyn, t->ev_obs[nxt], 0));
   rc = cz_launch<MODE_STEP>(t, in, out, true, actions, nullptr, nullptr, nullptr, obs, reward, terminated, truncated,
-                            error_flags, n_envs, flags, seed, env_offset, t->pipe_dyn);
+                            error_flags, n_envs, flags, seed, env_offset, t->pipe_dyn, 0, t->pipe_dyn_blocks);
   if (rc != CZ_OK) return rc;
   CZ_CUDA(cudaEventRecord(t->ev_dyn, t->pipe_dyn));
   CZ_CUDA(cudaStreamWaitEvent(t->pipe_obs, t->ev_dyn, 0));

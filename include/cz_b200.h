@@ -217,7 +217,7 @@ int cz_layout_index(const cz_tables* t, uint64_t seed, uint64_t global_env, uint
 double cz_spawn_uniform(uint64_t seed, uint64_t global_env, uint64_t episode, uint64_t t, uint64_t c);
 
 /* Pipelined throughput mode (specialised kernels only).  `state2` is TWO state matrices back to back
- * ([2][rows][n]); step k+1's dynamics (cooking_world.world_step + compute_rewards) run on an internal
+ * ([2][rows][n]; more after cz_pipeline_config); step k+1's dynamics (cooking_world.world_step + compute_rewards) run on an internal
  * high-priority stream reading one half and writing the other, while the observation writer
  * (get_feature_vector) of step k is still streaming out on a second internal stream.  Every step does
  * the full work of cz_step; only the ordering guarantee changes: the caller's stream is ordered after the
@@ -229,6 +229,13 @@ double cz_spawn_uniform(uint64_t seed, uint64_t global_env, uint64_t episode, ui
 int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* actions, double* obs, double* reward,
                       uint8_t* terminated, uint8_t* truncated, uint32_t* error_flags, int n_envs,
                       uint32_t flags, uint64_t seed, int64_t env_offset, void* stream);
+/* Ring size and background dynamics of the pipelined step (call while nothing is in flight; it drains like
+ * cz_pipeline_reset and selects buffer 0).  n_buffers (2..4): `state2` then holds that many state matrices and the dynamics
+ * may run n_buffers - 1 steps ahead of the row writer.  dyn_blocks_per_sm (0..8, 0 = full grid): the dynamics kernel is
+ * launched with that many blocks per SM and loops over its tiles, so it runs in the background of the row writer of the
+ * previous step(s) instead of displacing it — right for open-loop action streams (the step's latency grows), wrong when
+ * the next actions depend on this step's state. */
+int cz_pipeline_config(cz_tables* t, int n_buffers, int dyn_blocks_per_sm);
 int cz_pipeline_wait(cz_tables* t, void* stream);
 /* Order the caller's stream after the latest dynamics only (state, rewards, flags are final; the observation
  * rows of that step may still be streaming out): what a device policy reading the state needs. */

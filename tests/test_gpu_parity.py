@@ -165,12 +165,14 @@ def test_auto_reset_and_shard_independence():
                 assert_obs_equal(np.stack([orc.observe(i) for i in range(2)]), o[k].cpu().numpy(), f"autoreset env {k}")
 
 
+@pytest.mark.parametrize("ring", [(2, 0), (3, 2), (4, 1)], ids=["pingpong", "ring3_bg2", "ring4_bg1"])
 @pytest.mark.parametrize("level,agents", [("coop_test", 2), ("switch_test", 2), ("coexistence_test", 2),
                                           ("open4", 3), ("open4", 4)])
-def test_pipelined_step_is_bit_identical_to_the_in_place_step(level, agents):
-    """throughput mode (cz_step_pipelined: two streams, ping-pong state) does the same work as cz_step;
+def test_pipelined_step_is_bit_identical_to_the_in_place_step(level, agents, ring):
+    """throughput mode (cz_step_pipelined: two streams, a ring of state matrices) does the same work as cz_step;
     switch_test adds live Switch / Block slots to the observation writer, coexistence_test 16 static variants,
-    the open kitchen with 3-4 agents the two-pairs-per-lane writer"""
+    the open kitchen with 3-4 agents the two-pairs-per-lane writer.  ring = (state matrices, dynamics blocks per SM):
+    with a small dynamics grid the kernel loops over its tiles in the background of the row writer (cz_pipeline_config)"""
     import os
     from tests.replay import ROOT
     cfg = dict(level=level, meta_file="example", num_agents=agents, max_steps=30,
@@ -179,9 +181,10 @@ def test_pipelined_step_is_bit_identical_to_the_in_place_step(level, agents):
     if level == "open4":
         cfg.update(level=os.path.join(ROOT, "tests/golden/levels/open4.json"),
                    meta_file=os.path.join(ROOT, "tests/golden/levels/meta4.json"))
-    n = 5000
+    n = 5000 if ring[1] == 0 else 50011          # the capped grid only differs from the full one on a large batch
     a = _make(n, cfg, auto_reset=True, seed=3, layout_pool_size=64)
-    b = _make(n, cfg, auto_reset=True, seed=3, layout_pool_size=64, pipelined=True)
+    b = _make(n, cfg, auto_reset=True, seed=3, layout_pool_size=64, pipelined=True, pipeline_buffers=ring[0],
+              background_dynamics=ring[1])
     a.reset(); b.reset()
     rng = np.random.default_rng(1)
     for t in range(70):
