@@ -69,6 +69,7 @@ SIGNATURES = {
     "cz_pipeline_current": (C.c_int, [_P]),
     "cz_policy_create": (C.c_int, [_P, C.POINTER(PolicyDesc), C.POINTER(_P)]),
     "cz_policy_destroy": (C.c_int, [_P]),
+    "cz_policy_config": (C.c_int, [_P, C.c_int]),
     "cz_policy_act": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     "cz_random_actions": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _P]),
     "cz_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint64, C.c_int64, _P]),

@@ -41,7 +41,7 @@ class BatchedCookingEnv:
                  reward_scheme=None, agent_respawn_rate=0.0, grace_period=20, agent_despawn_rate=0.0, *,
                  device="cuda:0", recipe_pool=None, layout_pool_size="auto", layout_seed=0, layouts=None,
                  auto_reset=False, seed=0, env_offset=0, pipelined=False, obs_dtype=torch.float64, stream=None,
-                 pipeline_buffers=2, background_dynamics=0):
+                 pipeline_buffers=2, background_dynamics=0, background_policy=0):
         obs_spaces = obs_spaces or ["feature_vector"] * num_agents
         if any(o != "feature_vector" for o in obs_spaces):
             raise NotImplementedError("the batched entry point builds feature_vector observations only "
@@ -51,6 +51,7 @@ class BatchedCookingEnv:
                                       "in the reference itself, action_scheme2.py:15)")
         if render:
             raise NotImplementedError("rendering is out of scope")
+        self.background_policy = int(background_policy)    # blocks per SM of the device cook's kernel (0: one wave)
         self.stream = stream                    # a torch.cuda.Stream every call is enqueued on (default: torch's current stream)
         self.lib = _native.load_library()       # raises when the CUDA library is missing
         if not torch.cuda.is_available():
@@ -260,6 +261,8 @@ class BatchedCookingEnv:
             handle = C.c_void_p()
             _native.check(self.lib.cz_policy_create(self._handle, C.byref(desc), C.byref(handle)))
             self._policy = handle
+            if self.background_policy:
+                _native.check(self.lib.cz_policy_config(handle, self.background_policy))
             self.cook_actions = torch.zeros((N, A), dtype=torch.uint8, device=self.device)
             self.cook_crashed = torch.zeros((N,), dtype=torch.uint8, device=self.device)
         rid = None

@@ -256,8 +256,9 @@ cz_policy_kernel(const __grid_constant__ CzDev T, const __grid_constant__ CzPoli
   uint32_t* col = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * (D + A) * OSTRIDE + lane;
   uint32_t* ag = col + D * OSTRIDE;
   const size_t N = (size_t)n_envs;
-  const int env = blockIdx.x * CZ_POLICY_THREADS + threadIdx.x;
-  if (env >= n_envs) return;
+  // a grid smaller than the batch (cz_policy_config: background policy of the pipelined closed loop) walks it in strides
+#pragma unroll 1
+  for (int env = blockIdx.x * CZ_POLICY_THREADS + threadIdx.x; env < n_envs; env += gridDim.x * CZ_POLICY_THREADS) {
   for (int s = 0; s < D + A; ++s) cz_cp_async4(col + s * OSTRIDE, state + (size_t)s * N + env);
   const uint32_t* misc = state + (size_t)(D + A) * N;
   const uint32_t variant = misc[(size_t)CZ_ROW_VARIANT * N + env];
@@ -275,11 +276,13 @@ cz_policy_kernel(const __grid_constant__ CzDev T, const __grid_constant__ CzPoli
     actions[(size_t)env * A + i] = (uint8_t)(crash ? 0u : act);
   }
   if (crashed) crashed[env] = (uint8_t)bad;
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------
 struct cz_policy {
   const cz_tables* tables;
+  int blocks_per_sm;  // 0: one thread per environment in one wave; > 0: a grid of that many blocks per SM loops over the batch
   CzPolicyDev dev;
   void* allocs[4];
   int n_allocs;
@@ -319,6 +322,7 @@ extern "C" int cz_policy_create(const cz_tables* t, const cz_policy_desc* d, cz_
   if (!p) return cz_fail(CZ_EINVAL, "%s", "out of host memory");
   p->tables = t;
   p->n_allocs = 0;
+  p->blocks_per_sm = 0;
   int rc = pol_upload(p, d->lists, V * 8 * 64, &p->dev.lists);
   if (rc == CZ_OK) rc = pol_upload(p, d->list_len, V * 8, &p->dev.list_len);
   if (rc == CZ_OK) rc = pol_upload(p, d->reach, V * 64, &p->dev.reach);
@@ -331,6 +335,12 @@ extern "C" int cz_policy_create(const cz_tables* t, const cz_policy_desc* d, cz_
   return CZ_OK;
 }
 
+extern "C" int cz_policy_config(cz_policy* p, int blocks_per_sm) {
+  if (!p || blocks_per_sm < 0 || blocks_per_sm > 16) return cz_fail(CZ_EINVAL, "%s", "cz_policy_config: 0..16 blocks per SM");
+  p->blocks_per_sm = blocks_per_sm;
+  return CZ_OK;
+}
+
 extern "C" int cz_policy_act(const cz_policy* p, const uint32_t* state, const uint8_t* cook_recipes, uint8_t* actions,
                              uint8_t* crashed, int n_envs, void* stream) {
   if (!p || !state || !actions) return cz_fail(CZ_EINVAL, "%s", "null argument");
@@ -338,7 +348,8 @@ extern "C" int cz_policy_act(const cz_policy* p, const uint32_t* state, const ui
   if (n_envs == 0) return CZ_OK;
   const CzDev& T = p->tables->dev;
   const size_t smem = (size_t)(CZ_POLICY_THREADS / 32) * (T.D + T.A) * OSTRIDE * 4;
-  const int blocks = (n_envs + CZ_POLICY_THREADS - 1) / CZ_POLICY_THREADS;
+  int blocks = (n_envs + CZ_POLICY_THREADS - 1) / CZ_POLICY_THREADS;
+  if (p->blocks_per_sm > 0 && blocks > p->tables->num_sms * p->blocks_per_sm) blocks = p->tables->num_sms * p->blocks_per_sm;
   cz_policy_kernel<<<blocks, CZ_POLICY_THREADS, smem, (cudaStream_t)stream>>>(T, p->dev, state, cook_recipes, actions, crashed,
                                                                               n_envs);
   g_launches.fetch_add(1);

@@ -262,6 +262,10 @@ typedef struct cz_policy_desc {
 typedef struct cz_policy cz_policy;
 int cz_policy_create(const cz_tables* t, const cz_policy_desc* desc, cz_policy** out);
 int cz_policy_destroy(cz_policy* p);
+/* blocks_per_sm > 0: cz_policy_act launches that many blocks per SM and walks the batch in strides (a background policy
+ * for the pipelined closed loop: it shares the SMs with the row writer of the previous step instead of displacing it);
+ * 0 (default): one thread per environment in one wave. */
+int cz_policy_config(cz_policy* p, int blocks_per_sm);
 
 /* One CookingAgent.step per agent of every environment, on the CURRENT state.
  * cook_recipes u8 [n][A]: recipe-book index each cook follows, or NULL (cook i follows recipe i of

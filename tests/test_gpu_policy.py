@@ -224,3 +224,20 @@ def test_pipelined_closed_loop_equals_in_place_closed_loop():
             assert torch.equal(oa.view(torch.int64), ob.view(torch.int64)) and torch.equal(ra, rb), t
     b.wait()
     assert torch.equal(a.state, b.state)
+
+
+def test_strided_policy_grid_gives_the_same_decisions():
+    """cz_policy_config: a grid of b blocks per SM that walks the batch in strides (background policy; measured and not
+    used by default, profiles/r02_notes.md) decides exactly like the one-thread-per-environment launch"""
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=400,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    n = 70001
+    a = _make(n, cfg, seed=4, layout_pool_size=64)
+    b = _make(n, cfg, seed=4, layout_pool_size=64, background_policy=1)
+    a.reset(); b.reset()
+    for t in range(12):
+        act_a, cr_a = a.heuristic_actions()
+        act_b, cr_b = b.heuristic_actions()
+        assert torch.equal(act_a, act_b) and torch.equal(cr_a, cr_b), t
+        a.step(act_a); b.step(act_b)
+    assert torch.equal(a.state, b.state)
