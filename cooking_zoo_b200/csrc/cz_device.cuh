@@ -468,13 +468,16 @@ __device__ __noinline__ uint32_t cz_recipe_marks_of(const CzDev& T, const uint32
     m[k] = 0;
     if (k < n) {
       const uint32_t node = TAB_RNODE(rid, k);
-      uint64_t mask = (node & 256u) ? TAB_SMASK(e.variant, node & 7u) : cz_node_mask(e.o, TAB_RSPAN(rid, k));
       const uint32_t kids = node >> 16;
+      uint64_t mask = ~0ull;
       if (kids) {  // leaves (most nodes) skip the child loop
 #pragma unroll
         for (int j = k + 1; j < CZ_MAX_NODES; ++j)
           if (kids & (1u << j)) mask &= m[j];
       }
+      // a node whose children are not all satisfied at some common cell cannot be marked whatever lies on its own
+      // cells: its slots are only looked at when the children leave a candidate cell (most steps: none)
+      if (mask) mask &= (node & 256u) ? TAB_SMASK(e.variant, node & 7u) : cz_node_mask(e.o, TAB_RSPAN(rid, k));
       m[k] = mask;
       if (mask) marks |= 1u << k;
     }
