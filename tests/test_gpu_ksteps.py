@@ -166,3 +166,88 @@ def test_single_steps_of_small_batches_take_the_warp_kernel_and_ragged_sizes_wor
             assert torch.equal(ol.view(torch.int64), ow.view(torch.int64)), (n, t)
             assert torch.equal(rl.view(torch.int64), rw.view(torch.int64)) and torch.equal(tl, tw) and torch.equal(ul, uw)
         assert torch.equal(lane.state, warp.state)
+
+
+def _rich_level(rng, lp, mp):
+    """an 8x8 kitchen with many objects (more than 16 live dynamic slots: one environment per warp) and a meta file in
+    the order of example.json (packed observation plan: the specialised kernels)"""
+    import json
+    W = H = 8
+    rows = [["-"] * W] + [["-"] + [" "] * (W - 2) + ["-"] for _ in range(H - 2)] + [["-"] * W]
+    ring = [(x, 0) for x in range(1, W - 1)] + [(x, H - 1) for x in range(1, W - 1)] + \
+           [(0, y) for y in range(1, H - 1)] + [(W - 1, y) for y in range(1, H - 1)]
+    rng.shuffle(ring)
+    statics, need = [], {}
+    for name, count in (("Cutboard", 2), ("Blender", 1), ("Deliversquare", 2)):
+        for _ in range(count):
+            x, y = ring.pop()
+            statics.append({name: {"COUNT": 1, "X_POSITION": [x], "Y_POSITION": [y]}})
+            need[name] = need.get(name, 0) + 1
+    dyn = []
+    for name in ["Plate", "Tomato", "Onion", "Lettuce", "Carrot", "Banana", "Apple", "Watermelon", "Bread"]:
+        for _ in range(rng.randint(1, 3)):
+            if not ring:
+                break
+            x, y = ring.pop()
+            dyn.append({name: {"COUNT": 1, "X_POSITION": [x], "Y_POSITION": [y]}})
+            need[name] = need.get(name, 0) + 1
+    level = {"LEVEL_LAYOUT": "\n".join("".join(r) for r in rows), "STATIC_OBJECTS": statics, "DYNAMIC_OBJECTS": dyn,
+             "AGENTS": [{"MAX_COUNT": 4, "X_POSITION": list(range(1, W - 1)), "Y_POSITION": list(range(1, H - 1))}],
+             "DYNAMIC_EXCLUDED_POSITIONS": []}
+    json.dump(level, open(lp, "w"))
+    meta = []
+    for name in ["Cutboard", "Counter", "Blender", "Deliversquare", "Plate", "Tomato", "Onion", "Lettuce", "Carrot", "Banana",
+                 "Apple", "Watermelon", "Bread", "Agent", "Block", "Switch"]:
+        n = need.get(name, 0) + rng.randint(0, 1) + (need.get(name, 0) if name == "Bread" else 0)
+        n_counters = 2 * W + 2 * (H - 2) - sum(need.get(k, 0) for k in ("Cutboard", "Blender", "Deliversquare"))
+        meta.append({name: n_counters + rng.randint(0, 1) if name == "Counter" else (4 if name == "Agent" else n)})
+    json.dump(meta, open(mp, "w"))
+
+
+def test_k_steps_on_random_levels_and_meta_files(tmp_path, monkeypatch):
+    """the property-test generator of tests/test_oracle_vs_reference.py (random open kitchens up to 8x8, random meta
+    counts and order, OPTIONAL objects, 1-4 agents, both action schemes, despawn / respawn): K steps in one launch of the
+    warp kernel against K launches of the lane kernels, table classes and group widths as they fall"""
+    import random
+    from cooking_zoo_b200 import BatchedCookingEnv
+    from tests.test_oracle_vs_reference import _random_level, _random_meta
+    widths = set()
+    for seed in range(5000, 5024):
+        rng = random.Random(seed)
+        lp, mp = str(tmp_path / f"level_{seed}.json"), str(tmp_path / f"meta_{seed}.json")
+        if seed % 3 == 0:
+            level = _random_level(rng, lp)
+            _random_meta(rng, level, mp)
+            A = rng.randint(1, 4)
+        else:
+            _rich_level(rng, lp, mp)
+            A = rng.randint(1, 2)           # 3-4 agents x ~25 computed slots would leave the packed class
+        recipes = [BOOK[rng.randrange(8)] for _ in range(A)]
+        scheme = rng.choice(["scheme1", "scheme3"])
+        kw = dict(agent_respawn_rate=0.3, agent_despawn_rate=0.1, grace_period=1) if (seed & 1 and A > 1) else {}
+
+        def make():
+            e = BatchedCookingEnv(700, lp, mp, A, 25, recipes, end_condition_all_dishes=bool(seed & 2), action_scheme=scheme,
+                                  layout_pool_size=40, layout_seed=seed, auto_reset=True, seed=seed, **kw)
+            e.reset()
+            return e
+        monkeypatch.setenv("CZ_WARP_MAX_ENVS", "0")
+        lane = make()
+        monkeypatch.delenv("CZ_WARP_MAX_ENVS")
+        warp = make()
+        tb = warp.tables
+        if tb.num_agents * tb.num_comp_slots <= 64 and tb.num_obs_ranges == 1 and tb.obs_table_len <= 128 and tb.obs_len % 2 == 0:
+            widths.add(16 if lane.tables.num_dyn_slots <= 16 else 32)     # the warp kernel really ran
+        n_act = lane.tables.num_actions
+        for rd in range(3):
+            acts = _sticky_actions(12, 700, A, n_act, seed + rd)
+            obs, rew, term, trunc, _ = warp.step_k(12, actions=acts, keep_all=True)
+            for k in range(12):
+                o, r, te, tr, _ = lane.step(acts[k])
+                ctx = (seed, rd, k)
+                assert torch.equal(o.view(torch.int64), obs[k].view(torch.int64)), ctx
+                assert torch.equal(r.view(torch.int64), rew[k].view(torch.int64)), ctx
+                assert torch.equal(te, term[k]) and torch.equal(tr, trunc[k]), ctx
+            assert torch.equal(lane.state, warp.state) and torch.equal(lane.error_flags, warp.error_flags), (seed, rd)
+        lane.close(); warp.close()
+    assert widths == {16, 32}
