@@ -1350,7 +1350,8 @@ extern "C" int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* 
   // the observe kernel that read the half we are about to overwrite must be done
   if (t->pipe_obs_pending[nxt]) CZ_CUDA(cudaStreamWaitEvent(t->pipe_dyn, t->ev_obs[nxt], 0));
   rc = cz_launch<MODE_STEP>(t, in, out, true, actions, nullptr, nullptr, nullptr, obs, reward, terminated, truncated,
-                            error_flags, n_envs, flags, seed, env_offset, t->pipe_dyn, 0, t->pipe_dyn_blocks);
+                            error_flags, n_envs, flags, seed, env_offset, t->pipe_dyn, 0,
+                            t->pipe_steps == 0 ? 0 : t->pipe_dyn_blocks);  // nothing to hide behind on the first step: full grid
   if (rc != CZ_OK) return rc;
   CZ_CUDA(cudaEventRecord(t->ev_dyn, t->pipe_dyn));
   CZ_CUDA(cudaStreamWaitEvent(t->pipe_obs, t->ev_dyn, 0));

@@ -714,6 +714,15 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
   const int env = blockIdx.x * GROUPS + grp;
   BlockSmem* bs = reinterpret_cast<BlockSmem*>(smem_wk);
   const size_t head = cz_block_smem_head(T.V);
+  // everything that comes from global memory and does not depend on the block image is requested first, so that the
+  // state, the first step's actions and the image arrive in one round trip instead of three (a single-step launch is
+  // mostly prologue)
+  const bool live = env < n_envs;
+  const size_t N = (size_t)n_envs;
+  const int D = T.D;
+  const uint32_t rec0 = (live && g < D) ? __ldg(state + (size_t)g * N + env) : 0u;
+  const uint32_t misc0 = (live && g < NA + CZ_NUM_MISC_ROWS) ? __ldg(state + (size_t)(D + g) * N + env) : 0u;
+  uint32_t a_next = (live && actions && g < NA) ? actions[(size_t)env * NA + g] : 0u;
   for (int i = threadIdx.x; i < (int)(head / 16); i += 32 * WK_WARPS)
     reinterpret_cast<uint4*>(bs)[i] = __ldg(reinterpret_cast<const uint4*>(T.blob) + i);
   // (observer, slot) pairs of a row set: one word each, shared by the block
@@ -730,13 +739,12 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
 #pragma unroll 1
   for (int k = g; k < NA * stage2; k += G) stage[k] = make_double2(0.0, 0.0);  // never-occupied slots stay zero
   __syncthreads();
-  if (env >= n_envs) return;
+  if (!live) return;
 
   const SmemTabs* st = &bs->tabs;
   const double* sxl = bs->xlut + (T.W - 1);
   const double* syl = bs->ylut + (T.H - 1);
-  const int D = T.D, L2 = T.L >> 1, tab2 = T.tab_len >> 1;
-  const size_t N = (size_t)n_envs;
+  const int L2 = T.L >> 1, tab2 = T.tab_len >> 1;
   const uint64_t genv = (uint64_t)(env_offset + env);
 
   WEnv<NA, G> e;
@@ -749,10 +757,10 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
   e.plist = reinterpret_cast<uint2*>(wwords + 72);
   e.err = 0;
   // ---- state -> registers: lane g holds slot g; agents and the misc words are broadcast inside the group
-  e.rec = g < D ? __ldg(state + (size_t)g * N + env) : 0u;
+  e.rec = rec0;
   e.tf = g < D ? TAB_TF(g) : 0u;
   {
-    const uint32_t w = g < NA + CZ_NUM_MISC_ROWS ? __ldg(state + (size_t)(D + g) * N + env) : 0u;
+    const uint32_t w = misc0;
 #pragma unroll
     for (int i = 0; i < NA; ++i) e.ag[i] = g_shfl(e, w, i);
     e.sbits = g_shfl(e, w, NA + CZ_ROW_SBITS);
@@ -786,7 +794,8 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
     uint32_t a_mine = 0;
     if (g < NA) {
       if (actions) {
-        a_mine = actions[((size_t)k * N + env) * NA + g];
+        a_mine = a_next;  // requested one step ago: the load's latency hides behind a whole step
+        if (k + 1 < k_steps) a_next = actions[((size_t)(k + 1) * N + env) * NA + g];
       } else {
         const double u = cz_uniform(seed ^ CZ_ACTION_STREAM, genv, 0, action_step + (uint64_t)k, (uint64_t)g);
         const int a = (int)(u * num_actions);
