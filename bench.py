@@ -521,7 +521,7 @@ def run_gpu_arm(args):
     if want("cfg5"):
         try:
             from cooking_zoo_b200 import MixedAgentCookingEnv
-            n5 = 65536
+            n5 = args.cfg5_envs
             counts = (np.arange(n5) % 4) + 1
             lv5 = os.path.join(ROOT, "tests", "golden", "levels", "open4.json")
             mt5 = os.path.join(ROOT, "tests", "golden", "levels", "meta4.json")
@@ -570,6 +570,8 @@ def run_gpu_arm(args):
                     "closed_loop_env_steps_per_s": out5.get("in_place"), "closed_loop_pipelined_env_steps_per_s": out5.get("pipelined"),
                     "errors": {k: v for k, v in out5.items() if k.endswith("_error")},
                     "how": "10 closed-loop steps of every group captured as one CUDA graph (4 streams, 2-3 kernels per group and step)",
+                    "size_note": "four groups share the GPU, so the rate grows with the population: 65536 / 131072 / 262144 envs = "
+                                 "0.57 / 0.72 / 0.78 G env-steps/s (0.52 / 0.66 / 0.72 of roofline; profiles/r02_notes.md)",
                     "eager_env_steps_per_s": {"in_place": out5.get("in_place_eager"), "pipelined": out5.get("pipelined_eager"),
                                               "note": "host-bound: ~8 library calls and 8 stream joins per population step"},
                     "bytes_per_env_step": b5,
@@ -779,6 +781,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6000, help="oracle env-steps per host process for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true")
+    ap.add_argument("--cfg5-envs", type=int, default=262144, help="environments of the mixed-agent-count population (cfg5 block)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph of the K steps")
     ap.add_argument("--mode", default="pipelined", choices=["pipelined", "sync"],
                     help="pipelined (default): throughput mode for open-loop action streams, the dynamics of step k+1 run in "
