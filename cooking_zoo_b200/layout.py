@@ -10,6 +10,7 @@ Reference: cooking_zoo/cooking_world/engine/parsing.py:5-151 draws placements fr
      "objects": [[type, [[x, y]...]]...]   # world_objects insertion order, list order
      "agents": [[x, y]...], "agent_spawn": [[xs, ys]...]}
 """
+import math
 from fractions import Fraction
 
 from .entities import entity
@@ -148,9 +149,7 @@ def enumerate_layouts(level_object, meta, num_agents, max_layouts=4096):
     Raises TooManyLayouts when the tree has more than `max_layouts` leaves."""
     meta_count = dict(meta)
     lines = level_object["LEVEL_LAYOUT"].splitlines()
-    width, height = len(lines[-1]), len(lines)
-    for y, line in enumerate(lines):          # the reference takes the width from the last row (parsing.py:17)
-        width = len(line)
+    width, height = len(lines[-1]), len(lines)      # the reference takes the width from the last row (parsing.py:17)
     base_static = {}
     base_types = {}
     for y, line in enumerate(lines):
@@ -205,10 +204,9 @@ def enumerate_layouts(level_object, meta, num_agents, max_layouts=4096):
         if k == len(tasks):
             return finish(world, prob)
         kind, name, spec = tasks[k]
-        p_opt = Fraction(spec["OPTIONAL"]).limit_denominator(1 << 53) if "OPTIONAL" in spec and kind != "agent" else Fraction(1)
+        p_opt = Fraction(1)
         if "OPTIONAL" in spec and kind != "agent":
-            # `OPTIONAL <= random.random()` skips: random() is k / 2**53, so P(skip) = 1 - ceil(OPTIONAL * 2**53) / 2**53
-            import math
+            # `OPTIONAL <= random.random()` skips, and random() is k / 2**53: P(place) = ceil(OPTIONAL * 2**53) / 2**53
             p_opt = Fraction(min(max(math.ceil(Fraction(spec["OPTIONAL"]) * (1 << 53)), 0), 1 << 53), 1 << 53)
         static_at, dynamic_at, agents = world["static_at"], world["dynamic_at"], world["agents"]
         valid = {}
