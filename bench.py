@@ -744,10 +744,11 @@ def run_gpu_arm(args):
                                         if args.mode == "pipelined" else "cz_obs_envs_kernel (after cz_env_kernel<STEP,dynamics-only> on the same stream)")},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step)",
+                        "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step; four column ranges, the device->host copy of a range "
+                               "overlaps the kernels of the next: +0.7 % over one range, CZ_HOST_CHUNKS=1)",
                         "host_link_gbs": (h2d + d2h) * e2e_value / N / 1e9 / world,
                         "limiter": "the host link: the device->host copy of the rows is > 99 % of the call (kernels: 0.11 ms of "
-                                   "~11 ms), so overlapping or chunking the call can recover < 1 %; with several GPUs the copies "
+                                   "~11 ms), so chunking the call (done: four ranges) recovers < 1 %; with several GPUs the copies "
                                    "share the host's PCIe root / memory system (host_link_gbs is per GPU)",
                         "numa_node_of_rank0": numa_node},
                 "e2e_f32": None if not f32 or "error" in f32 else {

@@ -731,6 +731,7 @@ struct cz_tables {
   // pipelined step: dynamics on a high-priority stream, observations on a second one, ping-pong state
   cudaStream_t pipe_dyn, pipe_obs;
   cudaEvent_t ev_user, ev_dyn, ev_obs[4], ev_chunk[8];
+  int host_chunks;          // cz_step_host: column ranges whose device->host copies overlap the stepping of the next range
   int split;                // in-place step of a large batch: column ranges whose dynamics run under the previous range's rows
   int pipe_ready, pipe_cur, pipe_obs_pending[4];
   int pipe_buffers;         // state matrices of the pipelined step's ring (2..4, cz_pipeline_config)
@@ -963,6 +964,9 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     if (g && g[0] == '1') t->simple = t->simple2 = 0;
     const char* k = getenv("CZ_TWO_KERNEL_MIN_ENVS");
     t->two_kernel_min_envs = k ? atoi(k) : 49152;  // measured crossover between 32768 and 65536 (profiles/r01_two_kernel_sweep.txt)
+    const char* hc = getenv("CZ_HOST_CHUNKS");
+    t->host_chunks = hc ? atoi(hc) : 4;
+    if (t->host_chunks > 8) t->host_chunks = 8;
     const char* sp = getenv("CZ_SPLIT");
     t->split = sp ? atoi(sp) : 1;  // measured: every split is slower than the two plain launches (profiles/r02_notes.md)
     if (t->split > 8) t->split = 8;
@@ -1411,6 +1415,38 @@ extern "C" int cz_step_host(cz_tables* t, uint32_t* state_dev, const uint8_t* ac
   cudaStream_t s = (cudaStream_t)stream;
   size_t na = (size_t)n_envs * T.A;
   CZ_CUDA(cudaMemcpyAsync(t->d_actions, actions_host, na, cudaMemcpyHostToDevice, s));
+  // Large float64 batches on the specialised kernels: the step runs as column ranges and the device->host copy of range c
+  // leaves on a second stream while range c + 1 is still being stepped and written, so the copy engine starts after a
+  // quarter of the kernels instead of after all of them.  (The copy is > 99 % of this call: this recovers the kernels'
+  // ~0.1 ms of ~11 ms, no more.)
+  const int chunks = t->host_chunks;
+  if (chunks > 1 && (t->simple || t->simple2) && !(flags & CZ_STEP_OBS_F32) && n_envs >= 4 * 8192) {
+    int rc = cz_pipe_init(t);
+    if (rc != CZ_OK) return rc;
+    const int chunk = (((n_envs + chunks - 1) / chunks) + 255) & ~255;
+    cudaStream_t copy = t->pipe_obs;
+    int c = 0;
+    for (int e0 = 0; e0 < n_envs; e0 += chunk, ++c) {
+      const int n = n_envs - e0 < chunk ? n_envs - e0 : chunk;
+      const size_t o = (size_t)e0 * T.A;
+      rc = cz_launch<MODE_STEP>(t, state_dev + e0, state_dev + e0, true, t->d_actions + o, nullptr, nullptr, nullptr, nullptr,
+                                t->d_reward + o, t->d_term + o, t->d_trunc + o, nullptr, n, flags, seed, env_offset + e0, stream,
+                                n_envs);
+      if (rc != CZ_OK) return rc;
+      rc = cz_launch_obs64(t, state_dev + e0, t->d_obs + o * T.L, n, s, n_envs);
+      if (rc != CZ_OK) return rc;
+      CZ_CUDA(cudaEventRecord(t->ev_chunk[c], s));
+      CZ_CUDA(cudaStreamWaitEvent(copy, t->ev_chunk[c], 0));
+      CZ_CUDA(cudaMemcpyAsync(obs_host + o * T.L, t->d_obs + o * T.L, (size_t)n * T.A * T.L * sizeof(double), cudaMemcpyDeviceToHost, copy));
+      CZ_CUDA(cudaMemcpyAsync(reward_host + o, t->d_reward + o, (size_t)n * T.A * sizeof(double), cudaMemcpyDeviceToHost, copy));
+      CZ_CUDA(cudaMemcpyAsync(terminated_host + o, t->d_term + o, (size_t)n * T.A, cudaMemcpyDeviceToHost, copy));
+      CZ_CUDA(cudaMemcpyAsync(truncated_host + o, t->d_trunc + o, (size_t)n * T.A, cudaMemcpyDeviceToHost, copy));
+    }
+    CZ_CUDA(cudaEventRecord(t->ev_obs[0], copy));
+    CZ_CUDA(cudaStreamWaitEvent(s, t->ev_obs[0], 0));
+    CZ_CUDA(cudaStreamSynchronize(s));
+    return CZ_OK;
+  }
   int rc = cz_step(t, state_dev, t->d_actions, t->d_obs, t->d_reward, t->d_term, t->d_trunc, nullptr, n_envs, 1, flags, seed,
                    env_offset, 0, stream);
   if (rc != CZ_OK) return rc;

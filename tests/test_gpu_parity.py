@@ -350,3 +350,32 @@ def test_device_action_stream_matches_its_definition_and_is_shard_independent():
     for t in range(200):
         env.step(env.random_actions(t))
     assert int(env.error_flags.abs().sum()) == 0 and int(env.info()["t"].max()) <= 50
+
+
+@pytest.mark.parametrize("n", [333, 40011])
+def test_host_buffer_step_matches_the_device_step(n):
+    """cz_step_host (the reference-facing call with HOST buffers): small batches take one launch, batches of at least 32768
+    environments are stepped as four column ranges whose device->host copies overlap the next range's kernels"""
+    import ctypes as C
+    from cooking_zoo_b200 import _native
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=20,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    a = _make(n, cfg, auto_reset=True, seed=6, layout_pool_size=64)
+    b = _make(n, cfg, auto_reset=True, seed=6, layout_pool_size=64)
+    a.reset(); b.reset()
+    L = a.obs_len
+    h_obs = torch.empty((n, 2, L), dtype=torch.float64).pin_memory()
+    h_rew = torch.empty((n, 2), dtype=torch.float64).pin_memory()
+    h_te = torch.empty((n, 2), dtype=torch.uint8).pin_memory()
+    h_tr = torch.empty((n, 2), dtype=torch.uint8).pin_memory()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator().manual_seed(n)
+    for t in range(25):
+        act = torch.randint(0, 5, (n, 2), generator=g, dtype=torch.uint8).pin_memory()
+        _native.check(b.lib.cz_step_host(b._handle, b.state.data_ptr(), act.data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(),
+                                         h_te.data_ptr(), h_tr.data_ptr(), n, _native.STEP_AUTO_RESET, 6, 0, stream))
+        oa, ra, ta, ua, _ = a.step(act)
+        assert torch.equal(oa.cpu().view(torch.int64), h_obs.view(torch.int64)), t
+        assert torch.equal(ra.cpu().view(torch.int64), h_rew.view(torch.int64)), t
+        assert torch.equal(ta.cpu(), h_te) and torch.equal(ua.cpu(), h_tr), t
+    assert torch.equal(a.state, b.state)
