@@ -585,24 +585,27 @@ def run_gpu_arm(args):
     generic = None
     if want("generic"):
         try:
-            os.environ["CZ_GENERIC"] = "1"
-            envg = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
-                                     device=str(dev), recipe_pool=BOOK, layout_pool_size="auto", layout_seed=0, auto_reset=True,
-                                     seed=2026)
-            del os.environ["CZ_GENERIC"]
-            envg.reset(recipe_ids=recipe_ids)
-            cg = [0]
+            generic = {"workload": "the headline workload with the specialised classes switched off, in-place step"}
+            for key, val, what in (("all_generic", "1", "cz_env_kernel<.,.,0> (tables in global memory) + cz_obs_any_kernel"),
+                                   ("any_plan_writer", "2", "specialised dynamics kernel + cz_obs_any_kernel (what a custom meta "
+                                                            "file outside the packed observation plans gets)")):
+                os.environ["CZ_GENERIC"] = val
+                envg = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+                                         action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size="auto",
+                                         layout_seed=0, auto_reset=True, seed=2026)
+                del os.environ["CZ_GENERIC"]
+                envg.reset(recipe_ids=recipe_ids)
+                cg = [0]
 
-            def gen_step():
-                envg.step(actions[cg[0] % ring])
-                cg[0] += 1
-            vg = rate(gen_step, N, 100, 10)
-            bg = A * envg.obs_len * 8 + A * 8 + 2 * A + A + 2 * envg.tables.rows * 4
-            generic = {"workload": "the headline workload on the generic kernels (cz_env_kernel<.,.,0>: tables in global memory, any "
-                                   "observation plan), in-place step",
-                       "env_steps_per_s": vg, "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": vg * bg / 1e9, "peak": peak,
-                                                           "frac": vg * bg / 1e9 / peak}}
-            envg.close()
+                def gen_step():
+                    envg.step(actions[cg[0] % ring])
+                    cg[0] += 1
+                vg = rate(gen_step, N, 100, 10)
+                bg = A * envg.obs_len * 8 + A * 8 + 2 * A + A + 2 * envg.tables.rows * 4
+                generic[key] = {"kernels": what, "env_steps_per_s": vg,
+                                "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": vg * bg / 1e9, "peak": peak,
+                                             "frac": vg * bg / 1e9 / peak}}
+                envg.close()
         except Exception as ex:
             os.environ.pop("CZ_GENERIC", None)
             generic = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}

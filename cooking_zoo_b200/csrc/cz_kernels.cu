@@ -693,6 +693,94 @@ cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__
   }
 }
 
+// The same writer for ANY observation plan (tables outside the packed class: more than 64 (observer, slot) pairs, table runs
+// longer than 128 doubles, several computed ranges, odd row lengths, more than 16 variants): one warp per environment, loops
+// where the packed writer has one or two elements per lane, tables read from global memory.  The staging rows hold the whole
+// span of the computed ranges; with an even row length everything moves as 16-byte elements, otherwise as doubles.
+template <bool EVEN>
+__global__ void __launch_bounds__(32 * ENVS_WARPS, 8)  // 32 registers: a full SM of warps is worth more than the spills (0.73 vs 0.64 / 0.47 of roofline at 6 / 4 blocks)
+cz_obs_any_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, double* __restrict__ obs, int n_envs, int ld,
+                  int warps_per_block) {
+  extern __shared__ __align__(16) unsigned char smem_any[];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int env = blockIdx.x * warps_per_block + warp;
+  if (warp >= warps_per_block || env >= n_envs) return;
+  const int A = T.A, D = T.D, L = T.L;
+  const size_t N = (size_t)ld;
+  const int span = (T.stage_len + 1) & ~1;  // doubles per staging row (even: rows stay 16-byte aligned)
+  double* stage = reinterpret_cast<double*>(smem_any) + (size_t)warp * A * span;
+  const uint32_t* misc = state + (size_t)(D + A) * N;
+  const uint32_t var = __ldg(misc + (size_t)CZ_ROW_VARIANT * N + env);
+  const uint32_t sbits = __ldg(misc + (size_t)CZ_ROW_SBITS * N + env);
+  for (int k = lane; k < A * span; k += 32) stage[k] = 0.0;  // never-occupied slots are zeros
+  __syncwarp();
+  // computed slots: a lane takes (observer, slot) pairs lane, lane + 32, ... (pair p = observer * n_comp + slot)
+  const int n_pairs = A * T.n_comp;
+  for (int pr = lane; pr < n_pairs; pr += 32) {
+    const int a = (pr >= T.n_comp) + (pr >= 2 * T.n_comp) + (pr >= 3 * T.n_comp);  // A <= 4: no division
+    const int q = pr - a * T.n_comp;
+    const uint32_t d = __ldg(T.comp_slots + q);
+    const int off = (int)(d & 0xFFFu) - T.stage_lo;
+    const uint32_t flen = (d >> 12) & 7u, kind = (d >> 15) & 3u, idx = (d >> 17) & 255u;
+    uint32_t rec = 0, fb4 = 0;
+    bool present;
+    if (kind != 0u) {
+      const bool is_agent = kind == 2u;
+      const bool exists = !is_agent || (int)idx < A;
+      rec = exists ? __ldg(state + (size_t)(is_agent ? D + idx : idx) * N + env) : 0u;
+      present = is_agent ? exists : (rec & O_PRESENT) != 0;
+      const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+      fb4 = is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2);
+    } else {  // live Switch / Block (world_objects.py:174,221)
+      const uint32_t cell = __ldg(T.static_cells + var * T.S + idx);
+      present = cell != 0xFFu;
+      rec = present ? cell : 0u;
+      const uint32_t g = __ldg(T.grid + var * 64 + rec);
+      fb4 = ((g & 15u) == ST_SWITCH ? (sbits >> (12 + (g >> 4))) : (sbits >> (16 + (g >> 4)))) & 1u;
+    }
+    const uint32_t one = 1u << (flen - 1);
+    const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
+    const int x = rec & 7u, y = (rec >> 3) & 7u;
+    const uint32_t me = __ldg(state + (size_t)(D + a) * N + env);
+    const bool self = kind == 2u && (int)idx == a;  // the observer's own entry is x / W, y / H (cooking_env.py:364-368)
+    double X = __ldg(T.xlut + (x - (self ? 0 : (int)(me & 7u)) + T.W - 1));
+    double Y = __ldg(T.ylut + (y - (self ? 0 : (int)((me >> 3) & 7u)) + T.H - 1));
+    if (!present) { X = 0.0; Y = 0.0; }
+    double* out = stage + a * span + off;
+    out[0] = X;
+    out[1] = Y;
+#pragma unroll
+    for (uint32_t k = 0; k < 5; ++k)
+      if (k < flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, (fb >> k & 1u) ? 0x3FF00000u : 0u);
+  }
+  __syncwarp();
+  double* genv = obs + (size_t)env * A * L;
+  for (int a = 0; a < A; ++a) {
+    double* grow = genv + (size_t)a * L;
+    const double* srow = stage + a * span;
+    for (int r = 0; r < T.n_ranges; ++r) {  // computed ranges: staging -> row
+      const int o = T.ranges[r][0], n = T.ranges[r][1], so = o - T.stage_lo;
+      if (EVEN && !((o | n | so) & 1)) {
+        for (int k = lane; k < (n >> 1); k += 32)
+          reinterpret_cast<double2*>(grow + o)[k] = reinterpret_cast<const double2*>(srow + so)[k];
+      } else {
+        for (int k = lane; k < n; k += 32) grow[o + k] = srow[so + k];
+      }
+    }
+    const uint32_t cell = __ldg(state + (size_t)(D + a) * N + env) & 63u;
+    const double* tab = T.obs_table + ((size_t)var * 64 + cell) * T.tab_len;
+    for (int sg = 0; sg < T.n_segs; ++sg) {  // table segments (even offsets and lengths by construction): table -> row
+      const int o = T.segs[sg][0], n = T.segs[sg][1], to = T.segs[sg][2];
+      if (EVEN) {
+        for (int k = lane; k < (n >> 1); k += 32)
+          reinterpret_cast<double2*>(grow + o)[k] = __ldg(reinterpret_cast<const double2*>(tab + to) + k);
+      } else {
+        for (int k = lane; k < n; k += 32) grow[o + k] = __ldg(tab + to + k);
+      }
+    }
+  }
+}
+
 // =========================================================================================
 // Host side: tables object and the C ABI
 // =========================================================================================
@@ -731,6 +819,9 @@ struct cz_tables {
   // pipelined step: dynamics on a high-priority stream, observations on a second one, ping-pong state
   cudaStream_t pipe_dyn, pipe_obs;
   cudaEvent_t ev_user, ev_dyn, ev_obs[4], ev_chunk[8];
+  int fast_dyn;             // dynamics on the specialised (shared-memory table) kernels: V <= 16 variants and B <= 16 recipes,
+                            // whatever the observation plan looks like
+  int any_writer;           // generic tables, large in-place batches: dynamics kernel + any-plan row writer (CZ_ANY_WRITER=0: fused kernel)
   int host_chunks;          // cz_step_host: column ranges whose device->host copies overlap the stepping of the next range
   int split;                // in-place step of a large batch: column ranges whose dynamics run under the previous range's rows
   int pipe_ready, pipe_cur, pipe_obs_pending[4];
@@ -960,10 +1051,14 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   // 33-64 pairs (3-4 agent kitchens): specialised dynamics kernel + the warp-per-environment writer with two pairs per lane
   t->simple2 = packed && !t->simple && T.A * T.n_comp <= 64;
   {
-    const char* g = getenv("CZ_GENERIC");
-    if (g && g[0] == '1') t->simple = t->simple2 = 0;
+    t->fast_dyn = T.V <= CZ_SV && T.B <= CZ_SB;
+    const char* g = getenv("CZ_GENERIC");  // 1: everything generic; 2: only the observation plan (dynamics stay specialised)
+    if (g && (g[0] == '1' || g[0] == '2')) t->simple = t->simple2 = 0;
+    if (g && g[0] == '1') t->fast_dyn = 0;
     const char* k = getenv("CZ_TWO_KERNEL_MIN_ENVS");
     t->two_kernel_min_envs = k ? atoi(k) : 49152;  // measured crossover between 32768 and 65536 (profiles/r01_two_kernel_sweep.txt)
+    const char* aw = getenv("CZ_ANY_WRITER");
+    t->any_writer = aw ? atoi(aw) : 1;
     const char* hc = getenv("CZ_HOST_CHUNKS");
     t->host_chunks = hc ? atoi(hc) : 4;
     if (t->host_chunks > 8) t->host_chunks = 8;
@@ -990,6 +1085,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   SET_SMEM((cz_env_kernel<M, OBS_NONE, 3>)); SET_SMEM((cz_env_kernel<M, OBS_NONE, 4>))
   SET_MODE(MODE_STEP); SET_MODE(MODE_RESET); SET_MODE(MODE_OBSERVE);
   SET_SMEM(cz_obs32_kernel);
+  SET_SMEM(cz_obs_any_kernel<true>); SET_SMEM(cz_obs_any_kernel<false>);
   SET_SMEM((cz_warp_kernel<1, 16>)); SET_SMEM((cz_warp_kernel<2, 16>)); SET_SMEM((cz_warp_kernel<3, 16>)); SET_SMEM((cz_warp_kernel<4, 16>));
   SET_SMEM((cz_warp_kernel<1, 32>)); SET_SMEM((cz_warp_kernel<2, 32>)); SET_SMEM((cz_warp_kernel<3, 32>)); SET_SMEM((cz_warp_kernel<4, 32>));
 #undef SET_MODE
@@ -1061,7 +1157,7 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
 #define CZ_GO(O, NA)                                                                                                  \
   cz_env_kernel<MODE, O, NA><<<grid, CZ_THREADS, smem, s>>>(t->dev, state, state_out, actions, layout_ids, recipe_ids, mask, obs, \
                                                            reward, term, trunc, err, n_envs, flags, seed, env_offset, ld)
-  if (dyn_only && (t->simple || t->simple2)) {
+  if (dyn_only && (t->simple || t->simple2 || t->fast_dyn)) {
     switch (t->dev.A) {
       case 1: CZ_GO(OBS_NONE, 1); break;
       case 2: CZ_GO(OBS_NONE, 2); break;
@@ -1113,6 +1209,26 @@ static int cz_launch_obs64(const cz_tables* t, const uint32_t* state, double* ob
     default: CZ_OBS_GO(4); break;
   }
 #undef CZ_OBS_GO
+  g_launches.fetch_add(1);
+  CZ_CUDA(cudaGetLastError());
+  return CZ_OK;
+}
+
+// The any-plan float64 row writer (tables outside the packed class) on `s`.
+static int cz_launch_obs_any(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, cudaStream_t s, int ld = 0) {
+  if (!state || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
+  if (n_envs <= 0) return CZ_OK;
+  if (ld <= 0) ld = n_envs;
+  const CzDev& T = t->dev;
+  const size_t per_warp = (size_t)T.A * ((T.stage_len + 1) & ~1) * sizeof(double);
+  int warps = per_warp ? (int)(((size_t)96 * 1024) / per_warp) : ENVS_WARPS;  // at least two blocks per SM stay resident
+  if (warps > ENVS_WARPS) warps = ENVS_WARPS;
+  if (warps < 1) warps = 1;
+  const size_t smem = per_warp * warps;
+  if (smem > t->smem_optin) return cz_fail(CZ_ELIMIT, "%s", "observation rows too long for the row writer");
+  const int blocks = (n_envs + warps - 1) / warps;
+  if ((T.L & 1) == 0) cz_obs_any_kernel<true><<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs, ld, warps);
+  else cz_obs_any_kernel<false><<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs, ld, warps);
   g_launches.fetch_add(1);
   CZ_CUDA(cudaGetLastError());
   return CZ_OK;
@@ -1204,6 +1320,15 @@ static int cz_step_one(const cz_tables* t, uint32_t* state, const uint8_t* actio
                                   error_flags, n_envs, flags, seed, env_offset, stream);
     if (rc != CZ_OK) return rc;
     return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream);
+  }
+  // tables outside the packed class, large batches: the generic dynamics kernel, then the any-plan row writer (short
+  // blocks stream faster than the fused kernel's observation phase, as for the packed plans)
+  if (t && obs && !(flags & CZ_STEP_OBS_F32) && !t->simple && !t->simple2 && t->two_kernel_min_envs > 0 &&
+      n_envs >= t->two_kernel_min_envs && t->any_writer) {
+    int rc = cz_launch<MODE_STEP>(t, state, state, true, actions, nullptr, nullptr, nullptr, nullptr, reward, terminated, truncated,
+                                  error_flags, n_envs, flags, seed, env_offset, stream);
+    if (rc != CZ_OK) return rc;
+    return cz_launch_obs_any(t, state, obs, n_envs, (cudaStream_t)stream);
   }
   if ((flags & CZ_STEP_OBS_F32) && obs) {  // dynamics, then the float32 row writer on the same stream
     int rc = cz_launch<MODE_STEP>(t, state, state, true, actions, nullptr, nullptr, nullptr, nullptr, reward, terminated, truncated,

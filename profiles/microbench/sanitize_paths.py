@@ -62,6 +62,9 @@ def main(which):
         os.environ["CZ_GENERIC"] = "1"
         drive(make(5003), 4, 5003, 2)
         drive(make(3001, obs_dtype=torch.float32), 3, 3001, 2)
+        os.environ["CZ_GENERIC"] = "2"            # specialised dynamics + the any-plan row writer
+        os.environ["CZ_TWO_KERNEL_MIN_ENVS"] = "1000"
+        drive(make(5003), 4, 5003, 2)
     elif which == "warp":
         env = make(4099)                          # 16-lane groups: two environments per warp, ragged last warp
         drive(env, 3, 4099, 2, k_steps=8)

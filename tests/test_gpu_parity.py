@@ -379,3 +379,72 @@ def test_host_buffer_step_matches_the_device_step(n):
         assert torch.equal(ra.cpu().view(torch.int64), h_rew.view(torch.int64)), t
         assert torch.equal(ta.cpu(), h_te) and torch.equal(ua.cpu(), h_tr), t
     assert torch.equal(a.state, b.state)
+
+
+def test_generic_tables_large_batch_any_plan_writer(monkeypatch, tmp_path):
+    """tables outside the packed class step large batches as the generic dynamics kernel + cz_obs_any_kernel (warp per
+    environment, any observation plan); CZ_ANY_WRITER=0 keeps the fused generic kernel.  Checked on the headline tables
+    forced generic (against the specialised kernels) and on random / rich levels whose plans are really outside the class
+    (more than 64 pairs, long table runs, odd row lengths)."""
+    import random
+    from cooking_zoo_b200 import BatchedCookingEnv
+    from tests.test_oracle_vs_reference import _random_level, _random_meta
+    from tests.test_gpu_ksteps import _rich_level
+    cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=30,
+               recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
+    n = 50001
+    a = _make(n, cfg, auto_reset=True, seed=8, layout_pool_size=64)
+    monkeypatch.setenv("CZ_GENERIC", "1")
+    b = _make(n, cfg, auto_reset=True, seed=8, layout_pool_size=64)
+    monkeypatch.delenv("CZ_GENERIC")
+    a.reset(); b.reset()
+    rng = np.random.default_rng(2)
+    for t in range(35):
+        act = torch.from_numpy(rng.integers(0, 5, size=(n, 2)).astype(np.uint8)).cuda()
+        oa, ra, ta, ua, _ = a.step(act)
+        l0 = b.lib.cz_launch_count()
+        ob, rb, tb, ub, _ = b.step(act)
+        assert b.lib.cz_launch_count() - l0 == 2
+        assert torch.equal(oa.view(torch.int64), ob.view(torch.int64)), t
+        assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(ta, tb) and torch.equal(ua, ub)
+    assert torch.equal(a.state, b.state)
+    a.close(); b.close()
+    seen_odd = seen_many_pairs = False
+    for seed in (5003, 5005, 5006, 5020, 6001, 6004):
+        r = random.Random(seed)
+        lp, mp = str(tmp_path / f"level_{seed}.json"), str(tmp_path / f"meta_{seed}.json")
+        if seed >= 6000:
+            level = _random_level(r, lp)
+            _random_meta(r, level, mp)
+            A = 4
+        else:
+            _rich_level(r, lp, mp)
+            A = r.randint(1, 2)
+        recipes = ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"][:A]
+
+        def make():
+            e = BatchedCookingEnv(49152 + 77, lp, mp, A, 20, recipes, end_condition_all_dishes=True, action_scheme="scheme3",
+                                  layout_pool_size=32, layout_seed=seed, auto_reset=True, seed=seed)
+            e.reset()
+            return e
+        x = make()
+        tb_ = x.tables
+        packed = (tb_.num_agents * tb_.num_comp_slots <= 64 and tb_.num_obs_ranges == 1 and tb_.obs_table_len <= 128
+                  and tb_.obs_len % 2 == 0)
+        if packed:
+            x.close()
+            continue
+        seen_odd |= tb_.obs_len % 2 == 1
+        seen_many_pairs |= tb_.num_agents * tb_.num_comp_slots > 64
+        monkeypatch.setenv("CZ_ANY_WRITER", "0")
+        y = make()
+        monkeypatch.delenv("CZ_ANY_WRITER")
+        for t in range(25):
+            act = torch.from_numpy(rng.integers(0, 5, size=(x.num_envs, A)).astype(np.uint8)).cuda()
+            ox, rx, tx, ux, _ = x.step(act)
+            oy, ry, ty, uy, _ = y.step(act)
+            assert torch.equal(ox.view(torch.int64), oy.view(torch.int64)), (seed, t)
+            assert torch.equal(rx.view(torch.int64), ry.view(torch.int64)) and torch.equal(tx, ty) and torch.equal(ux, uy)
+        assert torch.equal(x.state, y.state)
+        x.close(); y.close()
+    assert seen_odd and seen_many_pairs
