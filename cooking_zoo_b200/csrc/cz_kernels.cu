@@ -821,6 +821,7 @@ struct cz_tables {
   cudaEvent_t ev_user, ev_dyn, ev_obs[4], ev_chunk[8];
   int fast_dyn;             // dynamics on the specialised (shared-memory table) kernels: V <= 16 variants and B <= 16 recipes,
                             // whatever the observation plan looks like
+  int obs32_pair;           // float32 rows of large batches: two environments per warp (CZ_OBS32_PAIR=0: one)
   int any_writer;           // generic tables, large in-place batches: dynamics kernel + any-plan row writer (CZ_ANY_WRITER=0: fused kernel)
   int host_chunks;          // cz_step_host: column ranges whose device->host copies overlap the stepping of the next range
   int split;                // in-place step of a large batch: column ranges whose dynamics run under the previous range's rows
@@ -1059,6 +1060,8 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     t->two_kernel_min_envs = k ? atoi(k) : 49152;  // measured crossover between 32768 and 65536 (profiles/r01_two_kernel_sweep.txt)
     const char* aw = getenv("CZ_ANY_WRITER");
     t->any_writer = aw ? atoi(aw) : 1;
+    const char* o32 = getenv("CZ_OBS32_PAIR");
+    t->obs32_pair = o32 ? atoi(o32) : 1;
     const char* hc = getenv("CZ_HOST_CHUNKS");
     t->host_chunks = hc ? atoi(hc) : 4;
     if (t->host_chunks > 8) t->host_chunks = 8;
@@ -1416,7 +1419,10 @@ extern "C" int cz_observe_f32(const cz_tables* t, const uint32_t* state, float* 
 }
 
 extern "C" int cz_observe(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, void* stream) {
-  if (t && t->simple2) return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream);
+  if (t && (t->simple2 || (t->simple && t->two_kernel_min_envs > 0 && n_envs >= t->two_kernel_min_envs)))
+    return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream);  // the short-block row writer (as in cz_step)
+  if (t && !t->simple && !t->simple2 && t->any_writer && t->two_kernel_min_envs > 0 && n_envs >= t->two_kernel_min_envs)
+    return cz_launch_obs_any(t, state, obs, n_envs, (cudaStream_t)stream);
   return cz_launch<MODE_OBSERVE>(t, state, const_cast<uint32_t*>(state), false, nullptr, nullptr, nullptr, nullptr, obs, nullptr,
                                  nullptr, nullptr, nullptr, n_envs, 0, 0, 0, stream);
 }
@@ -1489,7 +1495,7 @@ extern "C" int cz_step_pipelined(cz_tables* t, uint32_t* state2, const uint8_t* 
   // rewards / flags / state, run a policy) is ordered after this step's dynamics; only the rows need cz_pipeline_wait
   CZ_CUDA(cudaStreamWaitEvent(user, t->ev_dyn, 0));
   if (flags & CZ_STEP_OBS_F32) {
-    rc = cz_launch_obs32(t, out, reinterpret_cast<float*>(obs), n_envs, t->pipe_obs);
+    rc = cz_launch_obs32(t, out, reinterpret_cast<float*>(obs), n_envs, t->pipe_obs, false);
     if (rc != CZ_OK) return rc;
   } else {
     rc = cz_launch_obs64(t, out, obs, n_envs, t->pipe_obs);

@@ -48,10 +48,11 @@ def test_f32_rows_are_the_rounded_reference_rows(path):
 
 @pytest.mark.parametrize("pipelined", [False, True])
 def test_f32_mode_tracks_the_f64_mode_at_scale(pipelined):
-    """40000 auto-resetting envs, 60 steps: identical rewards / flags / state, obs32 == obs64.float() bit for bit"""
+    """40001 auto-resetting envs, 60 steps: identical rewards / flags / state, obs32 == obs64.float() bit for bit
+    (large batches: two environments per writer warp, the odd count leaves a lone last environment)"""
     cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=23,
                recipes=["TomatoLettuceSalad", "CarrotBanana"], end_all=True, reward_scheme=None)
-    n = 40000
+    n = 40001
     a = _make(n, cfg, auto_reset=True, seed=5, layout_pool_size=64)
     b = _make(n, cfg, auto_reset=True, seed=5, layout_pool_size=64, obs_dtype=torch.float32, pipelined=pipelined)
     oa, ob = a.reset(), b.reset()
@@ -64,6 +65,28 @@ def test_f32_mode_tracks_the_f64_mode_at_scale(pipelined):
         b.wait()
         assert torch.equal(oa.float().view(torch.int32), ob.view(torch.int32)), t
         assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(ta, tb) and torch.equal(ua, ub), t
+    assert torch.equal(a.state, b.state)
+
+
+@pytest.mark.parametrize("agents,n", [(1, 5001), (2, 2368), (3, 3001)])
+def test_f32_writers_by_agent_count(agents, n):
+    """one agent (two environments per warp, 1112-byte rows), the smallest two-per-warp batch, three agents (one per warp)"""
+    if agents == 3:
+        cfg = dict(level="tests/golden/levels/open4.json", meta_file="tests/golden/levels/meta4.json", num_agents=3, max_steps=19,
+                   recipes=["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad"], end_all=True, reward_scheme=None)
+    else:
+        cfg = dict(level="coop_test", meta_file="example", num_agents=agents, max_steps=19,
+                   recipes=["TomatoLettuceSalad", "CarrotBanana"][:agents], end_all=True, reward_scheme=None)
+    a = _make(n, cfg, auto_reset=True, seed=2, layout_pool_size=32)
+    b = _make(n, cfg, auto_reset=True, seed=2, layout_pool_size=32, obs_dtype=torch.float32)
+    oa, ob = a.reset(), b.reset()
+    assert torch.equal(oa.float().view(torch.int32), ob.view(torch.int32))
+    rng = np.random.default_rng(4)
+    for t in range(25):
+        act = torch.from_numpy(rng.integers(0, 5, size=(n, agents)).astype(np.uint8)).cuda()
+        oa, ob = a.step(act)[0], b.step(act)[0]
+        assert torch.equal(oa.float().view(torch.int32), ob.view(torch.int32)), t
+        assert torch.equal(b.observe().view(torch.int32), ob.view(torch.int32)), t
     assert torch.equal(a.state, b.state)
 
 

@@ -109,6 +109,7 @@ def test_fullsize_sampled_lockstep_invariants_and_idempotence():
     assert bool((pres[bread].sum(0) >= pres0[bread].sum(0)).all())     # Bread only ever multiplies
     assert int(env.error_flags.abs().sum()) == 0
     stepped = env.obs.clone()
+    env.obs.fill_(float("nan"))                                       # observe() must rewrite every element
     assert torch.equal(stepped.view(torch.int64), env.observe().view(torch.int64))   # obs == f(state)
 
 
