@@ -13,13 +13,21 @@ from cooking_zoo_b200 import BatchedCookingEnv  # noqa: E402
 R2 = ["TomatoLettuceSalad", "CarrotBanana"]
 
 
-def run(n, dtype):
-    env = BatchedCookingEnv(n, "coop_test", "example", 2, 400, R2, end_condition_all_dishes=True, action_scheme="scheme3",
-                            layout_pool_size="auto", auto_reset=True, seed=1, obs_dtype=dtype)
+R4 = ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "no_recipe"]
+
+
+def run(n, dtype, agents=2, open4=False):
+    if open4:   # the 1-4 agent kitchen of config 5
+        env = BatchedCookingEnv(n, "tests/golden/levels/open4.json", "tests/golden/levels/meta4.json", agents, 400, R4[:agents],
+                                end_condition_all_dishes=True, action_scheme="scheme3", layout_pool_size=64, auto_reset=True,
+                                seed=1, obs_dtype=dtype)
+    else:
+        env = BatchedCookingEnv(n, "coop_test", "example", agents, 400, R2[:agents], end_condition_all_dishes=True,
+                                action_scheme="scheme3", layout_pool_size="auto", auto_reset=True, seed=1, obs_dtype=dtype)
     env.reset()
     g = torch.Generator().manual_seed(0)
     for _ in range(8):
-        env.step(torch.randint(0, 5, (n, 2), generator=g, dtype=torch.uint8).cuda())
+        env.step(torch.randint(0, 5, (n, agents), generator=g, dtype=torch.uint8).cuda())
     for _ in range(5):
         env.observe()
     torch.cuda.synchronize()
@@ -30,8 +38,9 @@ def run(n, dtype):
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / 50
-    nbytes = n * 2 * 278 * (4 if dtype == torch.float32 else 8)
-    print(f"{'f32' if dtype == torch.float32 else 'f64'} rows, {n} envs: {us:.2f} us per launch, {nbytes / us / 1e3:.0f} GB/s of rows",
+    nbytes = env.obs.numel() * env.obs.element_size()
+    print(f"{'f32' if dtype == torch.float32 else 'f64'} rows, {'open4' if open4 else 'coop_test'}, {agents} agents, L = {env.obs_len}, "
+          f"{n} envs: {us:.2f} us per launch, {nbytes / us / 1e3:.0f} GB/s of rows",
           {k: v for k, v in os.environ.items() if k.startswith('CZ_')})
 
 
@@ -39,3 +48,7 @@ if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
     for dt in (torch.float32, torch.float64):
         run(n, dt)
+    if os.environ.get("OBS_TIME_OPEN4"):
+        for a in (1, 2, 3, 4):
+            run(n, torch.float64, a, True)
+        run(n, torch.float64, 1)
