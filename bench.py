@@ -550,8 +550,7 @@ def run_gpu_arm(args):
                             _native.check(grp.lib.cz_pipeline_reset(grp._handle, grp.lib.cz_pipeline_current(grp._handle)))
                     with torch.cuda.stream(side):
                         with torch.cuda.graph(graph5, stream=side, capture_error_mode="thread_local"):
-                            for _ in range(10):
-                                mix.cook_step()
+                            mix.cook_steps(10)      # one fork / join of the four group streams around the 10 steps
                             mix.wait()
                     torch.cuda.current_stream(dev).wait_stream(side)
                     out5[mode] = rate(graph5.replay, n5 * 10, 20, 3)
@@ -569,7 +568,8 @@ def run_gpu_arm(args):
                                 f"respawn 0.2 / grace 3, per-group recipes, auto-reset",
                     "closed_loop_env_steps_per_s": out5.get("in_place"), "closed_loop_pipelined_env_steps_per_s": out5.get("pipelined"),
                     "errors": {k: v for k, v in out5.items() if k.endswith("_error")},
-                    "how": "10 closed-loop steps of every group captured as one CUDA graph (4 streams, 2-3 kernels per group and step)",
+                    "how": "10 closed-loop steps of every group captured as one CUDA graph (MixedAgentCookingEnv.cook_steps(10): four "
+                           "independent stream branches, 2-3 kernels per group and step; the groups are not re-joined between steps)",
                     "size_note": "four groups share the GPU, so the rate grows with the population: 65536 / 131072 / 262144 envs = "
                                  "0.57 / 0.72 / 0.78 G env-steps/s (0.52 / 0.66 / 0.72 of roofline; profiles/r02_notes.md)",
                     "eager_env_steps_per_s": {"in_place": out5.get("in_place_eager"), "pipelined": out5.get("pipelined_eager"),

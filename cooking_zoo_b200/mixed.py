@@ -93,14 +93,22 @@ class MixedAgentCookingEnv:
         group's own stream, cz_policy_act followed by the step — no gathers or scatters through the global [N, A_max]
         views, no torch kernels, two library calls per group (what BASELINE config 5 times).  Outputs stay in the groups
         (`groups[a].obs / .reward / .terminated / .truncated`); the caller's stream is joined on return."""
+        self.cook_steps(1)
+
+    def cook_steps(self, k):
+        """`k` closed-loop steps of every group with ONE fork / join of the group streams around them: the groups are
+        independent populations, so group a's row writer may run under group b's cook and dynamics instead of every
+        phase of every group starting together (cook_step() joins the streams after each step).  The final outputs are
+        those of k calls of cook_step()."""
         cur = torch.cuda.current_stream(self.device)
-        for a, g in self.groups.items():
-            s = self.streams[a]
+        for a in sorted(self.groups, reverse=True):   # the widest rows first: their writers are the longest kernels
+            g, s = self.groups[a], self.streams[a]
             s.wait_stream(cur)
             g.stream = s
             try:
-                acts, _ = g.heuristic_actions()
-                g.step(acts)
+                for _ in range(int(k)):
+                    acts, _ = g.heuristic_actions()
+                    g.step(acts)
             finally:
                 g.stream = None
         for s in self.streams.values():

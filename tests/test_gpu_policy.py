@@ -205,6 +205,41 @@ def test_cfg5_mixed_agent_counts_heuristic_streams_spawning_per_env_recipes():
     assert len(alive) > 20
 
 
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_cook_steps_equals_the_step_by_step_closed_loop(pipelined):
+    """MixedAgentCookingEnv.cook_steps(k) (one fork / join of the group streams around k steps) == k x cook_step() ==
+    heuristic_actions() + step() through the global views: same states, rows, rewards and flags in every group"""
+    from cooking_zoo_b200 import MixedAgentCookingEnv
+    level = os.path.join(ROOT, "tests/golden/levels/open4.json")
+    meta = os.path.join(ROOT, "tests/golden/levels/meta4.json")
+    counts = (np.arange(3000) % 4) + 1
+    recipes = ["TomatoLettuceSalad", "CarrotBanana", "TomatoSalad", "AppleWatermelon"]
+
+    def make(pipe):
+        env = MixedAgentCookingEnv(counts, level, meta, 40, recipes, end_condition_all_dishes=True, action_scheme="scheme3",
+                                   layout_pool_size=32, auto_reset=True, seed=11, agent_respawn_rate=0.2,
+                                   agent_despawn_rate=0.05, grace_period=3, pipelined=pipe)
+        env.reset()
+        return env
+    a, b, c = make(pipelined), make(pipelined), make(False)
+    for _ in range(3):
+        a.cook_steps(7)
+        for _ in range(7):
+            b.cook_step()
+            act, _ = c.heuristic_actions()
+            c.step(act)
+        a.wait(); b.wait()
+        torch.cuda.synchronize()
+        for n in a.groups:
+            ga, gb, gc = a.groups[n], b.groups[n], c.groups[n]
+            for other in (gb, gc):
+                assert torch.equal(ga.state, other.state), n
+                assert torch.equal(ga.obs.view(torch.int64), other.obs.view(torch.int64)), n
+                assert torch.equal(ga.reward.view(torch.int64), other.reward.view(torch.int64)), n
+                assert torch.equal(ga.terminated, other.terminated) and torch.equal(ga.truncated, other.truncated), n
+            assert int(ga.error_flags.abs().sum()) == 0
+
+
 def test_pipelined_closed_loop_equals_in_place_closed_loop():
     """the cook only waits for the dynamics of the pipelined step (cz_pipeline_wait_state): same trajectories"""
     cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=60,
