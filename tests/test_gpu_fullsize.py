@@ -203,3 +203,75 @@ def test_exhaustive_lockstep_other_paths(name, level, meta, A, recipes, scheme, 
         assert np.array_equal(cte, te.cpu().numpy()) and np.array_equal(ctu, tu.cpu().numpy()), (name, t)
         assert np.array_equal(bits(co), bits(o.cpu().numpy())), (name, t)
     assert int(env.error_flags.abs().sum()) == 0
+
+
+def test_config4_whole_population_on_one_gpu():
+    """Maximum size: BASELINE config 4's whole population (1048576 environments) as ONE batch on one GPU — the observation
+    buffer is 4.66 GB, so every row offset is 64-bit arithmetic.  Checks: structural invariants of the final state, a
+    131072-environment shard stepped alone (env_offset) reproduces its slice bit for bit, sampled environments (first, last,
+    around the 2^32-byte boundary of the rows) in lockstep with the oracle, observe() == the rows of the last step."""
+    n, shard, steps = 1 << 20, 5, 12
+    rid = _recipe_ids(n, 8)
+    g = torch.Generator(device="cpu").manual_seed(21)
+    acts = torch.randint(0, 5, (steps, n, 2), generator=g, dtype=torch.uint8).cuda()
+    env = _env(n, auto_reset=True, seed=9)
+    lids = env.default_layout_ids().cpu().numpy()
+    env.reset(layout_ids=lids, recipe_ids=rid)
+    lo, hi = shard * N, (shard + 1) * N
+    part = _env(N, auto_reset=True, seed=9, env_offset=lo)
+    assert np.array_equal(part.default_layout_ids().cpu().numpy(), lids[lo:hi])
+    part.reset(layout_ids=lids[lo:hi], recipe_ids=rid[lo:hi])
+    assert torch.equal(env.obs[lo:hi].view(torch.int64), part.obs.view(torch.int64))
+    row_bytes = 2 * env.obs_len * 8
+    edge = (1 << 32) // row_bytes                      # the environment whose rows straddle byte 2^32 of the buffer
+    picks = sorted({0, 1, n - 1, n - 2, edge - 1, edge, edge + 1, lo, hi - 1, 777_777})
+    oracles = {k: OracleEnv(env.tables.layouts[lids[k]], [BOOK[int(r)] for r in rid[k]], 400, end_condition_all_dishes=True)
+               for k in picks}
+    idx = torch.as_tensor(picks).cuda()
+    for t in range(steps):
+        obs, rew, term, trunc, _ = env.step(acts[t])
+        o2, r2, te2, tr2, _ = part.step(acts[t, lo:hi].contiguous())
+        assert torch.equal(obs[lo:hi].view(torch.int64), o2.view(torch.int64)), t
+        assert torch.equal(rew[lo:hi].view(torch.int64), r2.view(torch.int64)) and torch.equal(term[lo:hi], te2), t
+        o, r = obs[idx].cpu().numpy(), rew[idx].cpu().numpy()
+        a = acts[t][idx].cpu().numpy()
+        for j, k in enumerate(picks):
+            rr, te, tu, _ = oracles[k].step(a[j])
+            assert np.array_equal(bits(rr), bits(r[j])), (k, t)
+            assert_obs_equal(np.stack([oracles[k].observe(i) for i in range(2)]), o[j], f"env {k} step {t}")
+    assert torch.equal(env.state[:, lo:hi], part.state)
+    assert int(env.error_flags.abs().sum()) == 0
+    last = obs[idx].clone()
+    env.obs.fill_(float("nan"))
+    assert torch.equal(env.observe()[idx].view(torch.int64), last.view(torch.int64))
+    del part
+    torch.cuda.empty_cache()
+    _check_invariants(env)
+
+
+@pytest.mark.parametrize("mode", ["pipelined", "f32", "k_steps"])
+def test_config4_whole_population_other_modes_equal_the_in_place_step(mode):
+    """1048576 environments in one batch: the pipelined step, the float32 rows and the K-steps-per-call entry point against
+    the in-place float64 step (the same 64-bit row offsets in every writer)"""
+    n, steps = 1 << 20, 6
+    rid = _recipe_ids(n, 8)
+    g = torch.Generator(device="cpu").manual_seed(22)
+    acts = torch.randint(0, 5, (steps, n, 2), generator=g, dtype=torch.uint8).cuda()
+    a = _env(n, auto_reset=True, seed=9)
+    kw = {"pipelined": dict(pipelined=True), "f32": dict(obs_dtype=torch.float32), "k_steps": {}}[mode]
+    b = _env(n, auto_reset=True, seed=9, **kw)
+    a.reset(recipe_ids=rid); b.reset(recipe_ids=rid)
+    for t in range(steps):
+        oa, ra, ta, ua, _ = a.step(acts[t])
+        if mode != "k_steps":
+            ob, rb, tb, ub, _ = b.step(acts[t])
+            b.wait()
+    if mode == "k_steps":
+        ob, rb, tb, ub, _ = b.step_k(steps, actions=acts)
+    if mode == "f32":
+        for lo in range(0, n, 1 << 18):      # compare in slices: oa.float() of the whole buffer would be another 2.3 GB
+            assert torch.equal(oa[lo:lo + (1 << 18)].float().view(torch.int32), ob[lo:lo + (1 << 18)].view(torch.int32)), lo
+    else:
+        assert torch.equal(oa.view(torch.int64), ob.view(torch.int64))
+    assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(ta, tb) and torch.equal(ua, ub)
+    assert torch.equal(a.state, b.state)
