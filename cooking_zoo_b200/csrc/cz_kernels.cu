@@ -712,7 +712,8 @@ cz_obs_any_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ 
   const uint32_t* misc = state + (size_t)(D + A) * N;
   const uint32_t var = __ldg(misc + (size_t)CZ_ROW_VARIANT * N + env);
   const uint32_t sbits = __ldg(misc + (size_t)CZ_ROW_SBITS * N + env);
-  for (int k = lane; k < A * span; k += 32) stage[k] = 0.0;  // never-occupied slots are zeros
+  for (int k = lane; k < (A * span) >> 1; k += 32)  // never-occupied slots are zeros (span is even: 16-byte elements)
+    reinterpret_cast<double2*>(stage)[k] = make_double2(0.0, 0.0);
   __syncwarp();
   // computed slots: a lane takes (observer, slot) pairs lane, lane + 32, ... (pair p = observer * n_comp + slot)
   const int n_pairs = A * T.n_comp;

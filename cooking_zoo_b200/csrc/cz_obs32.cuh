@@ -10,6 +10,10 @@
 #pragma once
 
 #define CZ_OBS32_MAX_WARPS 8
+#ifndef CZ_OBS32_UNROLL
+#define CZ_OBS32_UNROLL 4  // zero-fill and copy-out loops of the float32 writers: the loop overhead is most of their instructions
+#endif
+constexpr int kObs32Unroll = CZ_OBS32_UNROLL;  // (#pragma unroll takes a constant expression, not a macro)
 
 __global__ void __launch_bounds__(32 * CZ_OBS32_MAX_WARPS)
 cz_obs32_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, float* __restrict__ obs, int n_envs,
@@ -240,8 +244,10 @@ cz_obs32_pair_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict
   {  // the computed range of every row starts as zeros (never-occupied slots stay zero)
     const int o2 = T.ranges[0][0] >> 1, n2 = T.ranges[0][1] >> 1;
 #pragma unroll
-    for (int a = 0; a < 2 * NA; ++a)
+    for (int a = 0; a < 2 * NA; ++a) {
+#pragma unroll kObs32Unroll
       for (int k = lane; k < n2; k += 32) stage2[a * L2 + o2 + k] = make_float2(0.0f, 0.0f);
+    }
   }
   __syncwarp();
   cz_pair_store32(T, ls, p0, stage2, L2);
@@ -252,6 +258,7 @@ cz_obs32_pair_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict
   if (two) {
     float4* g4 = reinterpret_cast<float4*>(g);
     const float4* s4 = reinterpret_cast<const float4*>(stage2);
+#pragma unroll kObs32Unroll
     for (int k = lane; k < (NA * T.L) >> 1; k += 32) g4[k] = s4[k];
   } else {
     float2* g2 = reinterpret_cast<float2*>(g);
