@@ -653,9 +653,49 @@ def run_gpu_arm(args):
             c1.record()
             torch.cuda.synchronize(dev)
             loop_p_ms = c0.elapsed_time(c1) / kc
+            # the same pipelined closed loop as one CUDA graph of 20 steps (what the headline's timed region is): without
+            # the host's launch gaps between the three dependent kernels of a step
+            graphed_p = graphed_s = None
+            for pipe in (True, False):
+                try:
+                    envc.close()
+                    envc = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True,
+                                             action_scheme="scheme3", device=str(dev), recipe_pool=BOOK, layout_pool_size="auto",
+                                             layout_seed=0, auto_reset=True, seed=2026, pipelined=pipe)
+                    envc.reset(recipe_ids=recipe_ids)
+                    for _ in range(25):
+                        envc.step(envc.heuristic_actions()[0])
+                    envc.wait()
+                    torch.cuda.synchronize(dev)
+                    gc_ = torch.cuda.CUDAGraph()
+                    side_c = torch.cuda.Stream(dev)
+                    side_c.wait_stream(torch.cuda.current_stream(dev))
+                    if pipe:
+                        _native.check(lib.cz_pipeline_reset(envc._handle, lib.cz_pipeline_current(envc._handle)))
+                    with torch.cuda.stream(side_c):
+                        with torch.cuda.graph(gc_, stream=side_c, capture_error_mode="thread_local"):
+                            for _ in range(20):
+                                envc.step(envc.heuristic_actions()[0])
+                            envc.wait()
+                    torch.cuda.current_stream(dev).wait_stream(side_c)
+                    r_ = rate(gc_.replay, N * 20, 10, 3)
+                    if pipe:
+                        graphed_p = r_
+                        _native.check(lib.cz_pipeline_reset(envc._handle, lib.cz_pipeline_current(envc._handle)))
+                    else:
+                        graphed_s = r_
+                except Exception as ex:
+                    if pipe:
+                        graphed_p = f"{type(ex).__name__}: {str(ex)[:120]}"
+                    else:
+                        graphed_s = f"{type(ex).__name__}: {str(ex)[:120]}"
             cook = {"workload": f"{N} two-agent envs, every action from cz_policy_act (the scripted cook)",
                     "closed_loop_env_steps_per_s": N / (loop_ms / 1e3),
-                    "closed_loop_pipelined_env_steps_per_s": N / (loop_p_ms / 1e3), "policy_ms_per_launch": pol_ms,
+                    "closed_loop_pipelined_env_steps_per_s": N / (loop_p_ms / 1e3),
+                    "closed_loop_graph_env_steps_per_s": {"in_place": graphed_s, "pipelined": graphed_p,
+                                                          "how": "20 closed-loop steps (cz_policy_act + step) as one CUDA graph; "
+                                                                 "the two figures above are eager launches"},
+                    "policy_ms_per_launch": pol_ms,
                     "policy_decisions_per_s": N * A / (pol_ms / 1e3),
                     "recipes_done_now": float(envc.info()["recipe_done"].sum())}
             envc.close()
