@@ -819,7 +819,8 @@ struct cz_tables {
   int scratch_envs;
   // pipelined step: dynamics on a high-priority stream, observations on a second one, ping-pong state
   cudaStream_t pipe_dyn, pipe_obs;
-  cudaEvent_t ev_user, ev_dyn, ev_obs[4], ev_chunk[8];
+  cudaEvent_t ev_user, ev_dyn, ev_obs[4], ev_chunk[8], ev_pol_in, ev_pol_out;
+  int policy_on_dyn;        // cz_policy_act of a running pipeline launches on the dynamics stream (CZ_POLICY_ON_DYN=0: caller's stream)
   int fast_dyn;             // dynamics on the specialised (shared-memory table) kernels: V <= 16 variants and B <= 16 recipes,
                             // whatever the observation plan looks like
   int obs32_pair;           // float32 rows of large batches: two environments per warp (CZ_OBS32_PAIR=0: one)
@@ -1061,6 +1062,8 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     t->two_kernel_min_envs = k ? atoi(k) : 49152;  // measured crossover between 32768 and 65536 (profiles/r01_two_kernel_sweep.txt)
     const char* aw = getenv("CZ_ANY_WRITER");
     t->any_writer = aw ? atoi(aw) : 1;
+    const char* pod = getenv("CZ_POLICY_ON_DYN");
+    t->policy_on_dyn = pod ? atoi(pod) : 1;
     const char* o32 = getenv("CZ_OBS32_PAIR");
     t->obs32_pair = o32 ? atoi(o32) : 1;
     const char* hc = getenv("CZ_HOST_CHUNKS");
@@ -1112,6 +1115,7 @@ extern "C" int cz_tables_destroy(cz_tables* t) {
   if (t->pipe_ready) {
     cudaStreamDestroy(t->pipe_dyn); cudaStreamDestroy(t->pipe_obs);
     cudaEventDestroy(t->ev_user); cudaEventDestroy(t->ev_dyn);
+    cudaEventDestroy(t->ev_pol_in); cudaEventDestroy(t->ev_pol_out);
     for (int c = 0; c < 4; ++c) cudaEventDestroy(t->ev_obs[c]);
     for (int c = 0; c < 8; ++c) cudaEventDestroy(t->ev_chunk[c]);
   }
@@ -1440,6 +1444,8 @@ static int cz_pipe_init(cz_tables* t) {
   CZ_CUDA(cudaEventCreateWithFlags(&t->ev_dyn, cudaEventDisableTiming));
   for (int c = 0; c < 4; ++c) CZ_CUDA(cudaEventCreateWithFlags(&t->ev_obs[c], cudaEventDisableTiming));
   for (int c = 0; c < 8; ++c) CZ_CUDA(cudaEventCreateWithFlags(&t->ev_chunk[c], cudaEventDisableTiming));
+  CZ_CUDA(cudaEventCreateWithFlags(&t->ev_pol_in, cudaEventDisableTiming));
+  CZ_CUDA(cudaEventCreateWithFlags(&t->ev_pol_out, cudaEventDisableTiming));
   t->pipe_ready = 1;
   return CZ_OK;
 }

@@ -350,10 +350,24 @@ extern "C" int cz_policy_act(const cz_policy* p, const uint32_t* state, const ui
   const size_t smem = (size_t)(CZ_POLICY_THREADS / 32) * (T.D + T.A) * OSTRIDE * 4;
   int blocks = (n_envs + CZ_POLICY_THREADS - 1) / CZ_POLICY_THREADS;
   if (p->blocks_per_sm > 0 && blocks > p->tables->num_sms * p->blocks_per_sm) blocks = p->tables->num_sms * p->blocks_per_sm;
-  cz_policy_kernel<<<blocks, CZ_POLICY_THREADS, smem, (cudaStream_t)stream>>>(T, p->dev, state, cook_recipes, actions, crashed,
-                                                                              n_envs);
+  // Pipelined tables in the middle of a run: the cook's kernel goes onto the library's high-priority dynamics stream, where it
+  // is ordered behind the dynamics that produced `state` and gets SM slots ahead of the row writer's queued blocks (on the
+  // caller's normal-priority stream it only runs once the writer of the previous step has nothing left to schedule, which
+  // serialises cook and writer).  The caller's stream is ordered before and after it, as if the launch were its own.
+  cz_tables* tm = const_cast<cz_tables*>(p->tables);
+  const bool on_dyn = tm->policy_on_dyn && tm->pipe_ready && tm->pipe_steps > 0;
+  cudaStream_t user = (cudaStream_t)stream, s = on_dyn ? tm->pipe_dyn : user;
+  if (on_dyn) {
+    CZ_CUDA(cudaEventRecord(tm->ev_pol_in, user));
+    CZ_CUDA(cudaStreamWaitEvent(tm->pipe_dyn, tm->ev_pol_in, 0));
+  }
+  cz_policy_kernel<<<blocks, CZ_POLICY_THREADS, smem, s>>>(T, p->dev, state, cook_recipes, actions, crashed, n_envs);
   g_launches.fetch_add(1);
   CZ_CUDA(cudaGetLastError());
+  if (on_dyn) {
+    CZ_CUDA(cudaEventRecord(tm->ev_pol_out, tm->pipe_dyn));
+    CZ_CUDA(cudaStreamWaitEvent(user, tm->ev_pol_out, 0));
+  }
   return CZ_OK;
 }
 

@@ -1,5 +1,7 @@
 """Closed loop with the device cook, pipelined, 131072 envs: blocks per SM of the dynamics kernel x of the policy kernel.
-One CUDA graph of 40 steps per setting.  python profiles/microbench/closed_loop_sweep.py"""
+One CUDA graph of 40 steps per setting.  python profiles/microbench/closed_loop_sweep.py
+CZ_POLICY_ON_DYN=0 puts the cook's kernel back on the caller's stream (the round-2 sweep before the cook moved to the
+library's high-priority stream)."""
 import os
 import sys
 
@@ -12,7 +14,8 @@ N = 131072
 BOOK = ["TomatoSalad", "TomatoLettuceSalad", "CarrotBanana", "MashedCarrotBanana", "CucumberOnion", "AppleWatermelon",
         "TomatoLettuceOnionSalad", "no_recipe"]
 rid = torch.randint(0, 8, (N, 2), generator=torch.Generator().manual_seed(1), dtype=torch.uint8)
-for dyn, pol in ((0, 0), (3, 0), (0, 4), (4, 4), (6, 6), (4, 8), (8, 8), (6, 10), (3, 6)):
+COMBOS = ((0, 0), (3, 0), (0, 4), (4, 4), (6, 6), (4, 8), (8, 8), (6, 10), (3, 6), (3, 3), (2, 3), (4, 5), (5, 5), (3, 4), (2, 2))
+for dyn, pol in COMBOS:
     env = BatchedCookingEnv(N, "coop_test", "example", 2, 400, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
                             recipe_pool=BOOK, auto_reset=True, seed=1, pipelined=True, background_dynamics=dyn,
                             background_policy=pol)
