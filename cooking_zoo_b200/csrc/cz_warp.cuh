@@ -13,6 +13,9 @@
 // /root/reference/cooking_zoo/...  Bit-identity with cz_step x K is tested in tests/test_gpu_ksteps.py.
 // Included by cz_kernels.cu (needs BlockSmem, LaneSlot, cz_lane_slot_packed).
 #pragma once
+#ifndef CZ_WARP_TMA
+#define CZ_WARP_TMA 1  // the computed range of the rows leaves through cp.async.bulk (0: lane stores; K = 64: 4.45 vs 4.71 us per step)
+#endif
 
 #ifndef WK_WARPS
 #define WK_WARPS 4  // environments (warps) per block
@@ -837,16 +840,30 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
     // ---- get_feature_vector (cooking_env.py:352-373): the A rows of this step
     if (obs) {
       double2* g2 = reinterpret_cast<double2*>(obs + ((keep ? (size_t)k * N : 0) + (size_t)env) * NA * T.L);
+#if CZ_WARP_TMA
+      if (g == 0) cz_bulk_wait_read<0>();  // the TMA engine has read the staging rows of the previous step
+#endif
       g_sync(e);  // the copy-out of the previous step has read the staging rows
       for (int q0 = 0; q0 < n_pairs; q0 += G) {
         const int q = q0 + g;
         const bool live = q < n_pairs;
         wk_pair_store(T, e, live ? pmap[q] : 0u, live, sxl, syl, stage, stage2);
       }
+#if CZ_WARP_TMA
+      // the computed range of the NA rows leaves through the TMA engine: one elected lane, one bulk store per row
+      cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
+      g_sync(e);
+      if (g == 0) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a) cz_bulk_store_nocommit(g2 + a * L2 + o2, stage + a * stage2 + s2, (uint32_t)n2 * 16u);
+        cz_bulk_commit();
+      }
+#else
       g_sync(e);
 #pragma unroll
       for (int a = 0; a < NA; ++a)
         for (int q = g; q < n2; q += G) g2[a * L2 + o2 + q] = stage[a * stage2 + s2 + q];
+#endif
       const double2* tab = tab_lane + (size_t)e.variant * 64 * tab2;
 #pragma unroll
       for (int a = 0; a < NA; ++a) {  // table segments of row a: loads first, then the stores
@@ -862,6 +879,9 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
     }
   }
 
+#if CZ_WARP_TMA
+  if (obs && g == 0) cz_bulk_wait_read<0>();  // the staging rows must outlive the last bulk stores
+#endif
   // ---- registers -> state
   if (g < D) state[(size_t)g * N + env] = e.rec;
   if (g < NA + CZ_NUM_MISC_ROWS) {
