@@ -637,6 +637,10 @@ __device__ __forceinline__ void cz_pair_store(const CzDev& T, const LaneSlot& ls
     if (k < (int)ls.flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, (fb >> k & 1u) ? 0x3FF00000u : 0u);
 }
 
+#ifndef CZ_ENVS_TMA
+#define CZ_ENVS_TMA 1  // computed range of the rows through cp.async.bulk: the same time alone and in place, but fewer issue slots
+                       // taken from the background dynamics of the pipelined step (104.75 -> 102.74 us); 0: lane copies (A/B build)
+#endif
 // TWO = false: at most 32 (observer, slot) pairs, one per lane.  TWO = true: up to 64 pairs (3-4 agent kitchens),
 // a lane owns pairs `lane` and `lane + 32`.
 template <int NA, bool TWO>
@@ -668,12 +672,23 @@ cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__
   __syncwarp();
   cz_pair_store(T, ls, p, stage, stage2);
   if constexpr (TWO) cz_pair_store(T, ls1, p1, stage, stage2);
+#if CZ_ENVS_TMA
+  cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
+#endif
   __syncwarp();
   {
     const int n2 = T.ranges[0][1] >> 1, o2 = T.ranges[0][0] >> 1, s2 = (T.ranges[0][0] - T.stage_lo) >> 1;
+#if CZ_ENVS_TMA
+    if (lane == 0) {  // the computed range of the NA rows leaves through the TMA engine
+#pragma unroll
+      for (int a = 0; a < NA; ++a) cz_bulk_store_nocommit(g2 + a * L2 + o2, stage + a * stage2 + s2, (uint32_t)n2 * 16u);
+      cz_bulk_commit();
+    }
+#else
 #pragma unroll
     for (int a = 0; a < NA; ++a)
       for (int k = lane; k < n2; k += 32) cz_row_store(g2 + a * L2 + o2 + k, stage[a * stage2 + s2 + k]);
+#endif
   }
   {  // table segments: all rows' loads first, then the stores
     double2 v0[NA], v1[NA];
@@ -691,6 +706,9 @@ cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__
       if (ls.t1 >= 0) cz_row_store(g2 + a * L2 + ls.t1, v1[a]);
     }
   }
+#if CZ_ENVS_TMA
+  if (lane == 0) cz_bulk_wait_read<0>();  // the staging rows must outlive the bulk reads
+#endif
 }
 
 // The same writer for ANY observation plan (tables outside the packed class: more than 64 (observer, slot) pairs, table runs
