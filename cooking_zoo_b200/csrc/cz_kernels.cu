@@ -772,16 +772,18 @@ cz_obs_any_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ 
     for (uint32_t k = 0; k < 5; ++k)
       if (k < flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, (fb >> k & 1u) ? 0x3FF00000u : 0u);
   }
+  if (EVEN) cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
   __syncwarp();
   double* genv = obs + (size_t)env * A * L;
+  bool bulk = false;
   for (int a = 0; a < A; ++a) {
     double* grow = genv + (size_t)a * L;
     const double* srow = stage + a * span;
     for (int r = 0; r < T.n_ranges; ++r) {  // computed ranges: staging -> row
       const int o = T.ranges[r][0], n = T.ranges[r][1], so = o - T.stage_lo;
-      if (EVEN && !((o | n | so) & 1)) {
-        for (int k = lane; k < (n >> 1); k += 32)
-          reinterpret_cast<double2*>(grow + o)[k] = reinterpret_cast<const double2*>(srow + so)[k];
+      if (EVEN && !((o | n | so) & 1)) {  // 16-byte aligned on both sides, a multiple of 16 bytes: one bulk store (TMA engine)
+        if (lane == 0) cz_bulk_store_nocommit(grow + o, srow + so, (uint32_t)n * 8u);
+        bulk = true;
       } else {
         for (int k = lane; k < n; k += 32) grow[o + k] = srow[so + k];
       }
@@ -797,6 +799,10 @@ cz_obs_any_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ 
         for (int k = lane; k < n; k += 32) grow[o + k] = __ldg(tab + to + k);
       }
     }
+  }
+  if (bulk && lane == 0) {
+    cz_bulk_commit();
+    cz_bulk_wait_read<0>();  // the staging rows must outlive the bulk reads
   }
 }
 
