@@ -280,7 +280,7 @@ def run_reference_arm(args):
             "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample}, **extra),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -809,9 +809,20 @@ def run_gpu_arm(args):
                               "note": "in-place cz_step, outputs ordered on the caller's stream: dynamics kernel + row-writer kernel at this batch size (one fused kernel below 49152 environments)"},
                 "stats": {"episodes_started": float(stats[0]), "recipes_done_now": float(stats[1]),
                           "last_step_return": float(stats[2])}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_STDOUT_FD = None
+
+
+def emit(line):
+    """the run's JSON line on the real stdout (see main)"""
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -832,6 +843,12 @@ def main():
                          "the background of the observation writes of step k (two kernels, two streams, ping-pong state, "
                          "cz_pipeline_config); sync: the in-place step (dynamics kernel, then the row writer)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: everything libraries print while the run is under way (NCCL's version banner
+    # goes to stdout when NCCL_DEBUG is set) is sent to stderr, and the descriptor is handed back for the final print
+    sys.stdout.flush()
+    global _STDOUT_FD
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 6000
         args.warmup = args.warmup if args.warmup is not None else 200
