@@ -1096,13 +1096,16 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     const char* sp = getenv("CZ_SPLIT");
     t->split = sp ? atoi(sp) : 1;  // measured: every split is slower than the two plain launches (profiles/r02_notes.md)
     if (t->split > 8) t->split = 8;
-    const char* w = getenv("CZ_WARP_MAX_ENVS");
-    t->warp_max_envs = w ? atoi(w) : 6144;  // measured crossover of the per-launch times (profiles/r02_notes.md)
     const char* wk = getenv("CZ_WARP_K_MAX_ENVS");
     t->warp_k_max_envs = wk ? atoi(wk) : 32768;
     const char* wg = getenv("CZ_WARP_GROUP");  // 16 or 32 lanes per environment in the warp kernel (default: 16 when D <= 16)
     t->warp_group = T.D <= 16 ? 16 : 32;
     if (wg && atoi(wg) == 32) t->warp_group = 32;
+    // a single step goes to the warp kernel while the batch fits ONE wave of it (4 blocks x 8 environments per SM with
+    // 16-lane groups, 7 x 4 with 32-lane groups: 4736 / 4144 environments on 148 SMs); the second wave doubles its time and
+    // the fused lane-per-environment kernel wins (inplace_path_sweep.py: 4096 envs 10.8 vs 13.1 us, 6144 envs 18.3 vs 15.6 us)
+    const char* w = getenv("CZ_WARP_MAX_ENVS");
+    t->warp_max_envs = w ? atoi(w) : t->num_sms * (t->warp_group == 16 ? 32 : 28);
   }
 #define SET_SMEM(K) CZ_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin))
 #define SET_MODE(M)                                                                                    \
