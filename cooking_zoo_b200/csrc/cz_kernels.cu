@@ -614,7 +614,12 @@ __device__ __forceinline__ PairRegs cz_pair_load(const CzDev& T, const uint32_t*
 }
 
 // [x, y, flags..., 1] of the pair into its staging row
+__device__ __forceinline__ void cz_pair_store_at(const CzDev& T, const LaneSlot& ls, const PairRegs& p, double* span0);
 __device__ __forceinline__ void cz_pair_store(const CzDev& T, const LaneSlot& ls, const PairRegs& p, double2* stage, int stage2) {
+  cz_pair_store_at(T, ls, p, reinterpret_cast<double*>(stage + ls.agent * stage2));
+}
+// `span0`: where element stage_lo of the pair's row lives (staged span or whole staged row)
+__device__ __forceinline__ void cz_pair_store_at(const CzDev& T, const LaneSlot& ls, const PairRegs& p, double* span0) {
   if (ls.off < 0) return;
   const bool is_agent = ls.kind == 2, is_static = ls.kind == 0;
   const uint32_t rec = p.rec, me = p.me;
@@ -629,7 +634,7 @@ __device__ __forceinline__ void cz_pair_store(const CzDev& T, const LaneSlot& ls
   double X = __ldg(T.xlut + (x - (self ? 0 : (int)(me & 7u)) + T.W - 1));
   double Y = __ldg(T.ylut + (y - (self ? 0 : (int)((me >> 3) & 7u)) + T.H - 1));
   if (!present) { X = 0.0; Y = 0.0; }
-  double* out = reinterpret_cast<double*>(stage + ls.agent * stage2) + ls.off;
+  double* out = span0 + ls.off;
   out[0] = X;
   out[1] = Y;
 #pragma unroll
@@ -709,6 +714,65 @@ cz_obs_envs_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__
 #if CZ_ENVS_TMA
   if (lane == 0) cz_bulk_wait_read<0>();  // the staging rows must outlive the bulk reads
 #endif
+}
+
+// Single-agent batches: a row is only 2224 bytes, 4.3 sixteen-byte elements per lane, and the one-environment writer spends
+// its life waiting for its loads (4.4 TB/s).  Here a warp builds the rows of TWO neighbouring environments whole in shared
+// memory — table segments by cp.async (no registers), computed slots by the lanes, both environments' loads in flight
+// together — and hands the 2 * L doubles to the TMA engine as one bulk store (the float32 pair writer, cz_obs32.cuh).
+__device__ __forceinline__ void cz_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * ENVS_WARPS, 6)
+cz_obs_single_pair_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, double* __restrict__ obs, int n_envs,
+                          int ld) {
+  extern __shared__ __align__(16) unsigned char smem_rows[];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int env0 = (blockIdx.x * ENVS_WARPS + warp) * 2;
+  if (env0 >= n_envs) return;
+  const bool two = env0 + 1 < n_envs;
+  const int env1 = two ? env0 + 1 : env0;  // a lone last environment is built twice and written once
+  const int D = T.D, tab2 = T.tab_len >> 1, L2 = T.L >> 1;
+  const size_t N = (size_t)ld;
+  double2* rows = reinterpret_cast<double2*>(smem_rows) + (size_t)warp * 2 * L2;
+
+  const LaneSlot ls = cz_lane_slot_packed(T, lane);
+  const uint32_t var0 = __ldg(state + (size_t)(D + 1 + CZ_ROW_VARIANT) * N + env0);
+  const uint32_t var1 = __ldg(state + (size_t)(D + 1 + CZ_ROW_VARIANT) * N + env1);
+  const PairRegs p0 = cz_pair_load<1>(T, state, N, env0, var0, ls);
+  const PairRegs p1 = cz_pair_load<1>(T, state, N, env1, var1, ls);
+  {  // table segments of both rows: lane 0 holds the observer
+    const uint32_t c0 = __shfl_sync(0xffffffffu, p0.me, 0) & 63u, c1 = __shfl_sync(0xffffffffu, p1.me, 0) & 63u;
+    const double2* tab0 = reinterpret_cast<const double2*>(T.obs_table) + ((size_t)var0 * 64 + c0) * tab2 + lane;
+    const double2* tab1 = reinterpret_cast<const double2*>(T.obs_table) + ((size_t)var1 * 64 + c1) * tab2 + lane;
+    if (ls.t0 >= 0) {
+      cz_cp_async16(rows + ls.t0, tab0);
+      cz_cp_async16(rows + L2 + ls.t0, tab1);
+    }
+    if (ls.t1 >= 0) {
+      cz_cp_async16(rows + ls.t1, tab0 + 32);
+      cz_cp_async16(rows + L2 + ls.t1, tab1 + 32);
+    }
+  }
+  {  // never-occupied slots of the computed range are zeros
+    const int n2 = T.ranges[0][1] >> 1, o2 = T.ranges[0][0] >> 1;
+    for (int k = lane; k < n2; k += 32) {
+      rows[o2 + k] = make_double2(0.0, 0.0);
+      rows[L2 + o2 + k] = make_double2(0.0, 0.0);
+    }
+  }
+  __syncwarp();
+  cz_pair_store_at(T, ls, p0, reinterpret_cast<double*>(rows) + T.stage_lo);
+  cz_pair_store_at(T, ls, p1, reinterpret_cast<double*>(rows + L2) + T.stage_lo);
+  cz_cp_async_wait_all();
+  cz_fence_async_smem();  // generic-proxy and cp.async writes -> visible to the async proxy
+  __syncwarp();
+  if (lane == 0) {
+    cz_bulk_store_nocommit(obs + (size_t)env0 * T.L, rows, (uint32_t)((two ? 2 : 1) * T.L) * 8u);
+    cz_bulk_commit();
+    cz_bulk_wait_read<0>();  // the staged rows must outlive the read
+  }
 }
 
 // The same writer for ANY observation plan (tables outside the packed class: more than 64 (observer, slot) pairs, table runs
@@ -847,6 +911,7 @@ struct cz_tables {
   int policy_on_dyn;        // cz_policy_act of a running pipeline launches on the dynamics stream (CZ_POLICY_ON_DYN=0: caller's stream)
   int fast_dyn;             // dynamics on the specialised (shared-memory table) kernels: V <= 16 variants and B <= 16 recipes,
                             // whatever the observation plan looks like
+  int single_pair;          // float64 rows of large single-agent batches: two environments per warp (CZ_SINGLE_PAIR=0: one)
   int obs32_pair;           // float32 rows of large batches: two environments per warp (CZ_OBS32_PAIR=0: one)
   int any_writer;           // generic tables, large in-place batches: dynamics kernel + any-plan row writer (CZ_ANY_WRITER=0: fused kernel)
   int host_chunks;          // cz_step_host: column ranges whose device->host copies overlap the stepping of the next range
@@ -1088,6 +1153,8 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     t->any_writer = aw ? atoi(aw) : 1;
     const char* pod = getenv("CZ_POLICY_ON_DYN");
     t->policy_on_dyn = pod ? atoi(pod) : 1;
+    const char* sp1 = getenv("CZ_SINGLE_PAIR");
+    t->single_pair = sp1 ? atoi(sp1) : 1;
     const char* o32 = getenv("CZ_OBS32_PAIR");
     t->obs32_pair = o32 ? atoi(o32) : 1;
     const char* hc = getenv("CZ_HOST_CHUNKS");
@@ -1227,11 +1294,23 @@ static int cz_launch(const cz_tables* t, const uint32_t* state, uint32_t* state_
 }
 
 // The warp-per-environment float64 row writer (packed plans) on `s`.
-static int cz_launch_obs64(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, cudaStream_t s, int ld = 0) {
+// `alone`: nothing else is meant to share the SMs with this launch (in-place step, cz_observe) — see cz_launch_obs32
+static int cz_launch_obs64(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, cudaStream_t s, int ld = 0,
+                           bool alone = false) {
   if (ld <= 0) ld = n_envs;
   if (!state || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
   if (n_envs <= 0) return CZ_OK;
+  if (alone && t->simple && t->dev.A == 1 && t->single_pair && n_envs >= 2 * ENVS_WARPS * t->num_sms) {
+    const size_t smem = (size_t)ENVS_WARPS * 2 * t->dev.L * 8;  // two whole rows per warp
+    if (smem <= 48 * 1024) {
+      const int blocks = (n_envs + 2 * ENVS_WARPS - 1) / (2 * ENVS_WARPS);
+      cz_obs_single_pair_kernel<<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs, ld);
+      g_launches.fetch_add(1);
+      CZ_CUDA(cudaGetLastError());
+      return CZ_OK;
+    }
+  }
   const int blocks = (n_envs + ENVS_WARPS - 1) / ENVS_WARPS;
   const size_t smem = (size_t)ENVS_WARPS * t->dev.A * ((t->dev.stage_len + 1) / 2) * 16;
 #define CZ_OBS_GO(NA)                                                                                               \
@@ -1354,7 +1433,7 @@ static int cz_step_one(const cz_tables* t, uint32_t* state, const uint8_t* actio
     int rc = cz_launch<MODE_STEP>(t, state, state, true, actions, nullptr, nullptr, nullptr, nullptr, reward, terminated, truncated,
                                   error_flags, n_envs, flags, seed, env_offset, stream);
     if (rc != CZ_OK) return rc;
-    return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream);
+    return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream, 0, true);
   }
   // tables outside the packed class, large batches: the generic dynamics kernel, then the any-plan row writer (short
   // blocks stream faster than the fused kernel's observation phase, as for the packed plans)
@@ -1452,7 +1531,7 @@ extern "C" int cz_observe_f32(const cz_tables* t, const uint32_t* state, float* 
 
 extern "C" int cz_observe(const cz_tables* t, const uint32_t* state, double* obs, int n_envs, void* stream) {
   if (t && (t->simple2 || (t->simple && t->two_kernel_min_envs > 0 && n_envs >= t->two_kernel_min_envs)))
-    return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream);  // the short-block row writer (as in cz_step)
+    return cz_launch_obs64(t, state, obs, n_envs, (cudaStream_t)stream, 0, true);  // the short-block row writer (as in cz_step)
   if (t && !t->simple && !t->simple2 && t->any_writer && t->two_kernel_min_envs > 0 && n_envs >= t->two_kernel_min_envs)
     return cz_launch_obs_any(t, state, obs, n_envs, (cudaStream_t)stream);
   return cz_launch<MODE_OBSERVE>(t, state, const_cast<uint32_t*>(state), false, nullptr, nullptr, nullptr, nullptr, obs, nullptr,

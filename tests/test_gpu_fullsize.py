@@ -275,3 +275,30 @@ def test_config4_whole_population_other_modes_equal_the_in_place_step(mode):
         assert torch.equal(oa.view(torch.int64), ob.view(torch.int64))
     assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(ta, tb) and torch.equal(ua, ub)
     assert torch.equal(a.state, b.state)
+
+
+def test_single_agent_large_batch_every_environment_against_the_compiled_oracle():
+    """BASELINE config 1's shape (one agent, coop_test, TomatoLettuceSalad) as a large batch: 50001 environments (odd: the
+    two-environments-per-warp row writer ends on a lone environment), every environment compared with oracle/cz_oracle.c
+    every step; observe() rewrites the same rows."""
+    from cooking_zoo_b200 import BatchedCookingEnv
+    from oracle.cz_oracle_c import CBatch
+    n, recipes = 50001, ["TomatoLettuceSalad"]
+    env = BatchedCookingEnv(n, "coop_test", "example", 1, 10 ** 5, recipes, action_scheme="scheme3", layout_pool_size=64,
+                            layout_seed=4, seed=12)
+    lids = env.default_layout_ids().cpu().numpy()
+    obs = env.reset(layout_ids=lids).cpu().numpy()
+    cpu = CBatch([env.tables.layouts[l] for l in lids], [recipes] * n, 10 ** 5, action_scheme="scheme3")
+    assert np.array_equal(bits(cpu.observe()), bits(obs))
+    g = torch.Generator(device="cpu").manual_seed(78)
+    for t in range(40):
+        act = torch.randint(0, 5, (n, 1), generator=g, dtype=torch.uint8)
+        o, r, te, tu, _ = env.step(act.cuda())
+        co, cr, cte, ctu = cpu.step(act.numpy())
+        assert np.array_equal(bits(cr), bits(r.cpu().numpy())), t
+        assert np.array_equal(cte, te.cpu().numpy()) and np.array_equal(ctu, tu.cpu().numpy()), t
+        assert np.array_equal(bits(co), bits(o.cpu().numpy())), t
+    last = env.obs.clone()
+    env.obs.fill_(float("nan"))
+    assert torch.equal(env.observe().view(torch.int64), last.view(torch.int64))
+    assert int(env.error_flags.abs().sum()) == 0
