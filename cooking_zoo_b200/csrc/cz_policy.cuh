@@ -19,6 +19,7 @@ struct CzPolicyDev {
   const uint8_t* list_len;    // [V][8]
   const uint64_t* reach;      // [V][64]
   const uint8_t* first_step;  // [V][64][64]
+  int use_env_marks;          // cook i follows recipe i: take the node marks from the state (CZ_POLICY_ENV_MARKS=0: re-evaluate)
 };
 
 struct PolList {
@@ -125,13 +126,21 @@ __device__ __forceinline__ uint32_t pol_appliance(const CzDev& T, const CzPolicy
 }
 
 // CookingAgent.step for cook `i` following book recipe `rid`
+// `marks`: the node marks of this recipe as the environment's own step left them (CZ_ROW_MARKS; bit k = node k marked), or
+// 0x100 when the cook follows a recipe the environment does not score and the graph has to be evaluated here.  The cook
+// re-evaluates its private copy of the graph from the same world the environment evaluated after the step
+// (cooking_agent.py:12 / cooking_env.py:300, both Recipe.update_recipe_state, recipe.py:77-87), so the marks are the same.
 __device__ __forceinline__ uint32_t pol_cook(const CzDev& T, const CzPolicyDev& P, const uint32_t* o, uint32_t variant,
-                                             uint32_t agent_rec, uint32_t rid, bool& crash) {
+                                             uint32_t agent_rec, uint32_t rid, uint32_t marks, bool& crash) {
   const uint32_t me = A_XY(agent_rec);
-  // own recipe graph, re-evaluated from the world (cooking_agent.py:12, recipe.py:77-87)
-  uint64_t m[CZ_MAX_NODES];
   const int n = __ldg(T.recipe_len + rid);
   int pick = -1;  // find_node (base_agent.py:49-53): first unmarked node from the back of node_list
+  if (marks < 0x100u) {
+    const uint32_t open_nodes = ~marks & ((1u << n) - 1u);
+    pick = open_nodes ? 31 - __clz(open_nodes) : -1;
+  } else {
+  // own recipe graph, re-evaluated from the world (cooking_agent.py:12, recipe.py:77-87)
+  uint64_t m[CZ_MAX_NODES];
 #pragma unroll
   for (int k = CZ_MAX_NODES - 1; k >= 0; --k) {
     m[k] = 0;
@@ -146,6 +155,7 @@ __device__ __forceinline__ uint32_t pol_cook(const CzDev& T, const CzPolicyDev& 
       m[k] = mask;
       if (!mask && pick < 0) pick = k;
     }
+  }
   }
   if (pick < 0) return 0;
   const uint32_t node = __ldg(T.recipe_nodes + rid * CZ_MAX_NODES + pick);
@@ -263,6 +273,7 @@ cz_policy_kernel(const __grid_constant__ CzDev T, const __grid_constant__ CzPoli
   const uint32_t* misc = state + (size_t)(D + A) * N;
   const uint32_t variant = misc[(size_t)CZ_ROW_VARIANT * N + env];
   const uint32_t rids = misc[(size_t)CZ_ROW_RECIPES * N + env];
+  const uint32_t env_marks = misc[(size_t)CZ_ROW_MARKS * N + env];
   cz_cp_async_wait_all();
   uint32_t bad = 0;
   for (int i = 0; i < A; ++i) {
@@ -270,7 +281,9 @@ cz_policy_kernel(const __grid_constant__ CzDev T, const __grid_constant__ CzPoli
     const uint32_t rid = cook_recipes ? cook_recipes[(size_t)env * A + i] : ((rids >> (8 * i)) & 255u);
     bool crash = false;
     uint32_t act = 0;
-    if (rid < (uint32_t)T.B) act = pol_cook(T, P, col, variant, ag[i * OSTRIDE], rid, crash);
+    // cook i follows recipe i of its environment: the environment's step has already evaluated that graph
+    const uint32_t marks = (!cook_recipes && i < T.R && P.use_env_marks) ? ((env_marks >> (8 * i)) & 255u) : 0x100u;
+    if (rid < (uint32_t)T.B) act = pol_cook(T, P, col, variant, ag[i * OSTRIDE], rid, marks, crash);
     else crash = true;
     if (crash) bad |= 1u << i;
     actions[(size_t)env * A + i] = (uint8_t)(crash ? 0u : act);
@@ -327,6 +340,10 @@ extern "C" int cz_policy_create(const cz_tables* t, const cz_policy_desc* d, cz_
   if (rc == CZ_OK) rc = pol_upload(p, d->list_len, V * 8, &p->dev.list_len);
   if (rc == CZ_OK) rc = pol_upload(p, d->reach, V * 64, &p->dev.reach);
   if (rc == CZ_OK) rc = pol_upload(p, d->first_step, V * 64 * 64, &p->dev.first_step);
+  {
+    const char* em = getenv("CZ_POLICY_ENV_MARKS");
+    p->dev.use_env_marks = em ? atoi(em) : 1;
+  }
   if (rc != CZ_OK) {
     cz_policy_destroy(p);
     return rc;
