@@ -89,24 +89,42 @@ __device__ __forceinline__ int pol_closest(const CzPolicyDev& P, uint32_t varian
 #define POL_WALK(from, to) ((uint32_t)__ldg(P.first_step + ((size_t)variant * 64 + (from)) * 64 + (to)))
 
 // generic_sequence (base_agent.py:148-190): get food `slot` processed by an appliance of `kind`
-__device__ __forceinline__ uint32_t pol_appliance(const CzDev& T, const CzPolicyDev& P, const uint32_t* o, uint32_t variant,
-                                                  uint32_t agent_rec, uint32_t kind, uint32_t slot, bool& crash) {
+// Per-environment masks every cook of the environment shares (built once, by all lanes, before the divergent cook logic:
+// inside pol_appliance these loops ran at ~6 active lanes and were a quarter of the kernel's warp instructions).
+struct PolEnv {
+  uint64_t filled;  // cells whose static object holds something
+  uint64_t app[2];  // cells of the Cutboards / Blenders of the layout variant
+};
+
+__device__ __forceinline__ PolEnv pol_env_masks(const CzDev& T, const CzPolicyDev& P, const uint32_t* o, uint32_t variant) {
+  PolEnv pe;
+  pe.filled = 0;
+  for (int k = 0; k < T.D; ++k) {
+    const uint32_t r = o[k * OSTRIDE];
+    if ((r & O_PRESENT) && O_CK(r) == CK_STATIC) pe.filled |= 1ull << O_XY(r);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint32_t kind = j == 0 ? ST_CUTBOARD : ST_BLENDER;
+    const uint8_t* apps = P.lists + ((size_t)variant * 8 + kind) * 64;
+    const int n_apps = __ldg(P.list_len + variant * 8 + kind);
+    uint64_t cells = 0;
+    for (int k = 0; k < n_apps; ++k) cells |= 1ull << __ldg(apps + k);
+    pe.app[j] = cells;
+  }
+  return pe;
+}
+
+__device__ __forceinline__ uint32_t pol_appliance(const CzDev& T, const CzPolicyDev& P, const PolEnv& pe, const uint32_t* o,
+                                                  uint32_t variant, uint32_t agent_rec, uint32_t kind, uint32_t slot, bool& crash) {
   const uint32_t me = A_XY(agent_rec);
   const uint32_t rec = o[slot * OSTRIDE];
   const uint32_t at = O_XY(rec);
   const uint64_t near = __ldg(P.reach + variant * 64 + me);
-  const uint8_t* apps = P.lists + ((size_t)variant * 8 + kind) * 64;
-  const int n_apps = __ldg(P.list_len + variant * 8 + kind);
-  uint64_t app_cells = 0;
-  for (int k = 0; k < n_apps; ++k) app_cells |= 1ull << __ldg(apps + k);
-  app_cells &= near;
+  const uint64_t app_cells = pe.app[kind == ST_CUTBOARD ? 0 : 1] & near;
   // `obj in appliance.content` for a reachable appliance: walk into it (the bump chops / blends)
   if (O_CK(rec) == CK_STATIC && (app_cells >> at & 1ull)) return POL_WALK(me, at);
-  uint64_t filled = 0;  // static objects with content
-  for (int k = 0; k < T.D; ++k) {
-    const uint32_t r = o[k * OSTRIDE];
-    if ((r & O_PRESENT) && O_CK(r) == CK_STATIC) filled |= 1ull << O_XY(r);
-  }
+  const uint64_t filled = pe.filled;  // static objects with content
   const uint64_t empty_apps = app_cells & ~filled;
   int target;
   if (A_HAS(agent_rec) && A_HOLD(agent_rec) == slot) {
@@ -130,8 +148,8 @@ __device__ __forceinline__ uint32_t pol_appliance(const CzDev& T, const CzPolicy
 // 0x100 when the cook follows a recipe the environment does not score and the graph has to be evaluated here.  The cook
 // re-evaluates its private copy of the graph from the same world the environment evaluated after the step
 // (cooking_agent.py:12 / cooking_env.py:300, both Recipe.update_recipe_state, recipe.py:77-87), so the marks are the same.
-__device__ __forceinline__ uint32_t pol_cook(const CzDev& T, const CzPolicyDev& P, const uint32_t* o, uint32_t variant,
-                                             uint32_t agent_rec, uint32_t rid, uint32_t marks, bool& crash) {
+__device__ __forceinline__ uint32_t pol_cook(const CzDev& T, const CzPolicyDev& P, const PolEnv& pe, const uint32_t* o,
+                                             uint32_t variant, uint32_t agent_rec, uint32_t rid, uint32_t marks, bool& crash) {
   const uint32_t me = A_XY(agent_rec);
   const int n = __ldg(T.recipe_len + rid);
   int pick = -1;  // find_node (base_agent.py:49-53): first unmarked node from the back of node_list
@@ -183,7 +201,7 @@ __device__ __forceinline__ uint32_t pol_cook(const CzDev& T, const CzPolicyDev& 
     }
     if (pol_unmet(cond, best_rec)) {
       // handle_condition_sequence (base_agent.py:133-146): CHOPPED -> Cutboard, MASHED -> Blender
-      const uint32_t act = pol_appliance(T, P, o, variant, agent_rec, cond == 1u ? ST_CUTBOARD : ST_BLENDER,
+      const uint32_t act = pol_appliance(T, P, pe, o, variant, agent_rec, cond == 1u ? ST_CUTBOARD : ST_BLENDER,
                                          (uint32_t)(objs.base + best), crash);
       if (crash) return 0;
       if (act) return act;
@@ -275,6 +293,7 @@ cz_policy_kernel(const __grid_constant__ CzDev T, const __grid_constant__ CzPoli
   const uint32_t rids = misc[(size_t)CZ_ROW_RECIPES * N + env];
   const uint32_t env_marks = misc[(size_t)CZ_ROW_MARKS * N + env];
   cz_cp_async_wait_all();
+  const PolEnv pe = pol_env_masks(T, P, col, variant);
   uint32_t bad = 0;
   for (int i = 0; i < A; ++i) {
     // an environment scores at most CZ_MAX_RECIPES recipes; cook i follows recipe i unless told otherwise
@@ -283,7 +302,7 @@ cz_policy_kernel(const __grid_constant__ CzDev T, const __grid_constant__ CzPoli
     uint32_t act = 0;
     // cook i follows recipe i of its environment: the environment's step has already evaluated that graph
     const uint32_t marks = (!cook_recipes && i < T.R && P.use_env_marks) ? ((env_marks >> (8 * i)) & 255u) : 0x100u;
-    if (rid < (uint32_t)T.B) act = pol_cook(T, P, col, variant, ag[i * OSTRIDE], rid, marks, crash);
+    if (rid < (uint32_t)T.B) act = pol_cook(T, P, pe, col, variant, ag[i * OSTRIDE], rid, marks, crash);
     else crash = true;
     if (crash) bad |= 1u << i;
     actions[(size_t)env * A + i] = (uint8_t)(crash ? 0u : act);
