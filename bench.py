@@ -35,7 +35,7 @@ BOOK = ["TomatoSalad", "TomatoLettuceSalad", "CarrotBanana", "MashedCarrotBanana
         "AppleWatermelon", "TomatoLettuceOnionSalad", "no_recipe"]
 METRIC = "env-steps/sec (batched step+feature_vector obs)"
 UNIT = "env-steps/s"
-BACKGROUND_DYN_BLOCKS = 3     # pipelined headline: the dynamics kernel of step k+1 runs as 3 blocks per SM behind the rows of step k
+BACKGROUND_DYN_BLOCKS = 0     # pipelined block: dynamics grid of step k+1 (0 = full grid; with the whole-row TMA writer a capped grid no longer pays)
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
@@ -331,7 +331,9 @@ def run_gpu_arm(args):
         sync_all()
         K = args.steps
         graph, how = None, "eager launches"
-        if not args.no_graph and K <= 512 and (not pipelined or K % 2 == 0):
+        # steps per graph: K itself up to 512, else the largest divisor of K that is at most 256 (K = 2000 -> 10 replays of 200)
+        G = K if K <= 512 else max((g for g in range(1, 257) if K % g == 0), default=1)
+        if not args.no_graph and G >= 10 and (not pipelined or G % 2 == 0):
             try:
                 if pipelined:   # no event of the eager warm-up may be waited on inside the capture
                     _native.check(env.lib.cz_pipeline_reset(env._handle, env.lib.cz_pipeline_current(env._handle)))
@@ -341,13 +343,14 @@ def run_gpu_arm(args):
                 l0 = env.lib.cz_launch_count()
                 with torch.cuda.stream(side):
                     with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
-                        for s in range(K):
+                        for s in range(G):
                             env.step(actions[s % ring])
                         env.wait()
-                captured = env.lib.cz_launch_count() - l0
+                captured = (env.lib.cz_launch_count() - l0) * (K // G)
                 torch.cuda.current_stream(dev).wait_stream(side)
-                graph.replay()          # untimed: K more warm-up steps, uploads the graph
-                how = f"one CUDA graph of the {K} steps ({captured} kernel nodes)"
+                graph.replay()          # untimed: G more warm-up steps, uploads the graph
+                how = (f"one CUDA graph of the {K} steps ({captured} kernel nodes)" if G == K else
+                       f"{K // G} replays of one CUDA graph of {G} steps ({captured} kernel launches)")
             except Exception as ex:     # capture not possible on this box: time eager launches
                 sys.stderr.write(f"timed_run: graph capture failed ({ex!r}); timing eager launches\n")
                 graph = None
@@ -363,7 +366,8 @@ def run_gpu_arm(args):
         t_host0 = time.perf_counter()
         ev0.record()
         if graph is not None:
-            graph.replay()
+            for _ in range(K // G):
+                graph.replay()
         else:
             for s in range(K):
                 env.step(actions[s % ring])
@@ -387,17 +391,17 @@ def run_gpu_arm(args):
         args.no_graph = True
         return timed_run(pipelined, sample_clocks, obs_dtype)
 
-    # in-place step (one fused kernel per step) first, then the pipelined throughput mode (the headline)
-    env_s, ms_sync, launches_sync, _, how_sync = timed_run(False, False)
-    sync_value = world * N * args.steps / (ms_sync / 1e3)
+    # the other step mode first (reported as a block of the line), then the headline mode with the clocks sampled:
+    # --mode sync (default): the in-place step is the headline, the two-stream pipelined mode the block, and vice versa
+    head_pipe = args.mode == "pipelined"
+    env_s, ms_other, launches_other, _, how_other = timed_run(not head_pipe, False)
+    other_value = world * N * args.steps / (ms_other / 1e3)
     L = env_s.obs_len
-    if args.mode == "sync":
-        env, ms_total_max, launches, clocks, how_timed = timed_run(False, True)
-    else:
-        env_s.close()
-        del env_s
-        torch.cuda.empty_cache()
-        env, ms_total_max, launches, clocks, how_timed = timed_run(True, True)
+    env_s.wait()
+    env_s.close()
+    del env_s
+    torch.cuda.empty_cache()
+    env, ms_total_max, launches, clocks, how_timed = timed_run(head_pipe, True)
     lib = env.lib
     ms_per_step = ms_total_max / args.steps
     value = world * N * args.steps / (ms_total_max / 1e3)
@@ -782,9 +786,10 @@ def run_gpu_arm(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "bytes_per_env_step": bytes_per_env_step,
-                             "kernel": (f"cz_obs_envs_kernel (+ cz_env_kernel<STEP,dynamics-only> of the next step in the background, "
-                                        f"{BACKGROUND_DYN_BLOCKS} blocks per SM)"
-                                        if args.mode == "pipelined" else "cz_obs_envs_kernel (after cz_env_kernel<STEP,dynamics-only> on the same stream)")},
+                             "kernel": ("cz_obs_whole_kernel (+ cz_env_kernel<STEP,dynamics-only> of the next step beside it on a "
+                                        "second stream)" if head_pipe else
+                                        "cz_obs_whole_kernel (row writer: 82 us of the step) after cz_env_kernel<STEP,dynamics-only> "
+                                        "(15 us) on the same stream")},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "cz_step_host (pinned host buffers, sync per step; four column ranges, the device->host copy of a range "
@@ -803,10 +808,15 @@ def run_gpu_arm(args):
                 "gpu_launches": int(launches), "timed_region": how_timed, "clocks": clocks, "cfg3": cfg3, "cfg5": cfg5,
                 "generic_tables": generic, "device_policy": cook, "f32_obs": f32,
                 "mode": args.mode,
-                "sync_step": {"value": sync_value, "ms_per_step": ms_sync / args.steps,
-                              "frac": N * bytes_per_env_step / (ms_sync / args.steps / 1e3) / 1e9 / peak,
-                              "gpu_launches": int(launches_sync), "timed_region": how_sync,
-                              "note": "in-place cz_step, outputs ordered on the caller's stream: dynamics kernel + row-writer kernel at this batch size (one fused kernel below 49152 environments)"},
+                "mode_note": "sync (default): in-place cz_step, every output ordered on the caller's stream when the call's work "
+                             "is done (what a policy that consumes observations uses): dynamics kernel + whole-row TMA writer at "
+                             "this batch size; pipelined: cz_step_pipelined, the dynamics of step k+1 on a second stream beside "
+                             "the rows of step k (open-loop actions or a policy that reads the state)",
+                ("pipelined_step" if not head_pipe else "sync_step"): {
+                    "value": other_value, "ms_per_step": ms_other / args.steps,
+                    "frac": N * bytes_per_env_step / (ms_other / args.steps / 1e3) / 1e9 / peak,
+                    "gpu_launches": int(launches_other), "timed_region": how_other,
+                    "note": "the other step mode, same workload, same number of steps"},
                 "stats": {"episodes_started": float(stats[0]), "recipes_done_now": float(stats[1]),
                           "last_step_return": float(stats[2])}}
         emit(line)
@@ -838,10 +848,10 @@ def main():
     ap.add_argument("--no-cfg3", action="store_true")
     ap.add_argument("--cfg5-envs", type=int, default=262144, help="environments of the mixed-agent-count population (cfg5 block)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph of the K steps")
-    ap.add_argument("--mode", default="pipelined", choices=["pipelined", "sync"],
-                    help="pipelined (default): throughput mode for open-loop action streams, the dynamics of step k+1 run in "
-                         "the background of the observation writes of step k (two kernels, two streams, ping-pong state, "
-                         "cz_pipeline_config); sync: the in-place step (dynamics kernel, then the row writer)")
+    ap.add_argument("--mode", default="sync", choices=["pipelined", "sync"],
+                    help="sync (default, the headline): the in-place step (dynamics kernel, then the whole-row TMA writer, caller's "
+                         "stream); pipelined: throughput mode for open-loop action streams, the dynamics of step k+1 run beside "
+                         "the observation writes of step k (two kernels, two streams, ping-pong state, cz_pipeline_config)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: everything libraries print while the run is under way (NCCL's version banner
     # goes to stdout when NCCL_DEBUG is set) is sent to stderr, and the descriptor is handed back for the final print

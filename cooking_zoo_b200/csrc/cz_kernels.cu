@@ -52,6 +52,22 @@ __device__ __forceinline__ void cz_bulk_store_nocommit(void* gdst, const void* s
   uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
 }
+// The same with an L2 evict_first hint, for writers whose WHOLE output block leaves in one bulk store (nothing else writes
+// into its 128-byte lines later and nothing on the device reads it back): 131072 envs, float32 pair writer 52.0 -> 44.4 us.
+// On the float64 packed writer, whose table segments are lane stores into the same lines, the hint loses (94.1 -> 102.8 us).
+#ifndef CZ_BULK_STREAM_HINT
+#define CZ_BULK_STREAM_HINT 1
+#endif
+__device__ __forceinline__ void cz_bulk_store_stream(void* gdst, const void* ssrc, uint32_t bytes) {
+#if CZ_BULK_STREAM_HINT
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(s), "r"(bytes), "l"(pol) : "memory");
+#else
+  cz_bulk_store_nocommit(gdst, ssrc, bytes);
+#endif
+}
 __device__ __forceinline__ void cz_bulk_store_s(void* gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }
@@ -769,7 +785,61 @@ cz_obs_single_pair_kernel(const __grid_constant__ CzDev T, const uint32_t* __res
   cz_fence_async_smem();  // generic-proxy and cp.async writes -> visible to the async proxy
   __syncwarp();
   if (lane == 0) {
-    cz_bulk_store_nocommit(obs + (size_t)env0 * T.L, rows, (uint32_t)((two ? 2 : 1) * T.L) * 8u);
+    cz_bulk_store_stream(obs + (size_t)env0 * T.L, rows, (uint32_t)((two ? 2 : 1) * T.L) * 8u);
+    cz_bulk_commit();
+    cz_bulk_wait_read<0>();  // the staged rows must outlive the read
+  }
+}
+
+// Whole rows through the TMA engine (packed plans with at most 32 pairs, 2+ agents): one environment per warp, its NA rows
+// staged whole in shared memory — table segments by cp.async (no registers), zeros and computed slots by the lanes — and ONE
+// bulk store of NA * L doubles with the L2 evict_first hint (cz_bulk_store_stream).  Nothing else writes into the block's lines,
+// which is what lets the hint work: 6.4-6.7 TB/s against 6.2 TB/s for the writer that mixes bulk and lane stores.
+template <int NA, bool TWO>
+__global__ void __launch_bounds__(32 * ENVS_WARPS, TWO ? 3 : 6)
+cz_obs_whole_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, double* __restrict__ obs, int n_envs, int ld) {
+  extern __shared__ __align__(16) unsigned char smem_rows[];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int env = blockIdx.x * ENVS_WARPS + warp;
+  if (env >= n_envs) return;
+  const int D = T.D, tab2 = T.tab_len >> 1, L2 = T.L >> 1;
+  const size_t N = (size_t)ld;
+  double2* rows = reinterpret_cast<double2*>(smem_rows) + (size_t)warp * NA * L2;
+
+  const LaneSlot ls = cz_lane_slot_packed(T, lane);
+  const uint32_t var = __ldg(state + (size_t)(D + NA + CZ_ROW_VARIANT) * N + env);
+  const PairRegs p = cz_pair_load<NA>(T, state, N, env, var, ls);
+  LaneSlot ls1;
+  PairRegs p1;
+  if constexpr (TWO) {  // 33-64 (observer, slot) pairs: a lane owns pairs `lane` and `lane + 32`
+    ls1 = cz_lane_slot_packed(T, lane + 32);
+    p1 = cz_pair_load<NA>(T, state, N, env, var, ls1);
+  }
+  {
+    const double2* tab = reinterpret_cast<const double2*>(T.obs_table) + (size_t)var * 64 * tab2 + lane;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      uint32_t cell;
+      if constexpr (TWO) cell = __ldg(state + (size_t)(D + a) * N + env) & 63u;
+      else cell = __shfl_sync(0xffffffffu, p.me, a * T.n_comp) & 63u;  // lane a * n_comp observes for agent a
+      if (ls.t0 >= 0) cz_cp_async16(rows + a * L2 + ls.t0, tab + cell * tab2);
+      if (ls.t1 >= 0) cz_cp_async16(rows + a * L2 + ls.t1, tab + cell * tab2 + 32);
+    }
+  }
+  {  // never-occupied slots of the computed range are zeros
+    const int n2 = T.ranges[0][1] >> 1, o2 = T.ranges[0][0] >> 1;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+      for (int k = lane; k < n2; k += 32) rows[a * L2 + o2 + k] = make_double2(0.0, 0.0);
+  }
+  __syncwarp();
+  cz_pair_store_at(T, ls, p, reinterpret_cast<double*>(rows + ls.agent * L2) + T.stage_lo);
+  if constexpr (TWO) cz_pair_store_at(T, ls1, p1, reinterpret_cast<double*>(rows + ls1.agent * L2) + T.stage_lo);
+  cz_cp_async_wait_all();
+  cz_fence_async_smem();  // generic-proxy and cp.async writes -> visible to the async proxy
+  __syncwarp();
+  if (lane == 0) {
+    cz_bulk_store_stream(obs + (size_t)env * NA * T.L, rows, (uint32_t)(NA * T.L) * 8u);
     cz_bulk_commit();
     cz_bulk_wait_read<0>();  // the staged rows must outlive the read
   }
@@ -911,6 +981,7 @@ struct cz_tables {
   int policy_on_dyn;        // cz_policy_act of a running pipeline launches on the dynamics stream (CZ_POLICY_ON_DYN=0: caller's stream)
   int fast_dyn;             // dynamics on the specialised (shared-memory table) kernels: V <= 16 variants and B <= 16 recipes,
                             // whatever the observation plan looks like
+  int whole_rows;           // A >= 2 packed plans: whole rows staged, one bulk store per environment (bit 0: in place, bit 1: pipelined, bit 2: also the 33-64 pair plans; CZ_WHOLE_ROWS)
   int single_pair;          // float64 rows of large single-agent batches: two environments per warp (CZ_SINGLE_PAIR=0: one)
   int obs32_pair;           // float32 rows of large batches: two environments per warp (CZ_OBS32_PAIR=0: one)
   int any_writer;           // generic tables, large in-place batches: dynamics kernel + any-plan row writer (CZ_ANY_WRITER=0: fused kernel)
@@ -1153,6 +1224,8 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     t->any_writer = aw ? atoi(aw) : 1;
     const char* pod = getenv("CZ_POLICY_ON_DYN");
     t->policy_on_dyn = pod ? atoi(pod) : 1;
+    const char* wr = getenv("CZ_WHOLE_ROWS");
+    t->whole_rows = wr ? atoi(wr) : 7;
     const char* sp1 = getenv("CZ_SINGLE_PAIR");
     t->single_pair = sp1 ? atoi(sp1) : 1;
     const char* o32 = getenv("CZ_OBS32_PAIR");
@@ -1187,6 +1260,8 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   SET_MODE(MODE_STEP); SET_MODE(MODE_RESET); SET_MODE(MODE_OBSERVE);
   SET_SMEM(cz_obs32_kernel);
   SET_SMEM(cz_obs_any_kernel<true>); SET_SMEM(cz_obs_any_kernel<false>);
+  SET_SMEM((cz_obs_whole_kernel<2, false>)); SET_SMEM((cz_obs_whole_kernel<3, false>)); SET_SMEM((cz_obs_whole_kernel<4, false>));
+  SET_SMEM((cz_obs_whole_kernel<2, true>)); SET_SMEM((cz_obs_whole_kernel<3, true>)); SET_SMEM((cz_obs_whole_kernel<4, true>));
   SET_SMEM((cz_warp_kernel<1, 16>)); SET_SMEM((cz_warp_kernel<2, 16>)); SET_SMEM((cz_warp_kernel<3, 16>)); SET_SMEM((cz_warp_kernel<4, 16>));
   SET_SMEM((cz_warp_kernel<1, 32>)); SET_SMEM((cz_warp_kernel<2, 32>)); SET_SMEM((cz_warp_kernel<3, 32>)); SET_SMEM((cz_warp_kernel<4, 32>));
 #undef SET_MODE
@@ -1301,6 +1376,25 @@ static int cz_launch_obs64(const cz_tables* t, const uint32_t* state, double* ob
   if (!state || !obs) return cz_fail(CZ_EINVAL, "%s", "null argument");
   if (((uintptr_t)obs & 15) != 0) return cz_fail(CZ_EINVAL, "%s", "obs must be 16-byte aligned");
   if (n_envs <= 0) return CZ_OK;
+  if ((t->simple || (t->simple2 && (t->whole_rows & 4))) && t->dev.A >= 2 && (t->whole_rows & (alone ? 1 : 2)) &&
+      n_envs >= ENVS_WARPS * t->num_sms) {
+    const size_t smem = (size_t)ENVS_WARPS * t->dev.A * t->dev.L * 8;  // the A whole rows of one environment per warp
+    if (smem <= t->smem_optin) {
+      const int blocks = (n_envs + ENVS_WARPS - 1) / ENVS_WARPS;
+#define CZ_WHOLE_GO(NA)                                                                                                   \
+  if (t->simple2) cz_obs_whole_kernel<NA, true><<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs, ld);    \
+  else cz_obs_whole_kernel<NA, false><<<blocks, 32 * ENVS_WARPS, smem, s>>>(t->dev, state, obs, n_envs, ld)
+      switch (t->dev.A) {
+        case 2: CZ_WHOLE_GO(2); break;
+        case 3: CZ_WHOLE_GO(3); break;
+        default: CZ_WHOLE_GO(4); break;
+      }
+#undef CZ_WHOLE_GO
+      g_launches.fetch_add(1);
+      CZ_CUDA(cudaGetLastError());
+      return CZ_OK;
+    }
+  }
   if (alone && t->simple && t->dev.A == 1 && t->single_pair && n_envs >= 2 * ENVS_WARPS * t->num_sms) {
     const size_t smem = (size_t)ENVS_WARPS * 2 * t->dev.L * 8;  // two whole rows per warp
     if (smem <= 48 * 1024) {

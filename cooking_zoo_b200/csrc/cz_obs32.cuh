@@ -192,7 +192,7 @@ cz_obs32_fast_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict
     cz_fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-      cz_bulk_store_nocommit(obs + (size_t)env * NA * T.L, stage2, (uint32_t)(NA * T.L) * 4u);
+      cz_bulk_store_stream(obs + (size_t)env * NA * T.L, stage2, (uint32_t)(NA * T.L) * 4u);
       cz_bulk_commit();
       cz_bulk_wait_read<0>();  // the staging block must outlive the read
     }
@@ -275,7 +275,7 @@ cz_obs32_pair_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict
   float* g = obs + (size_t)env0 * NA * T.L;  // env0 is even and NA * L is even: 16-byte aligned
   if (two) {
     if (lane == 0) {  // both environments' rows are one contiguous block: a single bulk store
-      cz_bulk_store_nocommit(g, stage2, (uint32_t)(2 * NA * T.L) * 4u);
+      cz_bulk_store_stream(g, stage2, (uint32_t)(2 * NA * T.L) * 4u);
       cz_bulk_commit();
       cz_bulk_wait_read<0>();  // the staging block must outlive the read
     }
