@@ -940,6 +940,95 @@ cz_obs_any_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ 
   }
 }
 
+// The any-plan writer with WHOLE rows staged (A * L even, so that an environment's block is 16-byte aligned): table
+// segments by cp.async into their place in the staged rows, zeros over the computed ranges, computed slots by the lanes, and
+// one bulk store of the environment's A * L doubles with the L2 evict_first hint — the structure of cz_obs_whole_kernel
+// with loops where that kernel has one element per lane.
+__device__ __forceinline__ void cz_cp_async8d(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * ENVS_WARPS, 5)
+cz_obs_any_whole_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, double* __restrict__ obs, int n_envs,
+                        int ld, int warps_per_block) {
+  extern __shared__ __align__(16) unsigned char smem_any[];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int env = blockIdx.x * warps_per_block + warp;
+  if (warp >= warps_per_block || env >= n_envs) return;
+  const int A = T.A, D = T.D, L = T.L;
+  const size_t N = (size_t)ld;
+  double* rows = reinterpret_cast<double*>(smem_any) + (size_t)warp * A * L;  // A * L is even: every warp's block is 16-byte aligned
+  const uint32_t* misc = state + (size_t)(D + A) * N;
+  const uint32_t var = __ldg(misc + (size_t)CZ_ROW_VARIANT * N + env);
+  const uint32_t sbits = __ldg(misc + (size_t)CZ_ROW_SBITS * N + env);
+  const bool even = (L & 1) == 0;
+  for (int a = 0; a < A; ++a) {
+    double* srow = rows + a * L;
+    const uint32_t cell = __ldg(state + (size_t)(D + a) * N + env) & 63u;
+    const double* tab = T.obs_table + ((size_t)var * 64 + cell) * T.tab_len;
+    for (int sg = 0; sg < T.n_segs; ++sg) {  // table segments: table -> their place in the staged row, no registers
+      const int o = T.segs[sg][0], n = T.segs[sg][1], to = T.segs[sg][2];
+      if (even && !((o | n | to) & 1)) {
+        for (int k = lane; k < (n >> 1); k += 32) cz_cp_async16(srow + o + 2 * k, tab + to + 2 * k);
+      } else {
+        for (int k = lane; k < n; k += 32) cz_cp_async8d(srow + o + k, tab + to + k);
+      }
+    }
+    for (int r = 0; r < T.n_ranges; ++r) {  // never-occupied slots of the computed ranges are zeros
+      const int o = T.ranges[r][0], n = T.ranges[r][1];
+      for (int k = lane; k < n; k += 32) srow[o + k] = 0.0;
+    }
+  }
+  __syncwarp();
+  // computed slots: a lane takes (observer, slot) pairs lane, lane + 32, ... (pair p = observer * n_comp + slot)
+  const int n_pairs = A * T.n_comp;
+  for (int pr = lane; pr < n_pairs; pr += 32) {
+    const int a = (pr >= T.n_comp) + (pr >= 2 * T.n_comp) + (pr >= 3 * T.n_comp);  // A <= 4: no division
+    const int q = pr - a * T.n_comp;
+    const uint32_t d = __ldg(T.comp_slots + q);
+    const int off = (int)(d & 0xFFFu);
+    const uint32_t flen = (d >> 12) & 7u, kind = (d >> 15) & 3u, idx = (d >> 17) & 255u;
+    uint32_t rec = 0, fb4 = 0;
+    bool present;
+    if (kind != 0u) {
+      const bool is_agent = kind == 2u;
+      const bool exists = !is_agent || (int)idx < A;
+      rec = exists ? __ldg(state + (size_t)(is_agent ? D + idx : idx) * N + env) : 0u;
+      present = is_agent ? exists : (rec & O_PRESENT) != 0;
+      const uint32_t c = (rec >> 7) & 1u, m = (rec >> 8) & 1u;
+      fb4 = is_agent ? ((1u << A_ORI(rec)) >> 1) : (((c | m) ^ 1u) | c << 1 | m << 2);
+    } else {  // live Switch / Block (world_objects.py:174,221)
+      const uint32_t cell = __ldg(T.static_cells + var * T.S + idx);
+      present = cell != 0xFFu;
+      rec = present ? cell : 0u;
+      const uint32_t g = __ldg(T.grid + var * 64 + rec);
+      fb4 = ((g & 15u) == ST_SWITCH ? (sbits >> (12 + (g >> 4))) : (sbits >> (16 + (g >> 4)))) & 1u;
+    }
+    const uint32_t one = 1u << (flen - 1);
+    const uint32_t fb = present ? ((fb4 & (one - 1u)) | one) : 0u;
+    const int x = rec & 7u, y = (rec >> 3) & 7u;
+    const uint32_t me = __ldg(state + (size_t)(D + a) * N + env);
+    const bool self = kind == 2u && (int)idx == a;  // the observer's own entry is x / W, y / H (cooking_env.py:364-368)
+    double X = __ldg(T.xlut + (x - (self ? 0 : (int)(me & 7u)) + T.W - 1));
+    double Y = __ldg(T.ylut + (y - (self ? 0 : (int)((me >> 3) & 7u)) + T.H - 1));
+    if (!present) { X = 0.0; Y = 0.0; }
+    double* out = rows + a * L + off;
+    out[0] = X;
+    out[1] = Y;
+#pragma unroll
+    for (uint32_t k = 0; k < 5; ++k)
+      if (k < flen) *reinterpret_cast<uint2*>(out + 2 + k) = make_uint2(0u, (fb >> k & 1u) ? 0x3FF00000u : 0u);
+  }
+  cz_cp_async_wait_all();
+  cz_fence_async_smem();  // generic-proxy and cp.async writes -> visible to the async proxy
+  __syncwarp();
+  if (lane == 0) {
+    cz_bulk_store_stream(obs + (size_t)env * A * L, rows, (uint32_t)(A * L) * 8u);
+    cz_bulk_commit();
+    cz_bulk_wait_read<0>();  // the staged rows must outlive the read
+  }
+}
+
 // =========================================================================================
 // Host side: tables object and the C ABI
 // =========================================================================================
@@ -981,7 +1070,7 @@ struct cz_tables {
   int policy_on_dyn;        // cz_policy_act of a running pipeline launches on the dynamics stream (CZ_POLICY_ON_DYN=0: caller's stream)
   int fast_dyn;             // dynamics on the specialised (shared-memory table) kernels: V <= 16 variants and B <= 16 recipes,
                             // whatever the observation plan looks like
-  int whole_rows;           // A >= 2 packed plans: whole rows staged, one bulk store per environment (bit 0: in place, bit 1: pipelined, bit 2: also the 33-64 pair plans; CZ_WHOLE_ROWS)
+  int whole_rows;           // A >= 2 packed plans: whole rows staged, one bulk store per environment (bit 0: in place, bit 1: pipelined, bit 2: also the 33-64 pair plans, bit 3: the any-plan writer; CZ_WHOLE_ROWS)
   int single_pair;          // float64 rows of large single-agent batches: two environments per warp (CZ_SINGLE_PAIR=0: one)
   int obs32_pair;           // float32 rows of large batches: two environments per warp (CZ_OBS32_PAIR=0: one)
   int any_writer;           // generic tables, large in-place batches: dynamics kernel + any-plan row writer (CZ_ANY_WRITER=0: fused kernel)
@@ -1225,7 +1314,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     const char* pod = getenv("CZ_POLICY_ON_DYN");
     t->policy_on_dyn = pod ? atoi(pod) : 1;
     const char* wr = getenv("CZ_WHOLE_ROWS");
-    t->whole_rows = wr ? atoi(wr) : 7;
+    t->whole_rows = wr ? atoi(wr) : 15;
     const char* sp1 = getenv("CZ_SINGLE_PAIR");
     t->single_pair = sp1 ? atoi(sp1) : 1;
     const char* o32 = getenv("CZ_OBS32_PAIR");
@@ -1259,7 +1348,7 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
   SET_SMEM((cz_env_kernel<M, OBS_NONE, 3>)); SET_SMEM((cz_env_kernel<M, OBS_NONE, 4>))
   SET_MODE(MODE_STEP); SET_MODE(MODE_RESET); SET_MODE(MODE_OBSERVE);
   SET_SMEM(cz_obs32_kernel);
-  SET_SMEM(cz_obs_any_kernel<true>); SET_SMEM(cz_obs_any_kernel<false>);
+  SET_SMEM(cz_obs_any_kernel<true>); SET_SMEM(cz_obs_any_kernel<false>); SET_SMEM(cz_obs_any_whole_kernel);
   SET_SMEM((cz_obs_whole_kernel<2, false>)); SET_SMEM((cz_obs_whole_kernel<3, false>)); SET_SMEM((cz_obs_whole_kernel<4, false>));
   SET_SMEM((cz_obs_whole_kernel<2, true>)); SET_SMEM((cz_obs_whole_kernel<3, true>)); SET_SMEM((cz_obs_whole_kernel<4, true>));
   SET_SMEM((cz_warp_kernel<1, 16>)); SET_SMEM((cz_warp_kernel<2, 16>)); SET_SMEM((cz_warp_kernel<3, 16>)); SET_SMEM((cz_warp_kernel<4, 16>));
@@ -1428,6 +1517,18 @@ static int cz_launch_obs_any(const cz_tables* t, const uint32_t* state, double* 
   if (n_envs <= 0) return CZ_OK;
   if (ld <= 0) ld = n_envs;
   const CzDev& T = t->dev;
+  if ((t->whole_rows & 8) && ((T.A * T.L) & 1) == 0 && ((uintptr_t)obs & 15) == 0) {  // whole rows staged, one bulk store per environment
+    const size_t pw = (size_t)T.A * T.L * sizeof(double);
+    int warps = (int)(((size_t)72 * 1024) / pw);  // at least three blocks per SM stay resident
+    if (warps > ENVS_WARPS) warps = ENVS_WARPS;
+    if (warps >= 1) {
+      const int blocks = (n_envs + warps - 1) / warps;
+      cz_obs_any_whole_kernel<<<blocks, 32 * ENVS_WARPS, pw * warps, s>>>(t->dev, state, obs, n_envs, ld, warps);
+      g_launches.fetch_add(1);
+      CZ_CUDA(cudaGetLastError());
+      return CZ_OK;
+    }
+  }
   const size_t per_warp = (size_t)T.A * ((T.stage_len + 1) & ~1) * sizeof(double);
   int warps = per_warp ? (int)(((size_t)96 * 1024) / per_warp) : ENVS_WARPS;  // at least two blocks per SM stay resident
   if (warps > ENVS_WARPS) warps = ENVS_WARPS;
