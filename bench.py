@@ -574,14 +574,14 @@ def run_gpu_arm(args):
                     "errors": {k: v for k, v in out5.items() if k.endswith("_error")},
                     "how": "10 closed-loop steps of every group captured as one CUDA graph (MixedAgentCookingEnv.cook_steps(10): four "
                            "independent stream branches, 2-3 kernels per group and step; the groups are not re-joined between steps)",
-                    "size_note": "four groups share the GPU, so the rate grows with the population: 65536 / 131072 / 262144 envs = "
-                                 "0.57 / 0.72 / 0.78 G env-steps/s (0.52 / 0.66 / 0.72 of roofline; profiles/r02_notes.md)",
+                    "size_note": "four groups share the GPU, so the rate grows with the population (profiles/r02_notes.md §5, §7, §15)",
                     "eager_env_steps_per_s": {"in_place": out5.get("in_place_eager"), "pipelined": out5.get("pipelined_eager"),
                                               "note": "host-bound: ~8 library calls and 8 stream joins per population step"},
                     "bytes_per_env_step": b5,
-                    "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": (out5.get("pipelined") or 0) * b5 / 1e9, "peak": peak,
-                                 "frac": (out5.get("pipelined") or 0) * b5 / 1e9 / peak,
-                                 "in_place_frac": (out5.get("in_place") or 0) * b5 / 1e9 / peak}}
+                    "roofline": {"bound": "hbm", "unit": "GB/s", "achieved": (out5.get("in_place") or 0) * b5 / 1e9, "peak": peak,
+                                 "frac": (out5.get("in_place") or 0) * b5 / 1e9 / peak,
+                                 "mode": "in place (like the headline)",
+                                 "pipelined_frac": (out5.get("pipelined") or 0) * b5 / 1e9 / peak}}
         except Exception as ex:
             cfg5 = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
 
