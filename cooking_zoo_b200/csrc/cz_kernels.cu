@@ -1659,7 +1659,7 @@ static int cz_launch_warp(const cz_tables* t, uint32_t* state, const uint8_t* ac
   const int G = t->warp_group;
   const int groups = WK_WARPS * 32 / G;
   const int blocks = (n_envs + groups - 1) / groups;
-  const size_t smem = wk_smem_bytes(T.V, T.A, T.stage_len, G);
+  const size_t smem = wk_smem_bytes(T.V, T.A, CZ_WARP_WHOLE ? T.L : T.stage_len, G);
   cudaStream_t s = (cudaStream_t)stream;
 #define CZ_WARP_GO(NA)                                                                                                          \
   if (G == 16)                                                                                                                 \

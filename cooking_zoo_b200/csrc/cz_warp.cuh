@@ -13,6 +13,9 @@
 // /root/reference/cooking_zoo/...  Bit-identity with cz_step x K is tested in tests/test_gpu_ksteps.py.
 // Included by cz_kernels.cu (needs BlockSmem, LaneSlot, cz_lane_slot_packed).
 #pragma once
+#ifndef CZ_WARP_WHOLE
+#define CZ_WARP_WHOLE 0  // 1: whole rows staged (table segments by cp.async), one bulk store per environment and step (A/B build)
+#endif
 #ifndef CZ_WARP_TMA
 #define CZ_WARP_TMA 1  // the computed range of the rows leaves through cp.async.bulk (0: lane stores; K = 64: 4.45 vs 4.71 us per step)
 #endif
@@ -660,7 +663,7 @@ __device__ __forceinline__ void wk_step_env(const CzDev& T, WEnv<NA, G>& e, cons
 // `pm`: 0-11 row offset | 12-14 features after x,y | 15-16 kind | 17-24 index | 25-26 observer; `live`: the pair exists.
 template <int NA, int G>
 __device__ __forceinline__ void wk_pair_store(const CzDev& T, const WEnv<NA, G>& e, uint32_t pm, bool live, const double* sxl,
-                                              const double* syl, double2* stage, int stage2) {
+                                              const double* syl, double2* stage, int stage2, int lo) {
   constexpr bool FAST = true;
   const SmemTabs* st = e.st;
   const uint32_t flen = (pm >> 12) & 7u, kind = (pm >> 15) & 3u, idx = (pm >> 17) & 255u;
@@ -688,7 +691,7 @@ __device__ __forceinline__ void wk_pair_store(const CzDev& T, const WEnv<NA, G>&
   double X = sxl[x - (self ? 0 : (int)(me & 7u))];
   double Y = syl[y - (self ? 0 : (int)((me >> 3) & 7u))];
   if (!present) { X = 0.0; Y = 0.0; }
-  double* out = reinterpret_cast<double*>(stage + observer * stage2) + ((int)(pm & 0xFFFu) - T.stage_lo);
+  double* out = reinterpret_cast<double*>(stage + observer * stage2) + ((int)(pm & 0xFFFu) - lo);  // lo: row element at stage[0]
   out[0] = X;
   out[1] = Y;
 #pragma unroll
@@ -735,7 +738,7 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
     const int4 lm = __ldg(T.lane_map + threadIdx.x);
     pmap[threadIdx.x] = lm.x >= 0 ? ((uint32_t)lm.x & 0x1FFFFFFu) | ((uint32_t)lm.y << 25) : 0u;
   }
-  const int stage2 = (T.stage_len + 1) >> 1;  // double2 per staging row
+  const int stage2 = CZ_WARP_WHOLE ? (T.L >> 1) : ((T.stage_len + 1) >> 1);  // double2 per staging row (whole rows or the computed span)
   unsigned char* gsm = smem_wk + head + 256 + (size_t)grp * (WK_WORDS * 4 + (size_t)NA * stage2 * 16);
   uint32_t* wwords = reinterpret_cast<uint32_t*>(gsm);  // cells[64] | skp[8] | plist[32] uint2
   double2* stage = reinterpret_cast<double2*>(gsm + WK_WORDS * 4);
@@ -847,9 +850,30 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
       for (int q0 = 0; q0 < n_pairs; q0 += G) {
         const int q = q0 + g;
         const bool live = q < n_pairs;
-        wk_pair_store(T, e, live ? pmap[q] : 0u, live, sxl, syl, stage, stage2);
+        wk_pair_store(T, e, live ? pmap[q] : 0u, live, sxl, syl, stage, stage2, CZ_WARP_WHOLE ? 0 : T.stage_lo);
       }
-#if CZ_WARP_TMA
+#if CZ_WARP_WHOLE
+      {  // table segments of the NA rows: global -> their place in the staged rows, no registers
+        const double2* tabw = tab_lane + (size_t)e.variant * 64 * tab2;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          const double2* src = tabw + A_XY(e.ag[a]) * tab2;
+#pragma unroll
+          for (int j = 0; j < TK; ++j)
+            if (tdst[j] >= 0) cz_cp_async16(stage + a * stage2 + tdst[j], src + j * G);
+        }
+      }
+      cz_cp_async_wait_all();
+      cz_fence_async_smem();  // generic-proxy and cp.async writes -> visible to the async proxy
+      g_sync(e);
+      if (g == 0) {  // the NA rows of the environment are contiguous: one bulk store
+        cz_bulk_store_nocommit(g2, stage, (uint32_t)(NA * T.L) * 8u);
+        cz_bulk_commit();
+      }
+    }
+    if (false) {
+      double2* g2 = nullptr;
+#elif CZ_WARP_TMA
       // the computed range of the NA rows leaves through the TMA engine: one elected lane, one bulk store per row
       cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
       g_sync(e);
