@@ -14,7 +14,8 @@
 // Included by cz_kernels.cu (needs BlockSmem, LaneSlot, cz_lane_slot_packed).
 #pragma once
 #ifndef CZ_WARP_WHOLE
-#define CZ_WARP_WHOLE 0  // 1: whole rows staged (table segments by cp.async), one bulk store per environment and step (A/B build)
+#define CZ_WARP_WHOLE 1  // whole rows staged (table segments by cp.async), one bulk store per environment and step
+                        // (config 3, K = 64: 4.33 against 4.44 us per step for CZ_WARP_TMA alone; 0: A/B build)
 #endif
 #ifndef CZ_WARP_TMA
 #define CZ_WARP_TMA 1  // the computed range of the rows leaves through cp.async.bulk (0: lane stores; K = 64: 4.45 vs 4.71 us per step)
@@ -843,37 +844,37 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
     // ---- get_feature_vector (cooking_env.py:352-373): the A rows of this step
     if (obs) {
       double2* g2 = reinterpret_cast<double2*>(obs + ((keep ? (size_t)k * N : 0) + (size_t)env) * NA * T.L);
-#if CZ_WARP_TMA
+#if CZ_WARP_TMA || CZ_WARP_WHOLE
       if (g == 0) cz_bulk_wait_read<0>();  // the TMA engine has read the staging rows of the previous step
 #endif
       g_sync(e);  // the copy-out of the previous step has read the staging rows
+      const double2* tab = tab_lane + (size_t)e.variant * 64 * tab2;
+#if CZ_WARP_WHOLE
+      // whole rows staged: the table segments of the NA rows go global -> their place in the rows (cp.async, no registers,
+      // in flight under the pair stores), then ONE bulk store of the environment's NA * L doubles
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const double2* src = tab + A_XY(e.ag[a]) * tab2;
+#pragma unroll
+        for (int j = 0; j < TK; ++j)
+          if (tdst[j] >= 0) cz_cp_async16(stage + a * stage2 + tdst[j], src + j * G);
+      }
+#endif
       for (int q0 = 0; q0 < n_pairs; q0 += G) {
         const int q = q0 + g;
         const bool live = q < n_pairs;
         wk_pair_store(T, e, live ? pmap[q] : 0u, live, sxl, syl, stage, stage2, CZ_WARP_WHOLE ? 0 : T.stage_lo);
       }
 #if CZ_WARP_WHOLE
-      {  // table segments of the NA rows: global -> their place in the staged rows, no registers
-        const double2* tabw = tab_lane + (size_t)e.variant * 64 * tab2;
-#pragma unroll
-        for (int a = 0; a < NA; ++a) {
-          const double2* src = tabw + A_XY(e.ag[a]) * tab2;
-#pragma unroll
-          for (int j = 0; j < TK; ++j)
-            if (tdst[j] >= 0) cz_cp_async16(stage + a * stage2 + tdst[j], src + j * G);
-        }
-      }
       cz_cp_async_wait_all();
       cz_fence_async_smem();  // generic-proxy and cp.async writes -> visible to the async proxy
       g_sync(e);
-      if (g == 0) {  // the NA rows of the environment are contiguous: one bulk store
+      if (g == 0) {
         cz_bulk_store_nocommit(g2, stage, (uint32_t)(NA * T.L) * 8u);
         cz_bulk_commit();
       }
-    }
-    if (false) {
-      double2* g2 = nullptr;
-#elif CZ_WARP_TMA
+#else
+#if CZ_WARP_TMA
       // the computed range of the NA rows leaves through the TMA engine: one elected lane, one bulk store per row
       cz_fence_async_smem();  // generic-proxy writes -> visible to the async proxy
       g_sync(e);
@@ -888,7 +889,6 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
       for (int a = 0; a < NA; ++a)
         for (int q = g; q < n2; q += G) g2[a * L2 + o2 + q] = stage[a * stage2 + s2 + q];
 #endif
-      const double2* tab = tab_lane + (size_t)e.variant * 64 * tab2;
 #pragma unroll
       for (int a = 0; a < NA; ++a) {  // table segments of row a: loads first, then the stores
         const double2* src = tab + A_XY(e.ag[a]) * tab2;
@@ -900,10 +900,11 @@ cz_warp_kernel(const __grid_constant__ CzDev T, uint32_t* __restrict__ state, co
         for (int j = 0; j < TK; ++j)
           if (tdst[j] >= 0) g2[a * L2 + tdst[j]] = v[j];
       }
+#endif
     }
   }
 
-#if CZ_WARP_TMA
+#if CZ_WARP_TMA || CZ_WARP_WHOLE
   if (obs && g == 0) cz_bulk_wait_read<0>();  // the staging rows must outlive the last bulk stores
 #endif
   // ---- registers -> state
