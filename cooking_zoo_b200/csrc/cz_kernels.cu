@@ -1308,7 +1308,8 @@ extern "C" int cz_tables_create(const cz_table_desc* d, int device, cz_tables** 
     if (g && (g[0] == '1' || g[0] == '2')) t->simple = t->simple2 = 0;
     if (g && g[0] == '1') t->fast_dyn = 0;
     const char* k = getenv("CZ_TWO_KERNEL_MIN_ENVS");
-    t->two_kernel_min_envs = k ? atoi(k) : 49152;  // measured crossover between 32768 and 65536 (profiles/r01_two_kernel_sweep.txt)
+    t->two_kernel_min_envs = k ? atoi(k) : 20480;  // measured crossover between 16384 and 24576 with the whole-row writer
+                                                    // (profiles/microbench/inplace_path_sweep.py; 49152 with the round-1 writer)
     const char* aw = getenv("CZ_ANY_WRITER");
     t->any_writer = aw ? atoi(aw) : 1;
     const char* pod = getenv("CZ_POLICY_ON_DYN");

@@ -227,7 +227,7 @@ def test_masked_reset_touches_only_the_selected_environments(agents):
 
 
 def test_large_batch_two_kernel_step_equals_the_fused_kernel_on_a_ragged_batch(monkeypatch):
-    """in-place steps of >= 49152 environments run the dynamics kernel and then the row-writer kernel; the fused kernel
+    """in-place steps of >= 20480 environments run the dynamics kernel and then the row-writer kernel; the fused kernel
     (forced here through CZ_TWO_KERNEL_MIN_ENVS=0, read when the tables are created) must give the same bits.
     50001 environments: neither a whole tile nor a whole writer block at the end."""
     cfg = dict(level="coop_test", meta_file="example", num_agents=2, max_steps=40,
