@@ -796,7 +796,7 @@ cz_obs_single_pair_kernel(const __grid_constant__ CzDev T, const uint32_t* __res
 // bulk store of NA * L doubles with the L2 evict_first hint (cz_bulk_store_stream).  Nothing else writes into the block's lines,
 // which is what lets the hint work: 6.4-6.7 TB/s against 6.2 TB/s for the writer that mixes bulk and lane stores.
 template <int NA, bool TWO>
-__global__ void __launch_bounds__(32 * ENVS_WARPS, TWO ? 3 : 6)
+__global__ void __launch_bounds__(32 * ENVS_WARPS, (TWO ? 3 : 6) * 8 / ENVS_WARPS)
 cz_obs_whole_kernel(const __grid_constant__ CzDev T, const uint32_t* __restrict__ state, double* __restrict__ obs, int n_envs, int ld) {
   extern __shared__ __align__(16) unsigned char smem_rows[];
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
