@@ -314,7 +314,7 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def timed_run(pipelined, sample_clocks, obs_dtype=torch.float64):
+    def timed_run(pipelined, sample_clocks, obs_dtype=torch.float64, background=BACKGROUND_DYN_BLOCKS, force_eager=False):
         """W warm-up + K timed steps of one mode; returns (env, ms_total max over ranks, launches, clocks, how).
 
         The K timed steps are enqueued as ONE CUDA graph when K <= 512 (captured after the eager warm-up, replayed once
@@ -323,7 +323,7 @@ def run_gpu_arm(args):
         env = BatchedCookingEnv(N, LEVEL, META, A, MAX_STEPS, BOOK[1:3], end_condition_all_dishes=True, action_scheme="scheme3",
                                 device=str(dev), recipe_pool=BOOK, layout_pool_size="auto", layout_seed=0,
                                 auto_reset=True, seed=2026, env_offset=rank * N, pipelined=pipelined, obs_dtype=obs_dtype,
-                                background_dynamics=BACKGROUND_DYN_BLOCKS if pipelined else 0)
+                                background_dynamics=background if pipelined else 0)
         env.reset(recipe_ids=recipe_ids)
         for s in range(args.warmup):
             env.step(actions[s % ring])
@@ -333,7 +333,7 @@ def run_gpu_arm(args):
         graph, how = None, "eager launches"
         # steps per graph: K itself up to 512, else the largest divisor of K that is at most 256 (K = 2000 -> 10 replays of 200)
         G = K if K <= 512 else max((g for g in range(1, 257) if K % g == 0), default=1)
-        if not args.no_graph and G >= 10 and (not pipelined or G % 2 == 0):
+        if not args.no_graph and not force_eager and G >= 10 and (not pipelined or G % 2 == 0):
             try:
                 if pipelined:   # no event of the eager warm-up may be waited on inside the capture
                     _native.check(env.lib.cz_pipeline_reset(env._handle, env.lib.cz_pipeline_current(env._handle)))
@@ -401,6 +401,18 @@ def run_gpu_arm(args):
     env_s.close()
     del env_s
     torch.cuda.empty_cache()
+    # the pipelined step with a capped background dynamics grid needs eager launches with the whole-row writer (inside a graph
+    # the capped grid loses, profiles/r02_notes.md §17): reported as a second figure of the pipelined block
+    try:
+        env_b, ms_bg, _, _, how_bg = timed_run(True, False, background=3, force_eager=True)
+        env_b.wait()
+        env_b.close()
+        del env_b
+        torch.cuda.empty_cache()
+        bg_block = {"value": world * N * args.steps / (ms_bg / 1e3), "ms_per_step": ms_bg / args.steps, "timed_region": how_bg,
+                    "how": "cz_pipeline_config(2 state matrices, 3 dynamics blocks per SM), eager launches"}
+    except Exception as ex:
+        bg_block = {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
     env, ms_total_max, launches, clocks, how_timed = timed_run(head_pipe, True)
     lib = env.lib
     ms_per_step = ms_total_max / args.steps
@@ -817,6 +829,10 @@ def run_gpu_arm(args):
                     "frac": N * bytes_per_env_step / (ms_other / args.steps / 1e3) / 1e9 / peak,
                     "gpu_launches": int(launches_other), "timed_region": how_other,
                     "note": "the other step mode, same workload, same number of steps"},
+                "pipelined_background_dynamics": dict(bg_block, frac=(N * bytes_per_env_step / (bg_block["ms_per_step"] / 1e3) / 1e9 / peak
+                                                                      if "ms_per_step" in bg_block else None),
+                                                      note="may exceed 1: the roofline peak is a read+write copy bandwidth, the step is "
+                                                           "a write stream"),
                 "stats": {"episodes_started": float(stats[0]), "recipes_done_now": float(stats[1]),
                           "last_step_return": float(stats[2])}}
         emit(line)

@@ -7,6 +7,7 @@ step/reset semantics, with every per-environment quantity becoming a leading bat
 This file is thin host code: tensors are torch-owned device memory, the work happens in
 libcz_b200.so (include/cz_b200.h) on torch's current CUDA stream.
 """
+import os
 import ctypes as C
 
 import numpy as np
@@ -14,6 +15,9 @@ import torch
 
 from . import _native
 from .tables import compile_tables, NUM_MISC, ROW_SBITS, ROW_TINFO, ROW_MARKS, ROW_VARIANT
+
+
+_ALWAYS_GUARD = os.environ.get("CZ_PY_DEVICE_GUARD") == "1"   # A/B: always enter torch.cuda.device(...) around library calls
 
 
 class _LazyInfo:
@@ -95,8 +99,23 @@ class BatchedCookingEnv:
         self.error_flags = torch.zeros((N,), dtype=torch.int32, device=dev)
         self._actions = torch.zeros((N, A), dtype=torch.uint8, device=dev)
         self._info = _LazyInfo(self)
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._shape_actions = (N, A)
 
     # ------------------------------------------------------------------ helpers
+    def _call(self, fn, *args):
+        """one library call on this environment's device.  `with torch.cuda.device(...)` costs 20-30 us of host time per call,
+        more than the two kernel launches of a step; when torch's current device already is ours (the usual case) the
+        call goes straight through."""
+        idx = self._dev_index
+        if not _ALWAYS_GUARD and torch.cuda.current_device() == idx:
+            rc = fn(*args)
+        else:
+            with torch.cuda.device(idx):
+                rc = fn(*args)
+        if rc:
+            _native.check(rc)
+
     def _stream(self):
         if self.stream is not None:
             return C.c_void_p(self.stream.cuda_stream)
@@ -168,7 +187,7 @@ class BatchedCookingEnv:
         """step(actions[N, A]) -> (obs f64[N,A,L], reward f64[N,A], terminated u8[N,A], truncated u8[N,A], info)
         (cooking_env.py:243-288).  Outputs are views of buffers that the next step overwrites."""
         a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
-        if a.shape != (self.num_envs, self.num_agents):
+        if a.shape != self._shape_actions:
             raise ValueError("actions must have shape [num_envs, num_agents]")
         if a.dtype != torch.uint8 or a.device != self.device or not a.is_contiguous():
             # staging copy on the caller's stream: in pipelined mode that stream trails the previous step's dynamics
@@ -177,11 +196,9 @@ class BatchedCookingEnv:
             a = self._actions
         if self.pipelined:
             return self._step_pipelined(a)
-        with torch.cuda.device(self.device):
-            _native.check(self.lib.cz_step(self._handle, self.state.data_ptr(), a.data_ptr(), self.obs.data_ptr(),
-                                           self.reward.data_ptr(), self.terminated.data_ptr(),
-                                           self.truncated.data_ptr(), self.error_flags.data_ptr(), self.num_envs, 1,
-                                           self._flags, self.seed, self.env_offset, 0, self._stream()))
+        self._call(self.lib.cz_step, self._handle, self.state.data_ptr(), a.data_ptr(), self.obs.data_ptr(),
+                   self.reward.data_ptr(), self.terminated.data_ptr(), self.truncated.data_ptr(),
+                   self.error_flags.data_ptr(), self.num_envs, 1, self._flags, self.seed, self.env_offset, 0, self._stream())
         return self.obs, self.reward, self.terminated, self.truncated, self._info
 
     def step_k(self, k_steps, actions=None, action_step=0, keep_all=False):
@@ -221,11 +238,9 @@ class BatchedCookingEnv:
         return obs, rew, term, trunc, self._info
 
     def _step_pipelined(self, a):
-        with torch.cuda.device(self.device):
-            _native.check(self.lib.cz_step_pipelined(
-                self._handle, self._state2.data_ptr(), a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
-                self.terminated.data_ptr(), self.truncated.data_ptr(), self.error_flags.data_ptr(), self.num_envs,
-                self._flags, self.seed, self.env_offset, self._stream()))
+        self._call(self.lib.cz_step_pipelined, self._handle, self._state2.data_ptr(), a.data_ptr(), self.obs.data_ptr(),
+                   self.reward.data_ptr(), self.terminated.data_ptr(), self.truncated.data_ptr(), self.error_flags.data_ptr(),
+                   self.num_envs, self._flags, self.seed, self.env_offset, self._stream())
         self.state = self._state2[self.lib.cz_pipeline_current(self._handle)]
         return self.obs, self.reward, self.terminated, self.truncated, self._info
 
