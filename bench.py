@@ -404,6 +404,8 @@ def run_gpu_arm(args):
     # the pipelined step with a capped background dynamics grid needs eager launches with the whole-row writer (inside a graph
     # the capped grid loses, profiles/r02_notes.md §17): reported as a second figure of the pipelined block
     try:
+        if args.no_bg:
+            raise RuntimeError("skipped (--no-bg)")
         env_b, ms_bg, _, _, how_bg = timed_run(True, False, background=3, force_eager=True)
         env_b.wait()
         env_b.close()
@@ -863,6 +865,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true")
     ap.add_argument("--cfg5-envs", type=int, default=262144, help="environments of the mixed-agent-count population (cfg5 block)")
+    ap.add_argument("--no-bg", action="store_true", help="skip the eager background-dynamics figure of the pipelined block")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph of the K steps")
     ap.add_argument("--mode", default="sync", choices=["pipelined", "sync"],
                     help="sync (default, the headline): the in-place step (dynamics kernel, then the whole-row TMA writer, caller's "
