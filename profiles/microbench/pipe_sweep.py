@@ -37,7 +37,7 @@ for buffers in ([2, 3, 4] if len(sys.argv) < 2 else [2]):
         K = 48 if buffers == 3 else 50          # a multiple of the ring size: the graph ends on the buffer it started on
         K = 48 if buffers in (3, 4) else 50
         _native.check(env.lib.cz_pipeline_reset(env._handle, env.lib.cz_pipeline_current(env._handle)))
-        g = torch.cuda.CUDAGraph()
+        g = torch.cuda.CUDAGraph(keep_graph=True)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -54,7 +54,27 @@ for buffers in ([2, 3, 4] if len(sys.argv) < 2 else [2]):
         e1.record()
         torch.cuda.synchronize()
         graph = e0.elapsed_time(e1) / (4 * K) * 1e3
+        # the same graph instantiated with cudaGraphInstantiateFlagUseNodePriority: the kernel nodes keep the priority of the
+        # stream they were captured from (torch instantiates without the flag: every node then runs at the launch stream's)
+        prio = float("nan")
+        try:
+            from cuda.bindings import runtime as rt
+            err, gexec = rt.cudaGraphInstantiateWithFlags(g.raw_cuda_graph(), rt.cudaGraphInstantiateFlags.cudaGraphInstantiateFlagUseNodePriority)
+            assert err == rt.cudaError_t.cudaSuccess, err
+            st = torch.cuda.current_stream().cuda_stream
+            rt.cudaGraphLaunch(gexec, st)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(4):
+                rt.cudaGraphLaunch(gexec, st)
+            e1.record()
+            torch.cuda.synchronize()
+            prio = e0.elapsed_time(e1) / (4 * K) * 1e3
+            rt.cudaGraphExecDestroy(gexec)
+        except Exception as ex:
+            print("node-priority instantiate failed:", repr(ex)[:200])
         b = 4630 * N
         print(f"buffers={buffers} dyn_blocks/SM={blocks}: eager {eager:.2f} us/step ({b / eager / 1e3 / 6550.1:.3f})   "
-              f"graph {graph:.2f} us/step ({b / graph / 1e3 / 6550.1:.3f})", flush=True)
+              f"graph {graph:.2f} us/step ({b / graph / 1e3 / 6550.1:.3f})   graph with node priorities {prio:.2f} us/step "
+              f"({b / prio / 1e3 / 6550.1:.3f})", flush=True)
         env.close()
