@@ -302,3 +302,38 @@ def test_single_agent_large_batch_every_environment_against_the_compiled_oracle(
     env.obs.fill_(float("nan"))
     assert torch.equal(env.observe().view(torch.int64), last.view(torch.int64))
     assert int(env.error_flags.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("name,level,A,n", [
+    ("open4_a3_two_pairs_per_lane", "tests/golden/levels/open4.json", 3, 5003),
+    ("open4_a4_two_pairs_per_lane", "tests/golden/levels/open4.json", 4, 5003),
+    ("tiny4_a3", "tests/golden/levels/tiny4.json", 3, 24577),
+    ("tiny4_a4", "tests/golden/levels/tiny4.json", 4, 24577),
+    ("open4_a2", "tests/golden/levels/open4.json", 2, 24577),
+])
+def test_whole_row_writer_instantiations_against_the_compiled_oracle(name, level, A, n):
+    """every instantiation of the whole-row TMA writer (2-4 agents, one or two (observer, slot) pairs per lane) on a batch
+    large enough for the two-launch in-place step, ragged last block, every environment compared with oracle/cz_oracle.c"""
+    import os
+    from cooking_zoo_b200 import BatchedCookingEnv
+    from oracle.cz_oracle_c import CBatch
+    from tests.replay import ROOT
+    recipes = ["TomatoSalad", "no_recipe", "TomatoLettuceSalad", "CarrotBanana"][:A]
+    lv, mt = os.path.join(ROOT, level), os.path.join(ROOT, "tests/golden/levels/meta4.json")
+    env = BatchedCookingEnv(n, lv, mt, A, 10 ** 5, recipes, end_condition_all_dishes=True, action_scheme="scheme3",
+                            layout_pool_size=32, layout_seed=2, seed=41)
+    lids = env.default_layout_ids().cpu().numpy()
+    obs = env.reset(layout_ids=lids).cpu().numpy()
+    cpu = CBatch([env.tables.layouts[l] for l in lids], [recipes] * n, 10 ** 5, end_condition_all_dishes=True, action_scheme="scheme3")
+    assert np.array_equal(bits(cpu.observe()), bits(obs))
+    g = torch.Generator(device="cpu").manual_seed(79)
+    for t in range(30):
+        act = torch.randint(0, 5, (n, A), generator=g, dtype=torch.uint8)
+        l0 = env.lib.cz_launch_count()
+        o, r, te, tu, _ = env.step(act.cuda())
+        assert env.lib.cz_launch_count() - l0 == 2, name          # dynamics kernel + row writer
+        co, cr, cte, ctu = cpu.step(act.numpy())
+        assert np.array_equal(bits(cr), bits(r.cpu().numpy())), (name, t)
+        assert np.array_equal(cte, te.cpu().numpy()) and np.array_equal(ctu, tu.cpu().numpy()), (name, t)
+        assert np.array_equal(bits(co), bits(o.cpu().numpy())), (name, t)
+    assert int(env.error_flags.abs().sum()) == 0
